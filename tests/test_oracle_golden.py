@@ -1,0 +1,128 @@
+"""CPU: the oracle port against the committed golden fixtures (generated from the unmodified reference by
+tests/golden/make_golden.py).  Everything is bit-exact — the port restates the reference's arithmetic type by type."""
+import numpy as np
+import pytest
+
+from fmrx import synth
+from oracle import Chain, Port, RdsDecoder
+from oracle.port import format_block
+from util import F, LONG_STRIDE, PLL0, RDS_PHASE, assert_bits, sha
+
+
+@pytest.fixture(scope="module")
+def port():
+    return Port()
+
+
+def test_designs(golden, port):
+    g = golden["functions"]
+    assert_bits(port.lpf(2.4e6, 1e5, 151), g["lpf_rf0"], "rf lpf mode 0")
+    assert_bits(port.lpf(2.5e6, 1e5, 151), g["lpf_rf1"], "rf lpf mode 1")
+    assert_bits(port.lpf(240000, 16000, 151), g["lpf_mono0"], "mono lpf")
+    assert_bits(port.lpf(6e6, 16000, 3624), g["lpf_mono1"], "mode-1 lpf")
+    assert np.isnan(g["lpf_mono1"][1812]) and np.isnan(g["lpf_mono1"]).sum() == 1  # Q5
+    assert_bits(port.lpf(240000, 3000, 151), g["lpf_3k"], "3k lpf")
+    assert_bits(port.lpf(float(F(240000) * F(19)), 28500, 2869), g["lpf_anti"], "anti-image lpf")
+    assert_bits(port.lpf(240000 * 147, 16000, 151 * 147), g["lpf_441"], "44.1k lpf")
+    assert_bits(port.bpf(18.5e3, 19.5e3, 240000, 151), g["bpf_pilot0"], "pilot bpf")
+    assert_bits(port.bpf(22e3, 54e3, 240000, 151), g["bpf_stereo0"], "stereo bpf")
+    assert_bits(port.bpf(18.5e3, 19.5e3, 6e6, 151), g["bpf_pilot1"], "pilot bpf mode 1")
+    assert_bits(port.bpf(22e3, 54e3, 6e6, 151), g["bpf_stereo1"], "stereo bpf mode 1")
+    assert_bits(port.bpf(54000, 60000, 240000, 151), g["bpf_rds"], "rds bpf")
+    assert_bits(port.bpf(113500, 114500, 240000, 151), g["bpf_sq"], "squared bpf")
+    assert_bits(port.rrc(57000, 151), g["rrc"], "rrc")
+
+
+def test_unpack(golden, port):
+    g = golden["functions"]
+    assert_bits(port.unpack(g["unpack_in"]), g["unpack_out"], "unpack")
+    short = np.zeros(256, np.uint8)  # unread bytes stay 0 -> -1.0 (Q9)
+    short[:100] = g["unpack_in"][:100]
+    assert_bits(port.unpack(short), g["unpack_short_out"], "short read")
+
+
+def test_fir_family(golden, port):
+    g = golden["functions"]
+    x, xq = g["fir_x"], g["fir_xq"]
+    for decim in (1, 5, 10):
+        zi = np.zeros(150, F)
+        for b in range(x.shape[0]):
+            assert_bits(port.fir_decim(x[b], g["lpf_mono0"], zi, decim), g[f"fir_d{decim}"][b], f"fir d={decim} block {b}")
+    zi, zq = np.zeros(150, F), np.zeros(150, F)
+    for b in range(x.shape[0]):
+        yi, yq = port.fir_decim_iq(x[b], xq[b], g["lpf_rf0"], zi, zq, 10)
+        assert_bits(yi, g["fir_iq_i"][b], "iq.i"); assert_bits(yq, g["fir_iq_q"][b], "iq.q")
+        assert_bits(port.demod(yi, yq), g["demod"][b], "demod")
+        assert g["demod"][b][0] == 0.0  # Q3
+
+
+def test_resamplers(golden, port):
+    g = golden["functions"]
+    x = g["res_x"]
+    cases = [("res_24_125", "lpf_mono1", 125, 24, False, 0, x), ("res_19_80", "lpf_anti", 80, 19, True, 0, x),
+             ("res_147_800", "lpf_441", 800, 147, False, 0, g["res_x441"]), ("res_24_5", "lpf_mono1", 5, 24, False, 2949, x)]
+    for name, hn, d, u, gain, lim, xin in cases:
+        zi = np.zeros(g[hn].size - 1, F)
+        for b in range(xin.shape[0]):
+            assert_bits(port.resample(xin[b], g[hn], zi, d, u, gain, lim), g[name][b], f"{name} block {b}")
+    assert g["res_147_800"].shape[1] == 4410
+    assert np.isnan(g["res_24_125"][0][12::24]).all()  # Q5: every 24th output is NaN
+
+
+def test_plls(golden, port):
+    g = golden["functions"]
+    st = np.array(PLL0, F)
+    for b in range(g["pll_x"].shape[0]):
+        assert_bits(port.pll(g["pll_x"][b], 19e3, 240e3, 2.0, 0.0, 0.01, st), g["pll_nco"][b], f"pll block {b}")
+    assert_bits(st, g["pll_state"], "pll state")
+    st, zi, zl = np.array(PLL0, F), np.zeros(150, F), np.zeros(150, F)
+    for b in range(g["pllc_x"].shape[0]):
+        y, nco = port.pll_combine(g["pllc_x"][b], g["bpf_sq"], zi, 114000, 240000, 0.5, RDS_PHASE, 0.001, st)
+        assert_bits(y, g["pllc_y"][b], "pllCombine y"); assert_bits(nco, g["pllc_nco"][b], "pllCombine nco")
+        assert_bits(port.fir_mixer(nco, g["pllc_x"][b], g["lpf_3k"], zl), g["mixer_y"][b], "mixer")
+    assert_bits(st, g["pllc_state"], "pllCombine state")
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_chain(golden, mode):
+    g = golden[f"chain_mode{mode}"]
+    nblk = int(g["nblk"])
+    raw = synth.synth_iq(nblk, mode, seed=int(g["seed"]))
+    assert sha(raw) == str(g["input_sha256"]), "synthetic input drifted from the one the fixtures were made with"
+    for profile, name in ((0, "binary"), (1, "intent")):
+        ch = Chain(mode, profile)
+        audio, text = [], ""
+        for b in range(nblk):
+            audio.append(ch.block(raw[b * 307200:(b + 1) * 307200]))
+            for t in ("mono", "stereo", "audio_f") + (("rds_rrc",) if mode == 0 else ()):
+                assert_bits(ch.tap(t), g[f"{name}_{t}_{b}"], f"{name} {t} block {b}")
+            for t in ("demod", "pilot", "nco", "stereo_bpf", "rds_bpf", "rds_sq", "rds_nco", "rds_lpf", "rds_res"):
+                key = f"{name}_{t}_{b}"
+                if key in g.files:
+                    v = ch.tap(t)
+                    assert_bits(v[::LONG_STRIDE] if v.size >= 15360 else v, g[key], key)
+            if mode == 0:
+                text += format_block(b, ch.rds_offset, ch.rds()[1])
+        assert_bits(np.concatenate(audio), g[f"{name}_audio"], f"{name} audio")
+        if profile == 0:
+            assert_bits(np.concatenate(audio), g["binary_audio"], "audio vs fm_radio stdout")
+        if mode == 0:
+            assert text == str(g["frame_text"]) == str(g["binary_frame_text"])
+
+
+def test_decoder_standalone(golden):
+    g = golden["chain_mode0"]
+    dec, text = RdsDecoder(), ""
+    for b in range(int(g["nblk"])):
+        _, ev = dec.block_decode(g[f"intent_rds_rrc_{b}"])
+        text += format_block(b, dec.initial_offset, ev)
+    assert text == str(g["frame_text"])
+    assert "Re-Sync" in text and "Syndrome A at position 314" in text
+
+
+def test_binary_profile_stereo_dead_after_block0(golden):
+    """Q7: from block 1 on the shipped binary emits L == R."""
+    a = golden["chain_mode0"]["binary_audio"].reshape(-1, 3072, 2)
+    assert (a[1:, :, 0] == a[1:, :, 1]).all() and (a[0, :, 0] != a[0, :, 1]).any()
+    a1 = golden["chain_mode1"]["binary_audio"].reshape(-1, 2949, 2)
+    assert (a1[:, 12::24, :] == 0).all()  # Q5
