@@ -1,0 +1,189 @@
+/* fmrx — B200-native FM broadcast receive chain.  C-ABI of libfmrx.so.
+ *
+ * The reference (m1nty/Real-Time-Software-Defined-Radio) has no FFI: its only interfaces are the `fm_radio` process
+ * contract and the C++ free functions of src/filter.h, src/helper.h, src/rf_module.h and src/iofunc.h.  Every entry
+ * point below names the reference function (file:line under /root/reference) whose arithmetic it reproduces on the
+ * GPU; include/fmrx_dropin.hpp re-exposes them under the reference's own C++ names and signatures.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all pointers are HOST pointers unless the name says `_device`;
+ *  - every call returns FMRX_OK or a negative fmrx_status; nothing ever calls exit(); there is NO CPU fallback — with
+ *    no usable CUDA device every compute entry returns FMRX_ERR_CUDA (fmrx_last_error() has the driver's message);
+ *  - batched entries process `n_streams` independent streams x `n_blocks` consecutive blocks per stream in one
+ *    launch; arrays are stream-major ([stream][block][sample]); per-stream filter state (`zi`, PLL state) is carried
+ *    from block to block inside the call and written back at the end, exactly as if the reference function had been
+ *    called once per block (the state is saved one sample late, and that is reproduced);
+ *  - `exact != 0` selects the reference's rounding: separate fp32 multiply and add per tap, taps in ascending order
+ *    (results are bit-identical to the reference built with g++ -O3 on x86-64); `exact == 0` uses fused multiply-add
+ *    (<= 1e-6 relative RMS from the reference).
+ */
+#ifndef FMRX_H
+#define FMRX_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FMRX_VERSION 100
+#define FMRX_BLOCK_BYTES 307200 /* src/fm_radio.cpp:23 */
+#define FMRX_IF_PER_BLOCK 15360  /* 307200 / 2 / 10 */
+#define FMRX_RDS_PER_BLOCK 3648  /* floor(15361*19/80), src/filter.cpp:304 */
+#define FMRX_MAX_TAPS 151        /* register-tiled FIR kernels are specialised for the reference's 151 taps */
+#define FMRX_MAX_EVENTS 96       /* per stream per block */
+#define FMRX_MAX_BITS 80         /* per stream per block */
+
+typedef enum {
+    FMRX_OK = 0,
+    FMRX_ERR_ARG = -1,    /* bad argument (null pointer, unsupported size) */
+    FMRX_ERR_CUDA = -2,   /* CUDA runtime / driver error, or no device */
+    FMRX_ERR_ALLOC = -3,  /* device or pinned-host allocation failed */
+    FMRX_ERR_STATE = -4   /* handle used in the wrong state */
+} fmrx_status;
+
+const char *fmrx_last_error(void);
+int fmrx_version(void);
+int fmrx_device_count(void);
+
+/* ---- host-side filter design (bit-identical taps) ----------------------------------------------------------- */
+int fmrx_design_lpf(float Fs, float Fc, unsigned short ntaps, float *h); /* impulseResponseLPF, src/filter.cpp:19-38 */
+int fmrx_design_bpf(float Fb, float Fe, float Fs, int ntaps, float *h);  /* impulseResponseBPF, src/filter.cpp:41-60 */
+int fmrx_design_rrc(float Fs, int ntaps, float *h);                      /* impulseResponseRRC, src/filter.cpp:63-93 */
+
+/* ---- function-level operators (GPU; host buffers) ------------------------------------------------------------ */
+/* readStdInBlock's conversion, src/iofunc.cpp:61-69: out[k] = (raw[k]-128)/128 */
+int fmrx_unpack_iq(const uint8_t *raw, size_t n, float *out);
+/* convolveWithDecim / convolveWithDecimPointer, src/filter.cpp:126-185.  x:[S][B][n] y:[S][B][n/decim] zi:[S][nzi];
+ * ntaps must be 151, decim in {1,5,10}; nzi >= 150 (the last 150 entries are the live state, src/fm_radio.cpp:189-193) */
+int fmrx_fir_decim(float *y, const float *x, int n_streams, int n_blocks, int n, const float *h, int ntaps, float *zi,
+                   int nzi, int decim, int exact);
+/* convolveWithDecimIQ, src/filter.cpp:187-219 */
+int fmrx_fir_decim_iq(float *yi, float *yq, const float *xi, const float *xq, int n_streams, int n_blocks, int n,
+                      const float *h, int ntaps, float *zii, float *ziq, int decim, int exact);
+/* convolveWithDecimMode1 / ...Pointer / ...RDS, src/filter.cpp:222-339.  y:[S][B][ny] with ny = ny_limit>0 ?
+ * min(ny_limit, n*up/decim) : n*up/decim; gain_up multiplies by `up` (:333).  Any ntaps. */
+int fmrx_resample(float *y, int ny_limit, const float *x, int n_streams, int n_blocks, int n, const float *h, int ntaps,
+                  float *zi, int nzi, int decim, int up, int gain_up, int exact);
+/* convolveWithDecimAndMixer at its call site src/fm_radio.cpp:404 (src/filter.cpp:373-401): nco:[S][B][n] (element k
+ * pairs with sig element k), sig:[S][B][n], y:[S][B][n]; half-weight history (Q8) */
+int fmrx_fir_mixer(float *y, const float *nco, const float *sig, int n_streams, int n_blocks, int n, const float *h,
+                   int ntaps, float *zi);
+/* fmDemodArctan, src/rf_module.cpp:13-34 (previous sample reset at every block start, Q3) */
+int fmrx_demod(const float *I, const float *Q, int n_streams, int n_blocks, int n, float *out);
+/* fmPLL, src/helper.cpp:13-57.  state:[S][6] = {integrator, phaseEst, feedbackI, feedbackQ, trigOffset, ncoLast} */
+int fmrx_pll(float *nco, const float *x, int n_streams, int n_blocks, int n, float freq, float Fs, float scale,
+             float phase_adj, float bw, float *state);
+/* pllCombine, src/helper.cpp:108-173: y = BPF(x^2) (zi holds squares), nco as fmrx_pll on y.  The reference's
+ * untrimmed (n+1)-th NCO element is returned in state[5] (ncoLast). */
+int fmrx_pll_combine(float *y, float *nco, const float *x, int n_streams, int n_blocks, int n, const float *h, int ntaps,
+                     float *zi, float freq, float Fs, float scale, float phase_adj, float bw, float *state);
+/* rf_thread's per-block work fused, src/fm_radio.cpp:66-84: u8 IQ -> unpack -> deinterleave -> 151-tap LPF, /decim on
+ * I and Q -> discriminator.  raw:[S][B][2*n] bytes, demod:[S][B][n/decim]; optional yi,yq (may be NULL) receive the
+ * filtered I/Q.  Always reference-exact. */
+int fmrx_frontend(float *demod, float *yi, float *yq, const uint8_t *raw, int n_streams, int n_blocks, int n,
+                  const float *h, int ntaps, float *zii, float *ziq, int decim);
+
+/* ---- RDS clock/data recovery + frame sync: frame_thread, src/fm_radio.cpp:444-729 --------------------------- */
+enum { FMRX_EV_GOOD = 0, FMRX_EV_FALSE = 1, FMRX_EV_RESYNC = 2 };
+typedef struct {
+    int32_t block;     /* per-stream block id the event belongs to */
+    int32_t kind;      /* FMRX_EV_* */
+    int32_t letter;    /* 0..3 = offset word A..D; -1 for a resync */
+    uint32_t position; /* the reference's `printposition` */
+} fmrx_rds_event;
+
+/* opaque per-stream decoder state (block counter, sampling phase, Manchester alignment, carried bits, sync counters) */
+#define FMRX_RDS_STATE_WORDS 160
+/* rrc:[S][B][n] (n = 3648 in the chain; n/24 <= 160).  bits:[S][B][FMRX_MAX_BITS] n_bits:[S][B];
+ * events:[S][B][FMRX_MAX_EVENTS] n_events:[S][B]; state:[S][FMRX_RDS_STATE_WORDS] int32, zero-initialised by the
+ * caller before the first block. */
+int fmrx_rds_decode(const float *rrc, int n_streams, int n_blocks, int n, uint8_t *bits, int32_t *n_bits,
+                    fmrx_rds_event *events, int32_t *n_events, int32_t *state);
+/* sampling phase picked in block 0 (`initial_offset`, :503-517) from a decoder state */
+int fmrx_rds_state_offset(const int32_t *state);
+/* renders the exact stderr lines frame_thread prints for one block; returns the length written (excluding NUL) */
+int fmrx_rds_format_block(int block_id, int initial_offset, const fmrx_rds_event *ev, int n_ev, char *buf, int cap);
+
+/* ---- the batched receive chain ------------------------------------------------------------------------------ */
+enum { FMRX_PROFILE_BINARY = 0, FMRX_PROFILE_INTENT = 1 };   /* SURVEY App. A */
+enum { FMRX_PATH_AUDIO = 1, FMRX_PATH_RDS = 2 };
+enum { FMRX_NUMERICS_REFERENCE = 0, FMRX_NUMERICS_FMA = 1 }; /* audio-path FIR rounding, see `exact` above */
+
+typedef struct {
+    int32_t mode;       /* 0: 2.4 Msps, /10, /5, +RDS ; 1: 2.5 Msps, /10, x24 /125, no RDS (src/fm_radio.cpp:36-37,174-180) */
+    int32_t profile;    /* FMRX_PROFILE_* */
+    int32_t n_streams;  /* independent stations */
+    int32_t max_blocks; /* largest n_blocks a process call will be given */
+    int32_t device;     /* CUDA device ordinal */
+    int32_t paths;      /* FMRX_PATH_* mask; 0 = all the mode has */
+    int32_t numerics;   /* FMRX_NUMERICS_* */
+    int32_t reserved;
+} fmrx_config;
+
+typedef struct fmrx_batch fmrx_batch;
+
+/* outputs of one process call; any pointer may be NULL to skip that copy.  Host pointers for fmrx_batch_process,
+ * device pointers for fmrx_batch_process_device. */
+typedef struct {
+    int16_t *audio;          /* [S][B][2*audio_per_block] interleaved L,R (src/fm_radio.cpp:286-302) */
+    float *audio_f;          /* same shape, before quantisation */
+    uint8_t *rds_bits;       /* [S][B][FMRX_MAX_BITS] */
+    int32_t *rds_n_bits;     /* [S][B] */
+    fmrx_rds_event *rds_events; /* [S][B][FMRX_MAX_EVENTS] */
+    int32_t *rds_n_events;   /* [S][B] */
+} fmrx_outputs;
+
+int fmrx_batch_create(const fmrx_config *cfg, fmrx_batch **out);
+void fmrx_batch_destroy(fmrx_batch *);
+int fmrx_batch_audio_per_block(const fmrx_batch *); /* 3072 (mode 0) / 2949 (mode 1) */
+int fmrx_batch_reset(fmrx_batch *);                 /* back to block 0 with the reference's initial state */
+/* host -> host.  iq:[S][n_blocks][307200] bytes.  Copies are staged through pinned rings and overlapped with the
+ * kernels on separate CUDA streams (the replacement for the reference's producer/consumer threads). */
+int fmrx_batch_process(fmrx_batch *, const uint8_t *iq, int n_blocks, const fmrx_outputs *out);
+/* device -> device, asynchronous on the handle's stream; fmrx_batch_sync() waits. */
+int fmrx_batch_process_device(fmrx_batch *, const uint8_t *iq_device, int n_blocks, const fmrx_outputs *out_device);
+int fmrx_batch_sync(fmrx_batch *);
+void *fmrx_batch_cuda_stream(fmrx_batch *);         /* cudaStream_t of the compute stream */
+long long fmrx_batch_launch_count(const fmrx_batch *); /* kernels launched by this handle so far */
+/* per-stream initial_offset of the RDS decoder (host int32[S]) */
+int fmrx_batch_rds_offsets(fmrx_batch *, int32_t *offsets);
+
+/* intermediate signals of the most recent process call, for per-stage parity tests: copies [S][n_blocks][len] floats */
+enum {
+    FMRX_TAP_DEMOD = 0, FMRX_TAP_MONO, FMRX_TAP_PILOT, FMRX_TAP_NCO, FMRX_TAP_STEREO_BPF, FMRX_TAP_STEREO,
+    FMRX_TAP_RDS_BPF, FMRX_TAP_RDS_SQ, FMRX_TAP_RDS_NCO, FMRX_TAP_RDS_LPF, FMRX_TAP_RDS_RES, FMRX_TAP_RDS_RRC,
+    FMRX_TAP_COUNT
+};
+int fmrx_batch_tap_len(const fmrx_batch *, int which); /* samples per block of that signal */
+int fmrx_batch_tap(fmrx_batch *, int which, float *dst);
+
+/* per-stage device timing inside the real chain: while enabled, every stage of every enqueued chain is bracketed by
+ * CUDA events on the stream it runs on; fmrx_batch_stage_times() synchronises and returns the accumulated milliseconds
+ * and bracket counts per stage since profiling was (re-)enabled. */
+enum {
+    FMRX_STAGE_FRONTEND = 0, FMRX_STAGE_MONO, FMRX_STAGE_PILOT_BPF, FMRX_STAGE_STEREO_BPF, FMRX_STAGE_RDS_BPF,
+    FMRX_STAGE_RDS_SQ_BPF, FMRX_STAGE_PLL, FMRX_STAGE_STEREO_LPF, FMRX_STAGE_COMBINE, FMRX_STAGE_RDS_MIX_LPF,
+    FMRX_STAGE_RDS_RESAMPLE, FMRX_STAGE_RDS_RRC, FMRX_STAGE_RDS_DECODE, FMRX_STAGE_COUNT
+};
+int fmrx_batch_profile(fmrx_batch *, int enable);
+int fmrx_batch_stage_times(fmrx_batch *, double *ms /*[FMRX_STAGE_COUNT]*/, long long *count /*[FMRX_STAGE_COUNT] or NULL*/);
+
+/* opaque state blob (all filter histories, PLL states, decoder states, block counter) for checkpoint / resume */
+size_t fmrx_batch_state_bytes(const fmrx_batch *);
+int fmrx_batch_get_state(fmrx_batch *, void *blob);
+int fmrx_batch_set_state(fmrx_batch *, const void *blob);
+
+/* page-locked host memory for the ingest / egress rings (fmrx_batch_process copies asynchronously only from/to it) */
+int fmrx_pinned_alloc(void **ptr, size_t bytes);
+int fmrx_pinned_free(void *ptr);
+
+/* ---- measurement helpers (used by bench.py; not part of the receive path) ---------------------------------- */
+/* runs an FP32 issue-rate microbenchmark on `device` and returns the best-of-`reps` rate in T lane-ops/s:
+ * kind 0 = FFMA, 1 = FMUL+FADD pairs, 2 = packed FFMA2, 3 = packed FMUL2+FADD2 */
+int fmrx_measure_fp32_peak(int device, int kind, int reps, double *tera_ops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FMRX_H */

@@ -1,0 +1,88 @@
+// FP32 issue-rate microbenchmarks: the roofline denominators for the FIR kernels.  The FIR stages are FP32-pipe bound
+// (25-114 flop per input byte, far right of the HBM ridge), and MEASURED_PEAKS.json only carries HBM and
+// bf16-tensor peaks, so the FP32 peak is measured here, on the same device, by the same binary.
+//   kind 0: FFMA            (1 lane-op = 1 fused multiply-add)
+//   kind 1: FMUL + FADD     (the reference-exact tap: two roundings, two lane-ops)
+//   kind 2: FFMA2           (sm_100 packed fp32x2: two FMAs per lane per instruction)
+//   kind 3: FMUL2 + FADD2
+// Reported as tera lane-ops per second.
+#include <cuda_runtime.h>
+
+#include "fmrx_internal.h"
+
+namespace fmrx {
+namespace {
+
+constexpr int ILP = 16;
+constexpr int ITERS = 4096;
+
+template <int KIND>
+__global__ void __launch_bounds__(256) fp32_rate_kernel(float *sink, float a, float b) {
+    float2 acc[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) acc[i] = make_float2(threadIdx.x * 1e-3f + i, blockIdx.x * 1e-3f - i);
+    const float2 a2 = make_float2(a, a), b2 = make_float2(b, b);
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) {
+            if (KIND == 0) { acc[i].x = fmaf(acc[i].x, a, b); acc[i].y = fmaf(acc[i].y, a, b); }
+            if (KIND == 1) { acc[i].x = __fadd_rn(__fmul_rn(acc[i].x, a), b); acc[i].y = __fadd_rn(__fmul_rn(acc[i].y, a), b); }
+            if (KIND == 2) acc[i] = __ffma2_rn(acc[i], a2, b2);
+            if (KIND == 3) acc[i] = __fadd2_rn(__fmul2_rn(acc[i], a2), b2);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) s += acc[i].x + acc[i].y;
+    if (s == 123.456f) sink[0] = s;  // keep the chain alive without a store in practice
+}
+
+template <int KIND>
+int run(int reps, double *tera) {
+    cudaDeviceProp prop;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaError_t e = cudaGetDeviceProperties(&prop, dev);
+    if (e) return (int)e;
+    float *sink = nullptr;
+    e = cudaMalloc(&sink, 4);
+    if (e) return (int)e;
+    const int grid = prop.multiProcessorCount * 8;
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0); cudaEventCreate(&t1);
+    double best = 0.0;
+    for (int r = 0; r < reps + 2; ++r) {
+        cudaEventRecord(t0);
+        fp32_rate_kernel<KIND><<<grid, 256>>>(sink, 0.9999f, 1e-4f);
+        cudaEventRecord(t1);
+        e = cudaEventSynchronize(t1);
+        if (e) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, t0, t1);
+        // lane-ops: kinds 0/2 = 2 FMAs per (i, it) per thread; kinds 1/3 = 2 muls + 2 adds
+        const double ops = (double)grid * 256 * ITERS * ILP * ((KIND == 0 || KIND == 2) ? 2.0 : 4.0);
+        const double rate = ops / (ms * 1e-3) / 1e12;
+        if (r >= 2 && rate > best) best = rate;
+    }
+    launch_counter() += reps + 2;
+    cudaEventDestroy(t0); cudaEventDestroy(t1);
+    cudaFree(sink);
+    if (e) return (int)e;
+    *tera = best;
+    return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+int measure_fp32_peak(int, int kind, int reps, double *tera) {
+    if (reps < 1) reps = 1;
+    switch (kind) {
+        case 0: return run<0>(reps, tera);
+        case 1: return run<1>(reps, tera);
+        case 2: return run<2>(reps, tera);
+        case 3: return run<3>(reps, tera);
+        default: return (int)cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace fmrx

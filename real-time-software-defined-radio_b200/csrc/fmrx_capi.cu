@@ -1,0 +1,716 @@
+// C-ABI of libfmrx.so (include/fmrx.h): error plumbing, the function-level operators (host buffers in/out around the
+// same kernel launchers the chain uses) and the batched receive chain with its CUDA-stream pipeline.
+//
+// The chain reproduces the four thread bodies of /root/reference/src/fm_radio.cpp:
+//   rf_thread :31-147, mono_stero_thread :150-318, rds_thread :321-441, frame_thread :444-729
+// as a fixed sequence of kernel launches per (chunk of streams x blocks).  The reference's producer/consumer threads
+// and bounded queues (:86-138, :212-223, :376-387, :414-423) become: a copy-in stream, two compute streams and a
+// copy-out stream, chained by events, working on chunks of the stream dimension so that H2D of chunk c+1, the kernels of
+// chunk c and D2H of chunk c-1 overlap.  There is no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "fmrx_internal.h"
+
+namespace fmrx {
+
+static thread_local char g_err[512] = "";
+
+int fail(int status, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return status;
+}
+
+long long &launch_counter() {
+    static long long c = 0;
+    return c;
+}
+
+static int cuda_fail(cudaError_t e, const char *what) {
+    return fail(e == cudaErrorMemoryAllocation ? FMRX_ERR_ALLOC : FMRX_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+#define CU(call)                                           \
+    do {                                                   \
+        cudaError_t e_ = (call);                           \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+    } while (0)
+#define LAUNCH(call)                                                         \
+    do {                                                                     \
+        int e_ = (call);                                                     \
+        if (e_ != 0) return cuda_fail(static_cast<cudaError_t>(e_), #call); \
+    } while (0)
+
+// RAII device buffer for the function-level entries
+template <class T>
+struct Dev {
+    T *p = nullptr;
+    size_t n = 0;
+    ~Dev() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t count) { n = count; return cudaMalloc(&p, (count ? count : 1) * sizeof(T)); }
+    cudaError_t up(const T *h, size_t count) { cudaError_t e = alloc(count); return e ? e : cudaMemcpy(p, h, count * sizeof(T), cudaMemcpyHostToDevice); }
+    cudaError_t down(T *h, size_t count) const { return cudaMemcpy(h, p, count * sizeof(T), cudaMemcpyDeviceToHost); }
+};
+
+static int check_taps(const float *h, int ntaps) {
+    if (!h || ntaps != kTaps) return fail(FMRX_ERR_ARG, "this operator is specialised for %d taps (got %d)", kTaps, ntaps);
+    return FMRX_OK;
+}
+
+}  // namespace fmrx
+
+using namespace fmrx;
+
+extern "C" {
+
+const char *fmrx_last_error(void) { return g_err; }
+int fmrx_version(void) { return FMRX_VERSION; }
+int fmrx_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// function-level operators
+// ------------------------------------------------------------------------------------------------------------------
+int fmrx_unpack_iq(const uint8_t *raw, size_t n, float *out) {
+    if (!raw || !out) return fail(FMRX_ERR_ARG, "fmrx_unpack_iq: null pointer");
+    if (n == 0) return FMRX_OK;
+    Dev<uint8_t> d_in; Dev<float> d_out;
+    CU(d_in.up(raw, n)); CU(d_out.alloc(n));
+    LAUNCH(launch_unpack(d_in.p, n, d_out.p, nullptr));
+    CU(d_out.down(out, n));
+    return FMRX_OK;
+}
+
+int fmrx_fir_decim(float *y, const float *x, int n_streams, int n_blocks, int n, const float *h, int ntaps, float *zi, int nzi,
+                   int decim, int exact) {
+    if (!y || !x || !zi || n_streams <= 0 || n_blocks <= 0 || n < kTaps + 1 || nzi < kHist) return fail(FMRX_ERR_ARG, "fmrx_fir_decim: bad argument");
+    if (decim != 1 && decim != 5 && decim != 10) return fail(FMRX_ERR_ARG, "fmrx_fir_decim: decim must be 1, 5 or 10");
+    if (int e = check_taps(h, ntaps)) return e;
+    const size_t nx = (size_t)n_streams * n_blocks * n, ny = (size_t)n_streams * n_blocks * (n / decim);
+    Dev<float> dx, dy, dz;
+    CU(dx.up(x, nx)); CU(dy.alloc(ny)); CU(dz.up(zi, (size_t)n_streams * nzi));
+    FirJob j{};
+    j.x = dx.p; j.y = dy.p; j.zi = dz.p; j.h = h; j.ldx = (long long)n_blocks * n; j.ldy = (long long)n_blocks * (n / decim);
+    j.nzi = nzi; j.n = n; j.n_blocks = n_blocks; j.n_streams = n_streams; j.decim = decim; j.kind = SRC_PLAIN; j.exact = exact;
+    LAUNCH(launch_fir(j, nullptr));
+    CU(dy.down(y, ny)); CU(dz.down(zi, (size_t)n_streams * nzi));
+    return FMRX_OK;
+}
+
+int fmrx_fir_decim_iq(float *yi, float *yq, const float *xi, const float *xq, int n_streams, int n_blocks, int n, const float *h,
+                      int ntaps, float *zii, float *ziq, int decim, int exact) {
+    if (!yi || !yq || !xi || !xq || !zii || !ziq || n_streams <= 0 || n_blocks <= 0 || n < kTaps + 1) return fail(FMRX_ERR_ARG, "fmrx_fir_decim_iq: bad argument");
+    if (decim != 10) return fail(FMRX_ERR_ARG, "fmrx_fir_decim_iq: decim must be 10 (src/fm_radio.cpp:42)");
+    if (int e = check_taps(h, ntaps)) return e;
+    const size_t nx = (size_t)n_streams * n_blocks * n, ny = (size_t)n_streams * n_blocks * (n / decim), nz = (size_t)n_streams * kHist;
+    Dev<float> dxi, dxq, dyi, dyq, dzi, dzq;
+    CU(dxi.up(xi, nx)); CU(dxq.up(xq, nx)); CU(dyi.alloc(ny)); CU(dyq.alloc(ny)); CU(dzi.up(zii, nz)); CU(dzq.up(ziq, nz));
+    FirIqJob j{};
+    j.xi = dxi.p; j.xq = dxq.p; j.yi = dyi.p; j.yq = dyq.p; j.zii = dzi.p; j.ziq = dzq.p; j.h = h;
+    j.ldx = (long long)n_blocks * n; j.ldy = (long long)n_blocks * (n / decim); j.n = n; j.n_blocks = n_blocks; j.n_streams = n_streams;
+    j.decim = decim; j.exact = exact;
+    LAUNCH(launch_fir_iq(j, nullptr));
+    CU(dyi.down(yi, ny)); CU(dyq.down(yq, ny)); CU(dzi.down(zii, nz)); CU(dzq.down(ziq, nz));
+    return FMRX_OK;
+}
+
+int fmrx_resample(float *y, int ny_limit, const float *x, int n_streams, int n_blocks, int n, const float *h, int ntaps, float *zi,
+                  int nzi, int decim, int up, int gain_up, int exact) {
+    if (!y || !x || !h || !zi || n_streams <= 0 || n_blocks <= 0 || n <= 0 || ntaps <= 0 || nzi <= 0 || decim <= 0 || up <= 0)
+        return fail(FMRX_ERR_ARG, "fmrx_resample: bad argument");
+    if (n < nzi + 1) return fail(FMRX_ERR_ARG, "fmrx_resample: block (%d) must be longer than the state (%d): the reference's state update reads x[n-nzi-1]", n, nzi);
+    const long long ny_full = ((long long)n * up) / decim;
+    const int ny = (ny_limit > 0 && ny_limit < ny_full) ? ny_limit : (int)ny_full;
+    const size_t nx = (size_t)n_streams * n_blocks * n, nyt = (size_t)n_streams * n_blocks * ny;
+    Dev<float> dx, dy, dz, dh;
+    CU(dx.up(x, nx)); CU(dy.alloc(nyt)); CU(dz.up(zi, (size_t)n_streams * nzi)); CU(dh.up(h, ntaps));
+    ResampleJob j{};
+    j.x = dx.p; j.y = dy.p; j.zi = dz.p; j.h = dh.p; j.ldx = (long long)n_blocks * n; j.ldy = (long long)n_blocks * ny;
+    j.n = n; j.n_ref = n; j.ny = ny; j.n_blocks = n_blocks; j.n_streams = n_streams; j.ntaps = ntaps; j.nzi = nzi; j.decim = decim; j.up = up;
+    j.gain_up = gain_up; j.exact = exact;
+    LAUNCH(launch_resample(j, nullptr));
+    CU(dy.down(y, nyt)); CU(dz.down(zi, (size_t)n_streams * nzi));
+    return FMRX_OK;
+}
+
+int fmrx_fir_mixer(float *y, const float *nco, const float *sig, int n_streams, int n_blocks, int n, const float *h, int ntaps, float *zi) {
+    if (!y || !nco || !sig || !zi || n_streams <= 0 || n_blocks <= 0 || n < kTaps + 1) return fail(FMRX_ERR_ARG, "fmrx_fir_mixer: bad argument");
+    if (int e = check_taps(h, ntaps)) return e;
+    const size_t nx = (size_t)n_streams * n_blocks * n, nz = (size_t)n_streams * kHist;
+    Dev<float> da, db, dy, dz;
+    CU(da.up(nco, nx)); CU(db.up(sig, nx)); CU(dy.alloc(nx)); CU(dz.up(zi, nz));
+    FirJob j{};
+    j.x = da.p; j.x2 = db.p; j.y = dy.p; j.zi = dz.p; j.h = h; j.ldx = j.ldy = (long long)n_blocks * n;
+    j.nzi = kHist; j.n = n; j.n_blocks = n_blocks; j.n_streams = n_streams; j.decim = 1; j.kind = SRC_MIX_HALF; j.exact = 0;
+    LAUNCH(launch_fir(j, nullptr));
+    CU(dy.down(y, nx)); CU(dz.down(zi, nz));
+    return FMRX_OK;
+}
+
+int fmrx_demod(const float *I, const float *Q, int n_streams, int n_blocks, int n, float *out) {
+    if (!I || !Q || !out || n_streams <= 0 || n_blocks <= 0 || n <= 0) return fail(FMRX_ERR_ARG, "fmrx_demod: bad argument");
+    const size_t nx = (size_t)n_streams * n_blocks * n;
+    Dev<float> di, dq, dout;
+    CU(di.up(I, nx)); CU(dq.up(Q, nx)); CU(dout.alloc(nx));
+    LAUNCH(launch_demod(di.p, dq.p, dout.p, n_streams, n_blocks, n, nullptr));
+    CU(dout.down(out, nx));
+    return FMRX_OK;
+}
+
+int fmrx_pll(float *nco, const float *x, int n_streams, int n_blocks, int n, float freq, float Fs, float scale, float phase_adj,
+             float bw, float *state) {
+    if (!nco || !x || !state || n_streams <= 0 || n_blocks <= 0 || n <= 0) return fail(FMRX_ERR_ARG, "fmrx_pll: bad argument");
+    const size_t nx = (size_t)n_streams * n_blocks * n;
+    Dev<float> dx, dn, ds;
+    CU(dx.up(x, nx)); CU(dn.alloc(nx)); CU(ds.up(state, (size_t)n_streams * 6));
+    PllParams p{freq, Fs, scale, phase_adj, bw};
+    LAUNCH(launch_pll_blocks(dx.p, dn.p, p, ds.p, nullptr, nullptr, p, nullptr, (long long)n_blocks * n, n_streams, n, n_blocks, nullptr));
+    CU(dn.down(nco, nx)); CU(ds.down(state, (size_t)n_streams * 6));
+    return FMRX_OK;
+}
+
+int fmrx_pll_combine(float *y, float *nco, const float *x, int n_streams, int n_blocks, int n, const float *h, int ntaps, float *zi,
+                     float freq, float Fs, float scale, float phase_adj, float bw, float *state) {
+    if (!y || !nco || !x || !zi || !state || n_streams <= 0 || n_blocks <= 0 || n < kTaps + 1) return fail(FMRX_ERR_ARG, "fmrx_pll_combine: bad argument");
+    if (int e = check_taps(h, ntaps)) return e;
+    const size_t nx = (size_t)n_streams * n_blocks * n, nz = (size_t)n_streams * kHist;
+    Dev<float> dx, dy, dn, dz, ds;
+    CU(dx.up(x, nx)); CU(dy.alloc(nx)); CU(dn.alloc(nx)); CU(dz.up(zi, nz)); CU(ds.up(state, (size_t)n_streams * 6));
+    FirJob j{};
+    j.x = dx.p; j.y = dy.p; j.zi = dz.p; j.h = h; j.ldx = j.ldy = (long long)n_blocks * n;
+    j.nzi = kHist; j.n = n; j.n_blocks = n_blocks; j.n_streams = n_streams; j.decim = 1; j.kind = SRC_SQUARE; j.exact = 0;
+    LAUNCH(launch_fir(j, nullptr));
+    PllParams p{freq, Fs, scale, phase_adj, bw};
+    LAUNCH(launch_pll_blocks(dy.p, dn.p, p, ds.p, nullptr, nullptr, p, nullptr, (long long)n_blocks * n, n_streams, n, n_blocks, nullptr));
+    CU(dy.down(y, nx)); CU(dn.down(nco, nx)); CU(dz.down(zi, nz)); CU(ds.down(state, (size_t)n_streams * 6));
+    return FMRX_OK;
+}
+
+int fmrx_frontend(float *demod, float *yi, float *yq, const uint8_t *raw, int n_streams, int n_blocks, int n, const float *h, int ntaps,
+                  float *zii, float *ziq, int decim) {
+    if (!demod || !raw || !zii || !ziq || n_streams <= 0 || n_blocks <= 0 || n < kTaps + 1 || (yi == nullptr) != (yq == nullptr))
+        return fail(FMRX_ERR_ARG, "fmrx_frontend: bad argument");
+    if (decim != 10) return fail(FMRX_ERR_ARG, "fmrx_frontend: decim must be 10 (src/fm_radio.cpp:42)");
+    if (int e = check_taps(h, ntaps)) return e;
+    const size_t nraw = (size_t)n_streams * n_blocks * n * 2, ny = (size_t)n_streams * n_blocks * (n / 10), nz = (size_t)n_streams * kHist;
+    Dev<uint8_t> draw; Dev<float> dd, dyi, dyq, dzi, dzq;
+    CU(draw.up(raw, nraw)); CU(dd.alloc(ny)); CU(dzi.up(zii, nz)); CU(dzq.up(ziq, nz));
+    if (yi) { CU(dyi.alloc(ny)); CU(dyq.alloc(ny)); }
+    FrontendJob j{};
+    j.raw = draw.p; j.demod = dd.p; j.yi = yi ? dyi.p : nullptr; j.yq = yi ? dyq.p : nullptr; j.zii = dzi.p; j.ziq = dzq.p; j.h = h;
+    j.ld_raw = (long long)n_blocks * n * 2; j.ld_out = (long long)n_blocks * (n / 10); j.n = n; j.n_blocks = n_blocks; j.n_streams = n_streams;
+    LAUNCH(launch_frontend(j, nullptr));
+    CU(dd.down(demod, ny)); CU(dzi.down(zii, nz)); CU(dzq.down(ziq, nz));
+    if (yi) { CU(dyi.down(yi, ny)); CU(dyq.down(yq, ny)); }
+    return FMRX_OK;
+}
+
+int fmrx_rds_decode(const float *rrc, int n_streams, int n_blocks, int n, uint8_t *bits, int32_t *n_bits, fmrx_rds_event *events,
+                    int32_t *n_events, int32_t *state) {
+    if (!rrc || !state || n_streams <= 0 || n_blocks <= 0 || n < 24 * 8 || n / 24 / 2 + 1 > FMRX_MAX_BITS) return fail(FMRX_ERR_ARG, "fmrx_rds_decode: bad argument");
+    const size_t nx = (size_t)n_streams * n_blocks * n, nb = (size_t)n_streams * n_blocks;
+    Dev<float> dx; Dev<uint8_t> dbits; Dev<int32_t> dnb, dne, dst; Dev<fmrx_rds_event> dev;
+    CU(dx.up(rrc, nx)); CU(dbits.alloc(nb * FMRX_MAX_BITS)); CU(dnb.alloc(nb)); CU(dne.alloc(nb)); CU(dev.alloc(nb * FMRX_MAX_EVENTS));
+    CU(dst.up(state, (size_t)n_streams * FMRX_RDS_STATE_WORDS));
+    CU(cudaMemset(dbits.p, 0, nb * FMRX_MAX_BITS));
+    LAUNCH(launch_rds_decode(dx.p, (long long)n_blocks * n, n_streams, n_blocks, n, dbits.p, dnb.p, dev.p, dne.p, dst.p, nullptr));
+    if (bits) CU(dbits.down(bits, nb * FMRX_MAX_BITS));
+    if (n_bits) CU(dnb.down(n_bits, nb));
+    if (events) CU(dev.down(events, nb * FMRX_MAX_EVENTS));
+    if (n_events) CU(dne.down(n_events, nb));
+    CU(dst.down(state, (size_t)n_streams * FMRX_RDS_STATE_WORDS));
+    return FMRX_OK;
+}
+
+int fmrx_rds_state_offset(const int32_t *state) { return state ? state[1] : -1; }
+
+int fmrx_rds_format_block(int block_id, int initial_offset, const fmrx_rds_event *ev, int n_ev, char *buf, int cap) {
+    // the literal lines of src/fm_radio.cpp:516, :619-620, :652-701 (including the reference's spelling)
+    int w = 0;
+    auto emit = [&](const char *fmt, auto... a) {
+        int r = snprintf(buf && w < cap ? buf + w : nullptr, buf && w < cap ? (size_t)(cap - w) : 0, fmt, a...);
+        if (r > 0) w += r;
+    };
+    if (block_id == 0) emit("initial offset for clock recovery = %d\n", initial_offset);
+    emit(" \n****************Prcoessing Block: %d****************\n", block_id);
+    for (int i = 0; i < n_ev; ++i) {
+        if (ev[i].kind == FMRX_EV_RESYNC) emit("~~~~~Re-Sync~~~~~\n");
+        else emit("%sSyndrome %c at position %u\n", ev[i].kind == FMRX_EV_FALSE ? "False positive " : "", "ABCD"[ev[i].letter & 3], ev[i].position);
+    }
+    return w;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------------
+// the batched chain
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int NIQ = FMRX_BLOCK_BYTES / 2;  // complex samples per block
+constexpr int NIF = FMRX_IF_PER_BLOCK;
+constexpr int NRDS = FMRX_RDS_PER_BLOCK;
+constexpr double kPi = 3.14159265358979323846;
+constexpr int kMaxChunks = 8;
+
+}  // namespace
+
+struct fmrx_batch {
+    fmrx_config cfg{};
+    int S = 0, NB = 0, n_audio = 0, nzi_a = 0, audio_taps = 0, up = 1, decim_a = 5, mult = 1;
+    bool audio_on = false, rds_on = false, exact = true;
+    long long block_id = 0;  // blocks consumed per stream so far
+    int last_blocks = 0;
+    long long launches = 0;
+    // host taps
+    float h_rf[kTaps], h_pilot[kTaps], h_sbpf[kTaps], h_rbpf[kTaps], h_sq[kTaps], h_lpf3k[kTaps], h_rrc[kTaps];
+    std::vector<float> h_mono, h_stereo, h_anti;
+    float rds_phase = 0.f;
+    // device
+    float *d_h_mono = nullptr, *d_h_stereo = nullptr, *d_h_anti = nullptr;
+    char *d_state = nullptr;  // one blob: every carried state
+    size_t state_bytes = 0;
+    float *zi_i, *zi_q, *zi_mono, *zi_pilot, *zi_sbpf, *zi_stereo, *pll_st, *zi_rbpf, *zi_sq, *zi_lpf, *zi_rrc, *zi_anti, *rds_pll_st;
+    int32_t *dec_st;
+    uint8_t *d_iq = nullptr;
+    float *demod = nullptr, *mono = nullptr, *pilot = nullptr, *nco = nullptr, *sbpf = nullptr, *mixed = nullptr, *stereo = nullptr;
+    float *rbpf = nullptr, *rsq = nullptr, *rnco = nullptr, *rlpf = nullptr, *rres = nullptr, *rrrc = nullptr;
+    int16_t *audio = nullptr;
+    float *audio_f = nullptr;
+    uint8_t *bits = nullptr;
+    int32_t *nbits = nullptr, *nev = nullptr;
+    fmrx_rds_event *ev = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr, s_cmp[2] = {nullptr, nullptr};
+    cudaEvent_t e_in[kMaxChunks]{}, e_done[kMaxChunks]{}, e_out[kMaxChunks]{};
+    std::vector<void *> allocs;
+    // optional per-stage device timing (fmrx_batch_profile): event pairs around every stage of every enqueued chain
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_pool;
+    size_t prof_used = 0;
+    struct Mark { int stage; cudaEvent_t t0, t1; };
+    std::vector<Mark> marks;
+    double stage_ms[FMRX_STAGE_COUNT] = {0};
+    long long stage_launches[FMRX_STAGE_COUNT] = {0};
+
+    ~fmrx_batch() {
+        cudaSetDevice(cfg.device);
+        for (void *p : allocs) cudaFree(p);
+        for (auto e : prof_pool) cudaEventDestroy(e);
+        for (int i = 0; i < kMaxChunks; ++i) { if (e_in[i]) cudaEventDestroy(e_in[i]); if (e_done[i]) cudaEventDestroy(e_done[i]); if (e_out[i]) cudaEventDestroy(e_out[i]); }
+        if (s_in) cudaStreamDestroy(s_in);
+        if (s_out) cudaStreamDestroy(s_out);
+        for (auto s : s_cmp) if (s) cudaStreamDestroy(s);
+    }
+    template <class T>
+    cudaError_t dalloc(T *&p, size_t count) {
+        cudaError_t e = cudaMalloc(&p, (count ? count : 1) * sizeof(T));
+        if (!e) allocs.push_back(p);
+        return e;
+    }
+};
+
+namespace {
+
+int init_state(fmrx_batch *b) {
+    // reference initial conditions: all filter histories 0 (src/fm_radio.cpp:53-55,189-193,360-364), both PLLs
+    // {0,0,1,0,0,1} (:165-171,:343-349), decoder zeroed (:449-484)
+    CU(cudaMemsetAsync(b->d_state, 0, b->state_bytes, b->s_cmp[0]));
+    std::vector<float> pll((size_t)b->S * 6);
+    for (int s = 0; s < b->S; ++s) { float *p = &pll[(size_t)s * 6]; p[0] = 0; p[1] = 0; p[2] = 1; p[3] = 0; p[4] = 0; p[5] = 1; }
+    CU(cudaMemcpyAsync(b->pll_st, pll.data(), pll.size() * 4, cudaMemcpyHostToDevice, b->s_cmp[0]));
+    CU(cudaMemcpyAsync(b->rds_pll_st, pll.data(), pll.size() * 4, cudaMemcpyHostToDevice, b->s_cmp[0]));
+    CU(cudaStreamSynchronize(b->s_cmp[0]));
+    b->block_id = 0;
+    return FMRX_OK;
+}
+
+struct StageScope {
+    fmrx_batch *b; cudaStream_t st; int stage; cudaEvent_t t1 = nullptr;
+    StageScope(fmrx_batch *b_, cudaStream_t st_, int stage_) : b(b_), st(st_), stage(stage_) {
+        if (!b->profiling) return;
+        auto get = [&]() { if (b->prof_used == b->prof_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); b->prof_pool.push_back(e); } return b->prof_pool[b->prof_used++]; };
+        cudaEvent_t t0 = get(); t1 = get();
+        cudaEventRecord(t0, st);
+        b->marks.push_back({stage, t0, t1});
+    }
+    ~StageScope() { if (t1) cudaEventRecord(t1, st); }
+};
+#define STAGE(id) StageScope stage_scope_##id(b, st, id)
+
+// enqueue the whole chain for streams [s0, s0+ns) x nblk blocks on `st`
+int enqueue_chain(fmrx_batch *b, const uint8_t *iq, long long ld_iq, int s0, int ns, int nblk, const fmrx_outputs &o, cudaStream_t st) {
+    const long long before = launch_counter();
+    const long long ldif = (long long)b->NB * NIF, lda = (long long)b->NB * b->n_audio, ldr = (long long)b->NB * NRDS;
+    auto IF = [&](float *p) { return p + (long long)s0 * ldif; };
+    auto AU = [&](float *p) { return p + (long long)s0 * lda; };
+    auto RD = [&](float *p) { return p + (long long)s0 * ldr; };
+    const int ex = b->exact ? 1 : 0;
+    // ---- rf_thread: unpack + deinterleave + LPF/10 + discriminator (src/fm_radio.cpp:66-84)
+    FrontendJob f{};
+    f.raw = iq + (long long)s0 * ld_iq; f.demod = IF(b->demod); f.zii = b->zi_i + (long long)s0 * kHist; f.ziq = b->zi_q + (long long)s0 * kHist; f.h = b->h_rf;
+    f.ld_raw = ld_iq; f.ld_out = ldif; f.n = NIQ; f.n_blocks = nblk; f.n_streams = ns;
+    { STAGE(FMRX_STAGE_FRONTEND); LAUNCH(launch_frontend(f, st)); }
+
+    auto fir = [&](const float *x, const float *x2, float *y, float *zi, int nzi, const float *h, long long ldx, long long ldy, int n, int decim, int kind, int exact, int blocks) {
+        FirJob j{};
+        j.x = x; j.x2 = x2; j.y = y; j.zi = zi; j.h = h; j.ldx = ldx; j.ldy = ldy; j.nzi = nzi; j.n = n; j.n_blocks = blocks; j.n_streams = ns;
+        j.decim = decim; j.kind = kind; j.exact = exact;
+        return launch_fir(j, st);
+    };
+    const bool stereo_live = b->cfg.profile == FMRX_PROFILE_INTENT || b->block_id == 0;  // Q7
+    const int st_blocks = b->cfg.profile == FMRX_PROFILE_INTENT ? nblk : 1;
+
+    // ---- mono_stero_thread, filters (:226-236 / :255-265)
+    if (b->audio_on) {
+        STAGE(FMRX_STAGE_MONO);
+        if (b->cfg.mode == 1) {
+            ResampleJob r{};
+            r.x = IF(b->demod); r.y = AU(b->mono); r.zi = b->zi_mono + (long long)s0 * b->nzi_a; r.h = b->d_h_mono; r.ldx = ldif; r.ldy = lda;
+            r.n = NIF; r.n_ref = NIF; r.ny = b->n_audio; r.n_blocks = nblk; r.n_streams = ns; r.ntaps = b->audio_taps; r.nzi = b->nzi_a;
+            r.decim = b->decim_a; r.up = b->up; r.gain_up = 0; r.exact = ex;
+            LAUNCH(launch_resample(r, st));
+        } else {
+            LAUNCH(fir(IF(b->demod), nullptr, AU(b->mono), b->zi_mono + (long long)s0 * b->nzi_a, b->nzi_a, b->h_mono.data(), ldif, lda, NIF, 5, SRC_PLAIN, ex, nblk));
+        }
+    }
+    if (b->audio_on) {
+        if (stereo_live) {
+            STAGE(FMRX_STAGE_PILOT_BPF);
+            LAUNCH(fir(IF(b->demod), nullptr, IF(b->pilot), b->zi_pilot + (long long)s0 * b->nzi_a, b->nzi_a, b->h_pilot, ldif, ldif, NIF, 1, SRC_PLAIN, 1, st_blocks));
+        }
+        if (stereo_live) {
+            STAGE(FMRX_STAGE_STEREO_BPF);
+            LAUNCH(fir(IF(b->demod), nullptr, IF(b->sbpf), b->zi_sbpf + (long long)s0 * b->nzi_a, b->nzi_a, b->h_sbpf, ldif, ldif, NIF, 1, SRC_PLAIN, ex, st_blocks));
+        }
+    }
+    // ---- rds_thread, filters before the PLL (:395, :400's BPF)
+    if (b->rds_on) {
+        { STAGE(FMRX_STAGE_RDS_BPF); LAUNCH(fir(IF(b->demod), nullptr, IF(b->rbpf), b->zi_rbpf + (long long)s0 * kHist, kHist, b->h_rbpf, ldif, ldif, NIF, 1, SRC_PLAIN, 0, nblk)); }
+        STAGE(FMRX_STAGE_RDS_SQ_BPF);
+        LAUNCH(fir(IF(b->rbpf), nullptr, IF(b->rsq), b->zi_sq + (long long)s0 * kHist, kHist, b->h_sq, ldif, ldif, NIF, 1, SRC_SQUARE, 0, nblk));
+    }
+    // ---- both PLLs, one lane per (stream, loop) (:233/:262 and :400)
+    {
+        const PllParams pa{19e3f, 240e3f, 2.0f, 0.0f, 0.01f};
+        const PllParams pr{114000.0f, 240000.0f, 0.5f, b->rds_phase, 0.001f};
+        const bool a_on = b->audio_on && stereo_live;
+        STAGE(FMRX_STAGE_PLL);
+        if (a_on && b->rds_on && st_blocks == nblk) {
+            LAUNCH(launch_pll_blocks(IF(b->pilot), IF(b->nco), pa, b->pll_st + (long long)s0 * 6, IF(b->rsq), IF(b->rnco), pr, b->rds_pll_st + (long long)s0 * 6, ldif, ns, NIF, nblk, st));
+        } else {
+            if (a_on) LAUNCH(launch_pll_blocks(IF(b->pilot), IF(b->nco), pa, b->pll_st + (long long)s0 * 6, nullptr, nullptr, pa, nullptr, ldif, ns, NIF, st_blocks, st));
+            if (b->rds_on) LAUNCH(launch_pll_blocks(IF(b->rsq), IF(b->rnco), pr, b->rds_pll_st + (long long)s0 * 6, nullptr, nullptr, pr, nullptr, ldif, ns, NIF, nblk, st));
+        }
+    }
+    // ---- stereo mix + LPF, combine, quantise (:240-252 / :269-299)
+    if (b->audio_on) {
+        const float *stereo = nullptr;
+        if (stereo_live) {
+            STAGE(FMRX_STAGE_STEREO_LPF);
+            if (st_blocks < nblk) CU(cudaMemset2DAsync(AU(b->stereo), lda * 4, 0, (size_t)nblk * b->n_audio * 4, ns, st));
+            if (b->cfg.mode == 1) {
+                LAUNCH(launch_multiply(IF(b->sbpf), IF(b->nco), IF(b->mixed), ldif, st_blocks * NIF, ns, st));
+                ResampleJob r{};  // convolveWithDecimMode1(stereo_filt, mixed, stereo_coeff, stereo_initial, 5, 24), :245 (Q14)
+                r.x = IF(b->mixed); r.y = AU(b->stereo); r.zi = b->zi_stereo + (long long)s0 * b->nzi_a; r.h = b->d_h_stereo; r.ldx = ldif; r.ldy = lda;
+                r.n = NIF; r.n_ref = NIF; r.ny = b->n_audio; r.n_blocks = st_blocks; r.n_streams = ns; r.ntaps = b->audio_taps; r.nzi = b->nzi_a;
+                r.decim = 5; r.up = b->up; r.gain_up = 0; r.exact = ex;
+                LAUNCH(launch_resample(r, st));
+            } else {
+                LAUNCH(fir(IF(b->sbpf), IF(b->nco), AU(b->stereo), b->zi_stereo + (long long)s0 * b->nzi_a, b->nzi_a, b->h_stereo.data(), ldif, lda, NIF, 5, SRC_MIX_LATE, ex, st_blocks));
+            }
+            stereo = AU(b->stereo);
+        }
+        STAGE(FMRX_STAGE_COMBINE);
+        CombineJob c{};
+        c.mono = AU(b->mono); c.stereo = stereo; c.audio = b->audio + (long long)s0 * lda * 2; c.audio_f = b->audio_f + (long long)s0 * lda * 2;
+        c.ld = lda; c.n_total = nblk * b->n_audio; c.n_streams = ns; c.mult = b->mult;
+        LAUNCH(launch_combine(c, st));
+    }
+    // ---- rds_thread after the PLL (:404-411) and frame_thread
+    if (b->rds_on) {
+        { STAGE(FMRX_STAGE_RDS_MIX_LPF); LAUNCH(fir(IF(b->rnco), IF(b->rbpf), IF(b->rlpf), b->zi_lpf + (long long)s0 * kHist, kHist, b->h_lpf3k, ldif, ldif, NIF, 1, SRC_MIX_HALF, 0, nblk)); }
+        ResampleJob r{};
+        r.x = IF(b->rlpf); r.y = RD(b->rres); r.zi = b->zi_anti + (long long)s0 * (kTaps * 19 - 1); r.h = b->d_h_anti; r.ldx = ldif; r.ldy = ldr;
+        r.n = NIF; r.n_ref = NIF + 1; r.ny = NRDS; r.n_blocks = nblk; r.n_streams = ns; r.ntaps = kTaps * 19; r.nzi = kTaps * 19 - 1;
+        r.decim = 80; r.up = 19; r.gain_up = 1; r.exact = 0;
+        { STAGE(FMRX_STAGE_RDS_RESAMPLE); LAUNCH(launch_resample(r, st)); }
+        { STAGE(FMRX_STAGE_RDS_RRC); LAUNCH(fir(RD(b->rres), nullptr, RD(b->rrrc), b->zi_rrc + (long long)s0 * kHist, kHist, b->h_rrc, ldr, ldr, NRDS, 1, SRC_PLAIN, 0, nblk)); }
+        STAGE(FMRX_STAGE_RDS_DECODE);
+        LAUNCH(launch_rds_decode(RD(b->rrrc), ldr, ns, nblk, NRDS, b->bits + (long long)s0 * nblk * FMRX_MAX_BITS, b->nbits + (long long)s0 * nblk,
+                                 b->ev + (long long)s0 * nblk * FMRX_MAX_EVENTS, b->nev + (long long)s0 * nblk, b->dec_st + (long long)s0 * FMRX_RDS_STATE_WORDS, st));
+    }
+    (void)o;
+    b->launches += launch_counter() - before;
+    return FMRX_OK;
+}
+
+// copy one chunk's results to the caller (device->device or device->host depending on `kind`)
+int copy_outputs(fmrx_batch *b, int s0, int ns, int nblk, const fmrx_outputs &o, cudaMemcpyKind kind, cudaStream_t st) {
+    const size_t lda = (size_t)b->NB * b->n_audio, row = (size_t)nblk * b->n_audio;
+    if (b->audio_on && o.audio)
+        CU(cudaMemcpy2DAsync(o.audio + (size_t)s0 * row * 2, row * 2 * sizeof(int16_t), b->audio + (size_t)s0 * lda * 2, lda * 2 * sizeof(int16_t), row * 2 * sizeof(int16_t), ns, kind, st));
+    if (b->audio_on && o.audio_f)
+        CU(cudaMemcpy2DAsync(o.audio_f + (size_t)s0 * row * 2, row * 2 * sizeof(float), b->audio_f + (size_t)s0 * lda * 2, lda * 2 * sizeof(float), row * 2 * sizeof(float), ns, kind, st));
+    if (b->rds_on) {
+        const size_t q = (size_t)s0 * nblk, m = (size_t)ns * nblk;
+        if (o.rds_bits) CU(cudaMemcpyAsync(o.rds_bits + q * FMRX_MAX_BITS, b->bits + q * FMRX_MAX_BITS, m * FMRX_MAX_BITS, kind, st));
+        if (o.rds_n_bits) CU(cudaMemcpyAsync(o.rds_n_bits + q, b->nbits + q, m * sizeof(int32_t), kind, st));
+        if (o.rds_events) CU(cudaMemcpyAsync(o.rds_events + q * FMRX_MAX_EVENTS, b->ev + q * FMRX_MAX_EVENTS, m * FMRX_MAX_EVENTS * sizeof(fmrx_rds_event), kind, st));
+        if (o.rds_n_events) CU(cudaMemcpyAsync(o.rds_n_events + q, b->nev + q, m * sizeof(int32_t), kind, st));
+    }
+    return FMRX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fmrx_batch_create(const fmrx_config *cfg, fmrx_batch **out) {
+    if (!cfg || !out) return fail(FMRX_ERR_ARG, "fmrx_batch_create: null pointer");
+    *out = nullptr;
+    if ((cfg->mode != 0 && cfg->mode != 1) || cfg->n_streams <= 0 || cfg->max_blocks <= 0 || cfg->n_streams > 65535 || cfg->max_blocks > 65535)
+        return fail(FMRX_ERR_ARG, "fmrx_batch_create: mode must be 0 or 1, 1 <= n_streams,max_blocks <= 65535");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(FMRX_ERR_CUDA, "no CUDA device: libfmrx has no CPU fallback"); }
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(FMRX_ERR_ARG, "device %d out of range (%d devices)", cfg->device, ndev);
+    CU(cudaSetDevice(cfg->device));
+    fmrx_batch *b = new (std::nothrow) fmrx_batch();
+    if (!b) return fail(FMRX_ERR_ALLOC, "out of host memory");
+    struct Guard { fmrx_batch *p; ~Guard() { delete p; } } guard{b};
+    b->cfg = *cfg;
+    b->S = cfg->n_streams; b->NB = cfg->max_blocks;
+    const int paths = cfg->paths ? cfg->paths : (FMRX_PATH_AUDIO | FMRX_PATH_RDS);
+    b->audio_on = (paths & FMRX_PATH_AUDIO) != 0;
+    b->rds_on = (paths & FMRX_PATH_RDS) != 0 && cfg->mode == 0;  // src/fm_radio.cpp:324,446
+    b->exact = cfg->numerics == FMRX_NUMERICS_REFERENCE;
+    // ---- constants of the thread bodies
+    const float rf_Fs = cfg->mode == 1 ? 2500000.0f : 2400000.0f;  // :36-37
+    float audio_Fs = 240000.0f;                                    // :153
+    b->audio_taps = kTaps; b->up = 1; b->decim_a = 5; b->mult = 1;
+    if (cfg->mode == 1) { audio_Fs = 6000000.0f; b->decim_a = 125; b->up = 24; b->audio_taps = kTaps * 24; b->mult = 24; }  // :174-180,229
+    b->nzi_a = b->audio_taps - 1;                                  // :189-193
+    b->n_audio = (int)(((long long)NIF * b->up) / b->decim_a);
+    b->h_mono.resize(b->audio_taps); b->h_stereo.resize(b->audio_taps); b->h_anti.resize(kTaps * 19);
+    fmrx_design_lpf(rf_Fs, 100000.0f, kTaps, b->h_rf);                                  // :40-42,75
+    fmrx_design_lpf(audio_Fs, 16000.0f, (unsigned short)b->audio_taps, b->h_mono.data());   // :200
+    fmrx_design_bpf(18.5e3f, 19.5e3f, audio_Fs, kTaps, b->h_pilot);                     // :201
+    fmrx_design_bpf(22e3f, 54e3f, audio_Fs, kTaps, b->h_sbpf);                          // :202
+    fmrx_design_lpf(audio_Fs, 16000.0f, (unsigned short)b->audio_taps, b->h_stereo.data()); // :203
+    fmrx_design_bpf(54000.0f, 60000.0f, 240000.0f, kTaps, b->h_rbpf);                   // :366
+    fmrx_design_bpf(113500.0f, 114500.0f, 240000.0f, kTaps, b->h_sq);                   // :367
+    fmrx_design_lpf(240000.0f, 3000.0f, kTaps, b->h_lpf3k);                             // :368
+    fmrx_design_lpf(240000.0f * 19.0f, (float)(57000 / 2), kTaps * 19, b->h_anti.data()); // :369
+    fmrx_design_rrc(57000.0f, kTaps, b->h_rrc);                                         // :370
+    const float phase_adj = (float)(kPi / 3.3 - kPi / 1.5);                             // :342
+    b->rds_phase = (float)((double)phase_adj - kPi / 1.4);                              // :400
+
+    const size_t S = b->S, NB = b->NB;
+    // ---- carried state: one blob
+    struct Seg { void **p; size_t bytes; };
+    std::vector<Seg> segs = {
+        {(void **)&b->zi_i, S * kHist * 4}, {(void **)&b->zi_q, S * kHist * 4},
+        {(void **)&b->zi_mono, S * b->nzi_a * 4}, {(void **)&b->zi_pilot, S * b->nzi_a * 4}, {(void **)&b->zi_sbpf, S * b->nzi_a * 4}, {(void **)&b->zi_stereo, S * b->nzi_a * 4},
+        {(void **)&b->pll_st, S * 6 * 4}, {(void **)&b->zi_rbpf, S * kHist * 4}, {(void **)&b->zi_sq, S * kHist * 4}, {(void **)&b->zi_lpf, S * kHist * 4},
+        {(void **)&b->zi_rrc, S * kHist * 4}, {(void **)&b->zi_anti, S * (kTaps * 19 - 1) * 4}, {(void **)&b->rds_pll_st, S * 6 * 4},
+        {(void **)&b->dec_st, S * FMRX_RDS_STATE_WORDS * 4}};
+    size_t total = 0;
+    for (auto &sg : segs) total += (sg.bytes + 255) & ~(size_t)255;
+    b->state_bytes = total;
+    CU(b->dalloc(b->d_state, total));
+    size_t off = 0;
+    for (auto &sg : segs) { *sg.p = b->d_state + off; off += (sg.bytes + 255) & ~(size_t)255; }
+    // ---- taps of the long (resampler) filters
+    CU(b->dalloc(b->d_h_mono, b->audio_taps)); CU(b->dalloc(b->d_h_stereo, b->audio_taps)); CU(b->dalloc(b->d_h_anti, kTaps * 19));
+    CU(cudaMemcpy(b->d_h_mono, b->h_mono.data(), b->audio_taps * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(b->d_h_stereo, b->h_stereo.data(), b->audio_taps * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(b->d_h_anti, b->h_anti.data(), kTaps * 19 * 4, cudaMemcpyHostToDevice));
+    // ---- signals
+    CU(b->dalloc(b->d_iq, S * NB * FMRX_BLOCK_BYTES));
+    CU(b->dalloc(b->demod, S * NB * NIF));
+    if (b->audio_on) {
+        CU(b->dalloc(b->mono, S * NB * b->n_audio)); CU(b->dalloc(b->pilot, S * NB * NIF)); CU(b->dalloc(b->nco, S * NB * NIF));
+        CU(b->dalloc(b->sbpf, S * NB * NIF)); CU(b->dalloc(b->stereo, S * NB * b->n_audio));
+        if (cfg->mode == 1) CU(b->dalloc(b->mixed, S * NB * NIF));
+        CU(b->dalloc(b->audio, S * NB * b->n_audio * 2)); CU(b->dalloc(b->audio_f, S * NB * b->n_audio * 2));
+    }
+    if (b->rds_on) {
+        CU(b->dalloc(b->rbpf, S * NB * NIF)); CU(b->dalloc(b->rsq, S * NB * NIF)); CU(b->dalloc(b->rnco, S * NB * NIF)); CU(b->dalloc(b->rlpf, S * NB * NIF));
+        CU(b->dalloc(b->rres, S * NB * NRDS)); CU(b->dalloc(b->rrrc, S * NB * NRDS));
+        CU(b->dalloc(b->bits, S * NB * FMRX_MAX_BITS)); CU(b->dalloc(b->nbits, S * NB)); CU(b->dalloc(b->nev, S * NB)); CU(b->dalloc(b->ev, S * NB * FMRX_MAX_EVENTS));
+        CU(cudaMemset(b->bits, 0, S * NB * FMRX_MAX_BITS));
+    }
+    CU(cudaStreamCreateWithFlags(&b->s_in, cudaStreamNonBlocking)); CU(cudaStreamCreateWithFlags(&b->s_out, cudaStreamNonBlocking));
+    for (auto &s : b->s_cmp) CU(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    for (int i = 0; i < kMaxChunks; ++i) {
+        CU(cudaEventCreateWithFlags(&b->e_in[i], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&b->e_done[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&b->e_out[i], cudaEventDisableTiming));
+    }
+    if (int e = init_state(b)) return e;
+    guard.p = nullptr;
+    *out = b;
+    return FMRX_OK;
+}
+
+void fmrx_batch_destroy(fmrx_batch *b) { delete b; }
+int fmrx_batch_audio_per_block(const fmrx_batch *b) { return b ? b->n_audio : 0; }
+long long fmrx_batch_launch_count(const fmrx_batch *b) { return b ? b->launches : 0; }
+void *fmrx_batch_cuda_stream(fmrx_batch *b) { return b ? (void *)b->s_cmp[0] : nullptr; }
+
+int fmrx_batch_reset(fmrx_batch *b) {
+    if (!b) return fail(FMRX_ERR_ARG, "null handle");
+    CU(cudaSetDevice(b->cfg.device));
+    return init_state(b);
+}
+
+int fmrx_batch_sync(fmrx_batch *b) {
+    if (!b) return fail(FMRX_ERR_ARG, "null handle");
+    CU(cudaSetDevice(b->cfg.device));
+    CU(cudaStreamSynchronize(b->s_in)); CU(cudaStreamSynchronize(b->s_cmp[0])); CU(cudaStreamSynchronize(b->s_cmp[1])); CU(cudaStreamSynchronize(b->s_out));
+    return FMRX_OK;
+}
+
+int fmrx_batch_process_device(fmrx_batch *b, const uint8_t *iq_device, int n_blocks, const fmrx_outputs *out_device) {
+    if (!b || !iq_device) return fail(FMRX_ERR_ARG, "fmrx_batch_process_device: null pointer");
+    if (n_blocks <= 0 || n_blocks > b->NB) return fail(FMRX_ERR_ARG, "n_blocks %d outside 1..%d", n_blocks, b->NB);
+    CU(cudaSetDevice(b->cfg.device));
+    fmrx_outputs none{};
+    const fmrx_outputs &o = out_device ? *out_device : none;
+    if (int e = enqueue_chain(b, iq_device, (long long)n_blocks * FMRX_BLOCK_BYTES, 0, b->S, n_blocks, o, b->s_cmp[0])) return e;
+    if (int e = copy_outputs(b, 0, b->S, n_blocks, o, cudaMemcpyDeviceToDevice, b->s_cmp[0])) return e;
+    b->block_id += n_blocks;
+    b->last_blocks = n_blocks;
+    return FMRX_OK;
+}
+
+int fmrx_batch_process(fmrx_batch *b, const uint8_t *iq, int n_blocks, const fmrx_outputs *out) {
+    if (!b || !iq) return fail(FMRX_ERR_ARG, "fmrx_batch_process: null pointer");
+    if (n_blocks <= 0 || n_blocks > b->NB) return fail(FMRX_ERR_ARG, "n_blocks %d outside 1..%d", n_blocks, b->NB);
+    CU(cudaSetDevice(b->cfg.device));
+    fmrx_outputs none{};
+    const fmrx_outputs &o = out ? *out : none;
+    // chunk the stream dimension so copies and kernels overlap; small batches go through in one piece
+    const int chunks = b->S >= 64 ? (b->S >= 512 ? kMaxChunks : 4) : 1;
+    const long long row = (long long)n_blocks * FMRX_BLOCK_BYTES;
+    for (int c = 0; c < chunks; ++c) {
+        const int s0 = (int)((long long)b->S * c / chunks), s1 = (int)((long long)b->S * (c + 1) / chunks), ns = s1 - s0;
+        if (ns <= 0) continue;
+        cudaStream_t cs = b->s_cmp[c & 1];
+        CU(cudaMemcpyAsync(b->d_iq + (size_t)s0 * row, iq + (size_t)s0 * row, (size_t)ns * row, cudaMemcpyHostToDevice, b->s_in));
+        CU(cudaEventRecord(b->e_in[c], b->s_in));
+        CU(cudaStreamWaitEvent(cs, b->e_in[c], 0));
+        if (int e = enqueue_chain(b, b->d_iq, row, s0, ns, n_blocks, o, cs)) return e;
+        CU(cudaEventRecord(b->e_done[c], cs));
+        CU(cudaStreamWaitEvent(b->s_out, b->e_done[c], 0));
+        if (int e = copy_outputs(b, s0, ns, n_blocks, o, cudaMemcpyDeviceToHost, b->s_out)) return e;
+    }
+    CU(cudaStreamSynchronize(b->s_out)); CU(cudaStreamSynchronize(b->s_cmp[0])); CU(cudaStreamSynchronize(b->s_cmp[1]));
+    b->block_id += n_blocks;
+    b->last_blocks = n_blocks;
+    return FMRX_OK;
+}
+
+int fmrx_batch_rds_offsets(fmrx_batch *b, int32_t *offsets) {
+    if (!b || !offsets) return fail(FMRX_ERR_ARG, "null pointer");
+    CU(cudaSetDevice(b->cfg.device));
+    if (int e = fmrx_batch_sync(b)) return e;
+    CU(cudaMemcpy2D(offsets, sizeof(int32_t), b->dec_st + 1, FMRX_RDS_STATE_WORDS * sizeof(int32_t), sizeof(int32_t), b->S, cudaMemcpyDeviceToHost));
+    return FMRX_OK;
+}
+
+int fmrx_batch_tap_len(const fmrx_batch *b, int which) {
+    if (!b) return 0;
+    switch (which) {
+        case FMRX_TAP_MONO: case FMRX_TAP_STEREO: return b->n_audio;
+        case FMRX_TAP_RDS_RES: case FMRX_TAP_RDS_RRC: return NRDS;
+        default: return which >= 0 && which < FMRX_TAP_COUNT ? NIF : 0;
+    }
+}
+
+int fmrx_batch_tap(fmrx_batch *b, int which, float *dst) {
+    if (!b || !dst) return fail(FMRX_ERR_ARG, "null pointer");
+    const float *src[FMRX_TAP_COUNT] = {b->demod, b->mono, b->pilot, b->nco, b->sbpf, b->stereo, b->rbpf, b->rsq, b->rnco, b->rlpf, b->rres, b->rrrc};
+    if (which < 0 || which >= FMRX_TAP_COUNT || !src[which] || b->last_blocks == 0) return fail(FMRX_ERR_STATE, "tap %d not available", which);
+    CU(cudaSetDevice(b->cfg.device));
+    if (int e = fmrx_batch_sync(b)) return e;
+    const size_t len = fmrx_batch_tap_len(b, which), w = len * b->last_blocks * 4;
+    CU(cudaMemcpy2D(dst, w, src[which], len * b->NB * 4, w, b->S, cudaMemcpyDeviceToHost));
+    return FMRX_OK;
+}
+
+size_t fmrx_batch_state_bytes(const fmrx_batch *b) { return b ? b->state_bytes + sizeof(long long) : 0; }
+
+int fmrx_batch_get_state(fmrx_batch *b, void *blob) {
+    if (!b || !blob) return fail(FMRX_ERR_ARG, "null pointer");
+    CU(cudaSetDevice(b->cfg.device));
+    if (int e = fmrx_batch_sync(b)) return e;
+    std::memcpy(blob, &b->block_id, sizeof(long long));
+    CU(cudaMemcpy((char *)blob + sizeof(long long), b->d_state, b->state_bytes, cudaMemcpyDeviceToHost));
+    return FMRX_OK;
+}
+
+int fmrx_batch_set_state(fmrx_batch *b, const void *blob) {
+    if (!b || !blob) return fail(FMRX_ERR_ARG, "null pointer");
+    CU(cudaSetDevice(b->cfg.device));
+    if (int e = fmrx_batch_sync(b)) return e;
+    std::memcpy(&b->block_id, blob, sizeof(long long));
+    CU(cudaMemcpy(b->d_state, (const char *)blob + sizeof(long long), b->state_bytes, cudaMemcpyHostToDevice));
+    return FMRX_OK;
+}
+
+int fmrx_batch_profile(fmrx_batch *b, int enable) {
+    if (!b) return fail(FMRX_ERR_ARG, "null handle");
+    if (int e = fmrx_batch_sync(b)) return e;
+    b->profiling = enable != 0;
+    b->marks.clear();
+    b->prof_used = 0;
+    for (int i = 0; i < FMRX_STAGE_COUNT; ++i) { b->stage_ms[i] = 0; b->stage_launches[i] = 0; }
+    return FMRX_OK;
+}
+
+int fmrx_batch_stage_times(fmrx_batch *b, double *ms, long long *count) {
+    if (!b || !ms) return fail(FMRX_ERR_ARG, "null pointer");
+    if (int e = fmrx_batch_sync(b)) return e;
+    for (auto &m : b->marks) {
+        float t = 0.f;
+        CU(cudaEventElapsedTime(&t, m.t0, m.t1));
+        b->stage_ms[m.stage] += t;
+        b->stage_launches[m.stage] += 1;
+    }
+    b->marks.clear();
+    b->prof_used = 0;
+    for (int i = 0; i < FMRX_STAGE_COUNT; ++i) { ms[i] = b->stage_ms[i]; if (count) count[i] = b->stage_launches[i]; }
+    return FMRX_OK;
+}
+
+int fmrx_pinned_alloc(void **ptr, size_t bytes) {
+    if (!ptr) return fail(FMRX_ERR_ARG, "null pointer");
+    *ptr = nullptr;
+    cudaError_t e = cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(FMRX_ERR_ALLOC, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e)); }
+    return FMRX_OK;
+}
+
+int fmrx_pinned_free(void *ptr) {
+    if (ptr) CU(cudaFreeHost(ptr));
+    return FMRX_OK;
+}
+
+int fmrx_measure_fp32_peak(int device, int kind, int reps, double *tera) {
+    if (!tera) return fail(FMRX_ERR_ARG, "null pointer");
+    CU(cudaSetDevice(device));
+    LAUNCH(measure_fp32_peak(device, kind, reps, tera));
+    return FMRX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,102 @@
+// Internal declarations shared by the translation units of libfmrx.so: error plumbing and the kernel launchers.
+// All launchers take DEVICE pointers, enqueue on `st` and return a cudaError_t-compatible int (0 = ok).
+#ifndef FMRX_INTERNAL_H
+#define FMRX_INTERNAL_H
+#include <cstddef>
+#include <cstdint>
+
+#include "fmrx.h"
+
+struct CUstream_st;
+typedef CUstream_st *fmrx_stream_t;
+
+namespace fmrx {
+
+int fail(int status, const char *fmt, ...);
+long long &launch_counter();  // process-wide count of kernels launched by this library
+
+constexpr int kTaps = FMRX_MAX_TAPS;      // 151
+constexpr int kHist = FMRX_MAX_TAPS - 1;  // 150 samples of live history
+
+// how the FIR input sample at logical position p of block b is formed (p < 0 = history)
+enum SrcKind {
+    SRC_PLAIN = 0,    // x[p]; history one sample late (Q1)
+    SRC_SQUARE = 1,   // x[p]^2; zi holds squares (pllCombine, src/helper.cpp:139,162-164)
+    SRC_MIX_LATE = 2, // a[p]*b[p]; history one sample late (stereo mixer + LPF, src/fm_radio.cpp:269-274)
+    SRC_MIX_HALF = 3  // 2*a[p]*b[p] in the block, a*b (not late, no x2) in the history (Q8, src/filter.cpp:387,399)
+};
+
+struct FirJob {
+    const float *x;   // [S][ldx]: n_blocks*n samples per stream
+    const float *x2;  // second factor for the MIX kinds (same layout), else null
+    float *y;         // [S][ldy]: n_blocks*(n/decim)
+    float *zi;        // [S][nzi]; the last 150 entries are live
+    const float *h;   // HOST pointer to 151 taps (passed to the kernel by value)
+    long long ldx, ldy;
+    int nzi, n, n_blocks, n_streams, decim, kind, exact;
+};
+int launch_fir(const FirJob &j, fmrx_stream_t st);
+
+struct FirIqJob {  // two channels sharing taps (convolveWithDecimIQ)
+    const float *xi, *xq;
+    float *yi, *yq, *zii, *ziq;
+    const float *h;
+    long long ldx, ldy;
+    int n, n_blocks, n_streams, decim, exact;
+};
+int launch_fir_iq(const FirIqJob &j, fmrx_stream_t st);
+
+struct FrontendJob {  // rf_thread fused: u8 IQ -> FIR(151) /10 on I and Q -> discriminator
+    const uint8_t *raw;  // [S][ld_raw] bytes: n_blocks * 2n per stream
+    float *demod;        // [S][ld_out]
+    float *yi, *yq;      // optional filtered I/Q, same layout as demod
+    float *zii, *ziq;    // [S][150]
+    const float *h;      // HOST taps
+    long long ld_raw, ld_out;
+    int n, n_blocks, n_streams;  // n complex samples per block; decim is fixed at 10
+};
+int launch_frontend(const FrontendJob &j, fmrx_stream_t st);
+
+int launch_unpack(const uint8_t *raw, size_t n, float *out, fmrx_stream_t st);
+int launch_demod(const float *I, const float *Q, float *out, int n_streams, int n_blocks, int n, fmrx_stream_t st);
+
+struct ResampleJob {
+    const float *x;  // [S][ldx]
+    float *y;        // [S][ldy]
+    float *zi;       // [S][nzi]
+    const float *h;  // DEVICE taps [ntaps]
+    long long ldx, ldy;
+    // n = samples per block in memory; n_ref = the length the reference's vector had (differs only for the RDS resampler,
+    // whose input is the 15361-long mixer output, src/fm_radio.cpp:404-408); ny = outputs per block actually produced
+    int n, n_ref, ny, n_blocks, n_streams, ntaps, nzi, decim, up, gain_up, exact;
+};
+int launch_resample(const ResampleJob &j, fmrx_stream_t st);
+
+struct PllParams {
+    float freq, Fs, scale, phase_adj, bw;
+};
+// x,nco: [S][ld] with n_blocks*n samples; state [S][6].  One launch runs up to two independent PLL populations
+// (stereo pilot + RDS carrier); pass xb == nullptr for a single one.
+int launch_pll_blocks(const float *xa, float *ncoa, PllParams pa, float *sta, const float *xb, float *ncob, PllParams pb, float *stb,
+                      long long ld, int n_streams, int n, int n_blocks, fmrx_stream_t st);
+
+// mixed = a*b elementwise (mode-1 stereo path materialises it for the resampler, src/fm_radio.cpp:240-245)
+int launch_multiply(const float *a, const float *b, float *y, long long ld, int n_total, int n_streams, fmrx_stream_t st);
+
+struct CombineJob {  // L/R combine + quantise, src/fm_radio.cpp:277-299
+    const float *mono, *stereo;  // [S][ld]; stereo may be null (binary profile after block 0, Q7)
+    int16_t *audio;              // [S][2*ld] or null
+    float *audio_f;              // [S][2*ld] or null
+    long long ld;
+    int n_total, n_streams, mult;
+};
+int launch_combine(const CombineJob &j, fmrx_stream_t st);
+
+// rrc [S][ld] with n_blocks*n; outputs as in fmrx_rds_decode; state [S][FMRX_RDS_STATE_WORDS]
+int launch_rds_decode(const float *rrc, long long ld, int n_streams, int n_blocks, int n, uint8_t *bits, int32_t *n_bits,
+                      fmrx_rds_event *events, int32_t *n_events, int32_t *state, fmrx_stream_t st);
+
+int measure_fp32_peak(int device, int kind, int reps, double *tera);
+
+}  // namespace fmrx
+#endif

@@ -1,0 +1,152 @@
+// Carrier-recovery PLL + NCO (SURVEY 8a rows a13, a14's loop part) and the L/R combiner + quantiser (row a16).
+//
+// Reference: fmPLL, /root/reference/src/helper.cpp:13-57 (identical loop body inside pllCombine, :149-159); state struct
+// src/helper.h:17-19; call sites src/fm_radio.cpp:262 (19 kHz pilot, NCO x2) and :400 (114 kHz, NCO x0.5).
+//
+// The recurrence is sample-serial, so one stream runs per LANE and independent streams are packed 32 to a warp, one
+// warp per CTA so the (few) warps spread over all SMs.  Types follow the reference exactly (App. D.3): loop state is
+// fp32 with one rounding per operation (no FMA contraction), the phase detector and the oscillator go through the
+// double-precision atan2/sin/cos, and the oscillator argument is a double expression rounded to fp32.  Bit-exactness
+// matters here: once trigArg's fp32 ulp is coarse (after ~1 s of signal) two trajectories that differ in the last bit
+// decorrelate at the ulp level, far above the 1e-5 audio tolerance.
+#include <cuda_runtime.h>
+
+#include "fmrx_internal.h"
+
+namespace fmrx {
+namespace {
+
+constexpr double kTwoPi = 2 * 3.14159265358979323846;  // `2*PI`, src/helper.cpp:41 with src/dy4.h:13
+
+struct PllLoop {
+    float integ, phase, fbi, fbq, off;  // pll_state_type minus ncoLast
+    float Ki, Kp, scale, adj;
+    double w;  // (2*PI) * (double)(freq/Fs)
+};
+
+__device__ __forceinline__ float pll_step(PllLoop &c, float in, int k) {
+    const float eI = __fmul_rn(in, c.fbi);
+    const float eQ = __fmul_rn(in, -c.fbq);
+    const float eD = (float)atan2((double)eQ, (double)eI);
+    c.integ = __fadd_rn(c.integ, __fmul_rn(c.Ki, eD));
+    c.phase = __fadd_rn(c.phase, __fadd_rn(__fmul_rn(c.Kp, eD), c.integ));
+    const float cnt = __fadd_rn(__fadd_rn(c.off, (float)k), 1.0f);
+    const float trig = (float)__dadd_rn(__dmul_rn(c.w, (double)cnt), (double)c.phase);
+    double sn, cs;
+    sincos((double)trig, &sn, &cs);
+    c.fbi = (float)cs;
+    c.fbq = (float)sn;
+    return (float)cos((double)__fadd_rn(__fmul_rn(trig, c.scale), c.adj));
+}
+
+struct PllSide {
+    const float *x;
+    float *nco;
+    float *state;
+    float Ki, Kp, fratio, scale, adj;
+};
+
+__global__ void __launch_bounds__(32) pll_kernel(PllSide A, PllSide B, long long ld, int n_streams, int n, int n_blocks) {
+    int lane = blockIdx.x * 32 + threadIdx.x;
+    const PllSide &P = lane < n_streams ? A : B;
+    if (lane >= n_streams) lane -= n_streams;
+    if (lane >= n_streams || P.x == nullptr) return;
+    const float *x = P.x + (long long)lane * ld;
+    float *nco = P.nco + (long long)lane * ld;
+    float *st = P.state + (long long)lane * 6;
+    PllLoop c;
+    c.integ = st[0]; c.phase = st[1]; c.fbi = st[2]; c.fbq = st[3]; c.off = st[4];
+    float last = st[5];
+    c.Ki = P.Ki; c.Kp = P.Kp; c.scale = P.scale; c.adj = P.adj;
+    c.w = __dmul_rn(kTwoPi, (double)P.fratio);
+    for (int b = 0; b < n_blocks; ++b) {
+        const float *xb = x + (long long)b * n;
+        float *ob = nco + (long long)b * n;
+        int k = 0;
+        if ((((uintptr_t)xb | (uintptr_t)ob) & 15) == 0) {
+            for (; k + 4 <= n; k += 4) {
+                const float4 v = *reinterpret_cast<const float4 *>(xb + k);
+                float4 o;
+                o.x = last; last = pll_step(c, v.x, k);
+                o.y = last; last = pll_step(c, v.y, k + 1);
+                o.z = last; last = pll_step(c, v.z, k + 2);
+                o.w = last; last = pll_step(c, v.w, k + 3);
+                *reinterpret_cast<float4 *>(ob + k) = o;
+            }
+        }
+        for (; k < n; ++k) {
+            ob[k] = last;  // output sample k is the NCO value of step k-1 (src/helper.cpp:29,44,56)
+            last = pll_step(c, xb[k], k);
+        }
+        c.off = __fadd_rn(c.off, (float)n);  // src/helper.cpp:53
+    }
+    st[0] = c.integ; st[1] = c.phase; st[2] = c.fbi; st[3] = c.fbq; st[4] = c.off; st[5] = last;
+}
+
+// src/fm_radio.cpp:277-299: L=(m+s)/2, R=(m-s)/2; NaN -> 0 else static_cast<short>(x*16384*mult), which on x86-64 is
+// cvttss2si (truncate toward zero, 0x80000000 when out of range) followed by taking the low 16 bits.
+__device__ __forceinline__ int16_t quantise(float v, float mult) {
+    if (isnan(v)) return 0;
+    const float s = __fmul_rn(__fmul_rn(v, 16384.0f), mult);
+    const int w = (s > -2147483648.0f && s < 2147483648.0f) ? __float2int_rz(s) : (int)0x80000000;
+    return (int16_t)(unsigned short)(w & 0xFFFF);
+}
+
+__global__ void combine_kernel(const float *mono, const float *stereo, int16_t *audio, float *audio_f, long long ld, int n_total, float mult) {
+    const int s = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_total) return;
+    const float m = mono[(long long)s * ld + i];
+    const float t = stereo ? stereo[(long long)s * ld + i] : 0.0f;
+    const float l = __fdiv_rn(__fadd_rn(m, t), 2.0f), r = __fdiv_rn(__fsub_rn(m, t), 2.0f);
+    const long long o = ((long long)s * ld + i) * 2;
+    if (audio_f) *reinterpret_cast<float2 *>(audio_f + o) = make_float2(l, r);
+    if (audio) *reinterpret_cast<short2 *>(audio + o) = make_short2(quantise(l, mult), quantise(r, mult));
+}
+
+__global__ void multiply_kernel(const float *a, const float *b, float *y, long long ld, int n_total) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_total) return;
+    const long long q = (long long)blockIdx.y * ld + i;
+    y[q] = __fmul_rn(a[q], b[q]);
+}
+
+PllSide make_side(const float *x, float *nco, float *state, const PllParams &p) {
+    PllSide s;
+    s.x = x; s.nco = nco; s.state = state;
+    const float Cp = 2.666f, Ci = 3.555f;  // src/helper.cpp:15-16
+    s.Ki = (p.bw * p.bw) * Ci;
+    s.Kp = p.bw * Cp;
+    s.fratio = p.freq / p.Fs;
+    s.scale = p.scale;
+    s.adj = p.phase_adj;
+    return s;
+}
+
+}  // namespace
+
+int launch_pll_blocks(const float *xa, float *ncoa, PllParams pa, float *sta, const float *xb, float *ncob, PllParams pb, float *stb,
+                      long long ld, int n_streams, int n, int n_blocks, fmrx_stream_t st) {
+    PllSide A = make_side(xa, ncoa, sta, pa);
+    PllSide B = xb ? make_side(xb, ncob, stb, pb) : PllSide{};
+    const int lanes = xb ? 2 * n_streams : n_streams;
+    pll_kernel<<<(lanes + 31) / 32, 32, 0, st>>>(A, B, ld, n_streams, n, n_blocks);
+    launch_counter() += 1;
+    return (int)cudaGetLastError();
+}
+
+int launch_multiply(const float *a, const float *b, float *y, long long ld, int n_total, int n_streams, fmrx_stream_t st) {
+    dim3 grid((n_total + 255) / 256, n_streams);
+    multiply_kernel<<<grid, 256, 0, st>>>(a, b, y, ld, n_total);
+    launch_counter() += 1;
+    return (int)cudaGetLastError();
+}
+
+int launch_combine(const CombineJob &j, fmrx_stream_t st) {
+    dim3 grid((j.n_total + 255) / 256, j.n_streams);
+    combine_kernel<<<grid, 256, 0, st>>>(j.mono, j.stereo, j.audio, j.audio_f, j.ld, j.n_total, (float)j.mult);
+    launch_counter() += 1;
+    return (int)cudaGetLastError();
+}
+
+}  // namespace fmrx

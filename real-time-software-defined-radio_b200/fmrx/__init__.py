@@ -1,0 +1,394 @@
+"""fmrx — ctypes binding of libfmrx.so (include/fmrx.h), the B200-native FM receive chain.
+
+Two layers:
+  * `fmrx.lib()` / the thin wrappers below: one Python function per C-ABI entry, numpy arrays in and out;
+  * `fmrx.refapi`: the same operators under the reference's own function names and argument order
+    (impulseResponseLPF, convolveWithDecim, fmPLL, ... — /root/reference/src/filter.h, helper.h, rf_module.h), so a
+    test written against the reference reads the same against this library.
+
+There is no CPU fallback: importing works anywhere (so the not-gpu tests can check the ABI), but every compute call
+raises FmrxError when the extension is missing or no CUDA device is usable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(PKG_DIR, "libfmrx.so")
+CLI_PATH = os.path.join(PKG_DIR, "fm_radio")
+
+BLOCK_BYTES = 307200
+IF_PER_BLOCK = 15360
+RDS_PER_BLOCK = 3648
+MAX_EVENTS = 96
+MAX_BITS = 80
+RDS_STATE_WORDS = 160
+PROFILE_BINARY, PROFILE_INTENT = 0, 1
+PATH_AUDIO, PATH_RDS = 1, 2
+NUMERICS_REFERENCE, NUMERICS_FMA = 0, 1
+TAPS = dict(demod=0, mono=1, pilot=2, nco=3, stereo_bpf=4, stereo=5, rds_bpf=6, rds_sq=7, rds_nco=8, rds_lpf=9, rds_res=10, rds_rrc=11)
+
+STAGES = ("frontend", "mono", "pilot_bpf", "stereo_bpf", "rds_bpf", "rds_sq_bpf", "pll", "stereo_lpf", "combine", "rds_mix_lpf",
+          "rds_resample", "rds_rrc", "rds_decode")
+
+F = np.float32
+fp = C.POINTER(C.c_float)
+u8p = C.POINTER(C.c_uint8)
+i16p = C.POINTER(C.c_int16)
+i32p = C.POINTER(C.c_int32)
+
+
+class FmrxError(RuntimeError):
+    pass
+
+
+class RdsEvent(C.Structure):
+    _fields_ = [("block", C.c_int32), ("kind", C.c_int32), ("letter", C.c_int32), ("position", C.c_uint32)]
+
+
+EVENT_DTYPE = np.dtype([("block", np.int32), ("kind", np.int32), ("letter", np.int32), ("position", np.uint32)])
+evp = C.POINTER(RdsEvent)
+
+
+class Config(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("mode", "profile", "n_streams", "max_blocks", "device", "paths", "numerics", "reserved")]
+
+
+class Outputs(C.Structure):
+    _fields_ = [("audio", i16p), ("audio_f", fp), ("rds_bits", u8p), ("rds_n_bits", i32p), ("rds_events", evp), ("rds_n_events", i32p)]
+
+
+# every exported symbol with its signature — tests/test_abi.py checks this table against include/fmrx.h
+SIGNATURES = {
+    "fmrx_last_error": (C.c_char_p, []),
+    "fmrx_version": (C.c_int, []),
+    "fmrx_device_count": (C.c_int, []),
+    "fmrx_design_lpf": (C.c_int, [C.c_float, C.c_float, C.c_ushort, fp]),
+    "fmrx_design_bpf": (C.c_int, [C.c_float, C.c_float, C.c_float, C.c_int, fp]),
+    "fmrx_design_rrc": (C.c_int, [C.c_float, C.c_int, fp]),
+    "fmrx_unpack_iq": (C.c_int, [u8p, C.c_size_t, fp]),
+    "fmrx_fir_decim": (C.c_int, [fp, fp, C.c_int, C.c_int, C.c_int, fp, C.c_int, fp, C.c_int, C.c_int, C.c_int]),
+    "fmrx_fir_decim_iq": (C.c_int, [fp, fp, fp, fp, C.c_int, C.c_int, C.c_int, fp, C.c_int, fp, fp, C.c_int, C.c_int]),
+    "fmrx_resample": (C.c_int, [fp, C.c_int, fp, C.c_int, C.c_int, C.c_int, fp, C.c_int, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "fmrx_fir_mixer": (C.c_int, [fp, fp, fp, C.c_int, C.c_int, C.c_int, fp, C.c_int, fp]),
+    "fmrx_demod": (C.c_int, [fp, fp, C.c_int, C.c_int, C.c_int, fp]),
+    "fmrx_pll": (C.c_int, [fp, fp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, fp]),
+    "fmrx_pll_combine": (C.c_int, [fp, fp, fp, C.c_int, C.c_int, C.c_int, fp, C.c_int, fp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, fp]),
+    "fmrx_frontend": (C.c_int, [fp, fp, fp, u8p, C.c_int, C.c_int, C.c_int, fp, C.c_int, fp, fp, C.c_int]),
+    "fmrx_rds_decode": (C.c_int, [fp, C.c_int, C.c_int, C.c_int, u8p, i32p, evp, i32p, i32p]),
+    "fmrx_rds_state_offset": (C.c_int, [i32p]),
+    "fmrx_rds_format_block": (C.c_int, [C.c_int, C.c_int, evp, C.c_int, C.c_char_p, C.c_int]),
+    "fmrx_batch_create": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
+    "fmrx_batch_destroy": (None, [C.c_void_p]),
+    "fmrx_batch_audio_per_block": (C.c_int, [C.c_void_p]),
+    "fmrx_batch_reset": (C.c_int, [C.c_void_p]),
+    "fmrx_batch_process": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Outputs)]),
+    "fmrx_batch_process_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "fmrx_batch_sync": (C.c_int, [C.c_void_p]),
+    "fmrx_batch_cuda_stream": (C.c_void_p, [C.c_void_p]),
+    "fmrx_batch_launch_count": (C.c_longlong, [C.c_void_p]),
+    "fmrx_batch_rds_offsets": (C.c_int, [C.c_void_p, i32p]),
+    "fmrx_batch_tap_len": (C.c_int, [C.c_void_p, C.c_int]),
+    "fmrx_batch_tap": (C.c_int, [C.c_void_p, C.c_int, fp]),
+    "fmrx_batch_state_bytes": (C.c_size_t, [C.c_void_p]),
+    "fmrx_batch_get_state": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "fmrx_batch_set_state": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "fmrx_batch_profile": (C.c_int, [C.c_void_p, C.c_int]),
+    "fmrx_batch_stage_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+    "fmrx_pinned_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    "fmrx_pinned_free": (C.c_int, [C.c_void_p]),
+    "fmrx_measure_fp32_peak": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
+}
+
+_LIB = None
+
+
+def build(jobs: int = 8) -> None:
+    """Compile libfmrx.so and the fm_radio CLI in-tree (nvcc, sm_100a)."""
+    subprocess.check_call(["make", "-C", PKG_DIR, f"-j{jobs}", "all"], stdout=subprocess.DEVNULL)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise FmrxError(f"{LIB_PATH} is missing — build it with `make -C {PKG_DIR}` (there is no CPU fallback)")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype, fn.argtypes = res, args
+        _LIB = l
+    return _LIB
+
+
+def check(status: int) -> None:
+    if status != 0:
+        raise FmrxError(f"fmrx status {status}: {lib().fmrx_last_error().decode()}")
+
+
+def _p(a, t=fp):
+    return a.ctypes.data_as(t)
+
+
+def f32(a):
+    return np.ascontiguousarray(a, dtype=F)
+
+
+def _as3(a, dtype=F):
+    """[n] -> [1][1][n], [B][n] -> [1][B][n], [S][B][n] unchanged."""
+    a = np.ascontiguousarray(a, dtype=dtype)
+    while a.ndim < 3:
+        a = a[None]
+    return a
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# thin wrappers (numpy in / numpy out; state arrays are updated in place)
+# ---------------------------------------------------------------------------------------------------------------------
+def design_lpf(Fs, Fc, ntaps):
+    h = np.zeros(ntaps, F)
+    check(lib().fmrx_design_lpf(Fs, Fc, ntaps, _p(h)))
+    return h
+
+
+def design_bpf(Fb, Fe, Fs, ntaps):
+    h = np.zeros(ntaps, F)
+    check(lib().fmrx_design_bpf(Fb, Fe, Fs, ntaps, _p(h)))
+    return h
+
+
+def design_rrc(Fs, ntaps):
+    h = np.zeros(ntaps, F)
+    check(lib().fmrx_design_rrc(Fs, ntaps, _p(h)))
+    return h
+
+
+def unpack_iq(raw):
+    raw = np.ascontiguousarray(raw, np.uint8)
+    out = np.zeros(raw.size, F)
+    check(lib().fmrx_unpack_iq(_p(raw, u8p), raw.size, _p(out)))
+    return out.reshape(raw.shape)
+
+
+def fir_decim(x, h, zi, decim, exact=True):
+    """x: [n] | [B][n] | [S][B][n]; zi: [nzi] | [S][nzi] (updated in place).  Returns y with x's leading shape."""
+    x3, h = _as3(x), f32(h)
+    S, B, n = x3.shape
+    assert zi.dtype == F and zi.flags.c_contiguous and zi.size % S == 0
+    y = np.zeros((S, B, n // decim), F)
+    check(lib().fmrx_fir_decim(_p(y), _p(x3), S, B, n, _p(h), h.size, _p(zi), zi.size // S, decim, int(exact)))
+    return y.reshape(np.shape(x)[:-1] + (n // decim,))
+
+
+def fir_decim_iq(xi, xq, h, zii, ziq, decim=10, exact=True):
+    a, b, h = _as3(xi), _as3(xq), f32(h)
+    S, B, n = a.shape
+    yi, yq = np.zeros((S, B, n // decim), F), np.zeros((S, B, n // decim), F)
+    check(lib().fmrx_fir_decim_iq(_p(yi), _p(yq), _p(a), _p(b), S, B, n, _p(h), h.size, _p(zii), _p(ziq), decim, int(exact)))
+    shp = np.shape(xi)[:-1] + (n // decim,)
+    return yi.reshape(shp), yq.reshape(shp)
+
+
+def resample(x, h, zi, decim, up, gain_up=False, ny_limit=0, exact=True):
+    x3, h = _as3(x), f32(h)
+    S, B, n = x3.shape
+    ny = (n * up) // decim
+    if 0 < ny_limit < ny:
+        ny = ny_limit
+    y = np.zeros((S, B, ny), F)
+    check(lib().fmrx_resample(_p(y), ny_limit, _p(x3), S, B, n, _p(h), h.size, _p(zi), zi.size // S, decim, up, int(gain_up), int(exact)))
+    return y.reshape(np.shape(x)[:-1] + (ny,))
+
+
+def fir_mixer(nco, sig, h, zi):
+    a, b, h = _as3(nco), _as3(sig), f32(h)
+    S, B, n = b.shape
+    y = np.zeros((S, B, n), F)
+    check(lib().fmrx_fir_mixer(_p(y), _p(a), _p(b), S, B, n, _p(h), h.size, _p(zi)))
+    return y.reshape(np.shape(sig))
+
+
+def demod(i, q):
+    a, b = _as3(i), _as3(q)
+    S, B, n = a.shape
+    out = np.zeros((S, B, n), F)
+    check(lib().fmrx_demod(_p(a), _p(b), S, B, n, _p(out)))
+    return out.reshape(np.shape(i))
+
+
+def pll(x, freq, Fs, scale, phase_adj, bw, state):
+    x3 = _as3(x)
+    S, B, n = x3.shape
+    nco = np.zeros((S, B, n), F)
+    check(lib().fmrx_pll(_p(nco), _p(x3), S, B, n, freq, Fs, scale, phase_adj, bw, _p(state)))
+    return nco.reshape(np.shape(x))
+
+
+def pll_combine(x, h, zi, freq, Fs, scale, phase_adj, bw, state):
+    x3, h = _as3(x), f32(h)
+    S, B, n = x3.shape
+    y, nco = np.zeros((S, B, n), F), np.zeros((S, B, n), F)
+    check(lib().fmrx_pll_combine(_p(y), _p(nco), _p(x3), S, B, n, _p(h), h.size, _p(zi), freq, Fs, scale, phase_adj, bw, _p(state)))
+    return y.reshape(np.shape(x)), nco.reshape(np.shape(x))
+
+
+def frontend(raw, h, zii, ziq, decim=10, want_iq=False):
+    """raw: u8 [2n] | [B][2n] | [S][B][2n] interleaved I,Q."""
+    r3, h = _as3(raw, np.uint8), f32(h)
+    S, B, n2 = r3.shape
+    n = n2 // 2
+    d = np.zeros((S, B, n // decim), F)
+    yi = np.zeros_like(d) if want_iq else None
+    yq = np.zeros_like(d) if want_iq else None
+    check(lib().fmrx_frontend(_p(d), _p(yi) if want_iq else None, _p(yq) if want_iq else None, _p(r3, u8p), S, B, n, _p(h), h.size, _p(zii), _p(ziq), decim))
+    shp = np.shape(raw)[:-1] + (n // decim,)
+    return (d.reshape(shp), yi.reshape(shp), yq.reshape(shp)) if want_iq else d.reshape(shp)
+
+
+def rds_decode(rrc, state):
+    """rrc: [n] | [B][n] | [S][B][n]; state: int32 [S][160] updated in place.
+    Returns (bits [S][B][80] u8, n_bits [S][B], events [S][B][96] structured, n_events [S][B])."""
+    r3 = _as3(rrc)
+    S, B, n = r3.shape
+    bits = np.zeros((S, B, MAX_BITS), np.uint8)
+    nb = np.zeros((S, B), np.int32)
+    ev = np.zeros((S, B, MAX_EVENTS), EVENT_DTYPE)
+    ne = np.zeros((S, B), np.int32)
+    check(lib().fmrx_rds_decode(_p(r3), S, B, n, _p(bits, u8p), _p(nb, i32p), _p(ev, evp), _p(ne, i32p), _p(state, i32p)))
+    return bits, nb, ev, ne
+
+
+def rds_format_block(block_id, initial_offset, events):
+    ev = np.ascontiguousarray(events, EVENT_DTYPE)
+    buf = C.create_string_buffer(16384)
+    n = lib().fmrx_rds_format_block(block_id, initial_offset, _p(ev, evp) if ev.size else None, ev.size, buf, 16384)
+    return buf.raw[:n].decode()
+
+
+def measure_fp32_peak(kind, device=0, reps=5):
+    v = C.c_double(0)
+    check(lib().fmrx_measure_fp32_peak(device, kind, reps, C.byref(v)))
+    return v.value
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the batched chain
+# ---------------------------------------------------------------------------------------------------------------------
+class Batch:
+    """n_streams independent stations processed in lock step, max_blocks blocks per call."""
+
+    def __init__(self, n_streams=1, mode=0, profile=PROFILE_BINARY, max_blocks=1, device=0, paths=0, numerics=NUMERICS_REFERENCE):
+        self.cfg = Config(mode, profile, n_streams, max_blocks, device, paths, numerics, 0)
+        self.h = C.c_void_p()
+        check(lib().fmrx_batch_create(C.byref(self.cfg), C.byref(self.h)))
+        self.S, self.mode, self.max_blocks = n_streams, mode, max_blocks
+        self.n_audio = lib().fmrx_batch_audio_per_block(self.h)
+        self.rds = mode == 0 and (paths == 0 or paths & PATH_RDS)
+        self.audio_on = paths == 0 or bool(paths & PATH_AUDIO)
+        self.block_id = 0
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            lib().fmrx_batch_destroy(self.h)
+            self.h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def reset(self):
+        check(lib().fmrx_batch_reset(self.h))
+        self.block_id = 0
+
+    def process(self, iq, want_float=False):
+        """iq: u8 [S][B*307200] (or [B*307200] for one stream).  Returns a dict with audio int16 [S][B][2*n_audio]
+        (L,R interleaved), optionally audio_f, and for mode 0 rds_bits / rds_n_bits / rds_events / rds_n_events."""
+        iq = np.ascontiguousarray(iq, np.uint8).reshape(self.S, -1)
+        assert iq.shape[1] % BLOCK_BYTES == 0, "whole 307200-byte blocks only (SURVEY Q9)"
+        B = iq.shape[1] // BLOCK_BYTES
+        res, o = {}, Outputs()
+        if self.audio_on:
+            res["audio"] = np.zeros((self.S, B, 2 * self.n_audio), np.int16)
+            o.audio = _p(res["audio"], i16p)
+            if want_float:
+                res["audio_f"] = np.zeros((self.S, B, 2 * self.n_audio), F)
+                o.audio_f = _p(res["audio_f"])
+        if self.rds:
+            res["rds_bits"] = np.zeros((self.S, B, MAX_BITS), np.uint8); o.rds_bits = _p(res["rds_bits"], u8p)
+            res["rds_n_bits"] = np.zeros((self.S, B), np.int32); o.rds_n_bits = _p(res["rds_n_bits"], i32p)
+            res["rds_events"] = np.zeros((self.S, B, MAX_EVENTS), EVENT_DTYPE); o.rds_events = _p(res["rds_events"], evp)
+            res["rds_n_events"] = np.zeros((self.S, B), np.int32); o.rds_n_events = _p(res["rds_n_events"], i32p)
+        check(lib().fmrx_batch_process(self.h, iq.ctypes.data_as(C.c_void_p), B, C.byref(o)))
+        res["first_block"] = self.block_id
+        self.block_id += B
+        self.last_blocks = B
+        return res
+
+    def process_device(self, iq_ptr: int, n_blocks: int, out_ptrs: Outputs | None = None):
+        """Raw device pointers (e.g. torch tensor .data_ptr()); asynchronous — call sync()."""
+        check(lib().fmrx_batch_process_device(self.h, C.c_void_p(iq_ptr), n_blocks, C.byref(out_ptrs) if out_ptrs is not None else None))
+        self.block_id += n_blocks
+        self.last_blocks = n_blocks
+
+    def sync(self):
+        check(lib().fmrx_batch_sync(self.h))
+
+    def tap(self, name):
+        which = TAPS[name]
+        n = lib().fmrx_batch_tap_len(self.h, which)
+        out = np.zeros((self.S, self.last_blocks, n), F)
+        check(lib().fmrx_batch_tap(self.h, which, _p(out)))
+        return out
+
+    def rds_offsets(self):
+        out = np.zeros(self.S, np.int32)
+        check(lib().fmrx_batch_rds_offsets(self.h, _p(out, i32p)))
+        return out
+
+    def rds_text(self, res, stream=0):
+        """The stderr lines the reference's frame_thread prints for the blocks of `res` (src/fm_radio.cpp:516,619-701)."""
+        off = int(self.rds_offsets()[stream])
+        out = []
+        for b in range(res["rds_n_events"].shape[1]):
+            ne = int(res["rds_n_events"][stream, b])
+            out.append(rds_format_block(res["first_block"] + b, off, res["rds_events"][stream, b, :ne]))
+        return "".join(out)
+
+    def profile(self, enable=True):
+        check(lib().fmrx_batch_profile(self.h, int(enable)))
+
+    def stage_times(self):
+        """{stage: (total ms, brackets)} accumulated since profile(True)."""
+        ms = (C.c_double * len(STAGES))()
+        cnt = (C.c_longlong * len(STAGES))()
+        check(lib().fmrx_batch_stage_times(self.h, ms, cnt))
+        return {n: (ms[i], cnt[i]) for i, n in enumerate(STAGES)}
+
+    def process_into(self, iq, n_blocks, out: "Outputs"):
+        """Host path with caller-provided (ideally pinned) buffers; `iq` is anything with a ctypes-able address."""
+        ptr = iq if isinstance(iq, int) else iq.ctypes.data
+        check(lib().fmrx_batch_process(self.h, C.c_void_p(ptr), n_blocks, C.byref(out)))
+        self.block_id += n_blocks
+        self.last_blocks = n_blocks
+
+    @property
+    def launches(self):
+        return lib().fmrx_batch_launch_count(self.h)
+
+    def get_state(self):
+        buf = np.zeros(lib().fmrx_batch_state_bytes(self.h), np.uint8)
+        check(lib().fmrx_batch_get_state(self.h, buf.ctypes.data_as(C.c_void_p)))
+        return buf
+
+    def set_state(self, blob, block_id=None):
+        blob = np.ascontiguousarray(blob, np.uint8)
+        check(lib().fmrx_batch_set_state(self.h, blob.ctypes.data_as(C.c_void_p)))
+        self.block_id = int(blob[:8].view(np.int64)[0])

@@ -1,0 +1,159 @@
+"""GPU: the batched receive chain through the C-ABI against the golden fixtures, the oracle port, and (size-independent)
+properties.  Audio is bit-exact in both profiles and both modes; RDS float stages <= 1e-5 relative RMS; RDS bits,
+events and the rendered stderr lines bit-exact."""
+import numpy as np
+import pytest
+
+import fmrx
+from fmrx import synth
+from oracle import Chain
+from oracle.port import format_block
+from util import LONG_STRIDE, assert_bits, rel_rms, sha
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+NAMES = {0: "binary", 1: "intent"}
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("profile", [0, 1])
+def test_chain_golden(golden, mode, profile):
+    g = golden[f"chain_mode{mode}"]
+    nblk, name = int(g["nblk"]), NAMES[profile]
+    raw = synth.synth_iq(nblk, mode, seed=int(g["seed"]))
+    assert sha(raw) == str(g["input_sha256"])
+    with fmrx.Batch(1, mode=mode, profile=profile, max_blocks=1) as rx:
+        audio, text = [], ""
+        for b in range(nblk):
+            res = rx.process(raw[b * 307200:(b + 1) * 307200], want_float=True)
+            audio.append(res["audio"][0, 0])
+            assert_bits(res["audio_f"][0, 0], g[f"{name}_audio_f_{b}"], f"float audio block {b}")
+            assert_bits(rx.tap("mono")[0, 0], g[f"{name}_mono_{b}"], f"mono block {b}")
+            if profile == 1 or b == 0:
+                assert_bits(rx.tap("stereo")[0, 0], g[f"{name}_stereo_{b}"], f"stereo block {b}")
+            for t in ("demod", "pilot", "nco", "stereo_bpf"):
+                key = f"{name}_{t}_{b}"
+                if key in g.files:
+                    assert_bits(rx.tap(t)[0, 0][::LONG_STRIDE], g[key], key)
+            if mode == 0:
+                for t in ("rds_bpf", "rds_sq", "rds_lpf", "rds_res"):
+                    key = f"{name}_{t}_{b}"
+                    if key in g.files:
+                        v = rx.tap(t)[0, 0]
+                        assert rel_rms(v[::LONG_STRIDE] if v.size >= 15360 else v, g[key]) < TOL, key
+                assert rel_rms(rx.tap("rds_rrc")[0, 0], g[f"{name}_rds_rrc_{b}"]) < TOL, f"rrc block {b}"
+                text += rx.rds_text(res)
+        audio = np.concatenate(audio)
+        assert_bits(audio, g[f"{name}_audio"], "int16 audio")
+        if profile == 0:
+            assert_bits(audio, g["binary_audio"], "int16 audio vs the reference executable's stdout")
+        if mode == 0:
+            assert text == str(g["binary_frame_text"]), "RDS stderr lines vs the reference executable"
+
+
+def test_multi_block_calls_equal_single_block_calls():
+    raw = synth.synth_iq(6, 0, seed=5)
+    with fmrx.Batch(1, mode=0, profile=1, max_blocks=1) as a, fmrx.Batch(1, mode=0, profile=1, max_blocks=4) as b:
+        one = [a.process(raw[k * 307200:(k + 1) * 307200]) for k in range(6)]
+        r1, r2 = b.process(raw[:4 * 307200]), b.process(raw[4 * 307200:])
+        many_audio = np.concatenate([r1["audio"][0], r2["audio"][0]])
+        assert_bits(many_audio, np.stack([r["audio"][0, 0] for r in one]), "audio")
+        many_bits = np.concatenate([r1["rds_bits"][0], r2["rds_bits"][0]])
+        assert np.array_equal(many_bits, np.stack([r["rds_bits"][0, 0] for r in one]))
+        ev = np.concatenate([r1["rds_events"][0], r2["rds_events"][0]])
+        assert np.array_equal(ev, np.stack([r["rds_events"][0, 0] for r in one]))
+
+
+def test_binary_profile_multi_block_first_call():
+    """Q7 inside one call: block 0 keeps its stereo difference, blocks 1.. are L == R."""
+    raw = synth.synth_iq(3, 0, seed=3)
+    with fmrx.Batch(1, mode=0, profile=0, max_blocks=3) as rx:
+        a = rx.process(raw)["audio"][0].reshape(3, 3072, 2)
+    ch = Chain(0, 0)
+    ref = np.stack([ch.block(raw[k * 307200:(k + 1) * 307200]) for k in range(3)]).reshape(3, 3072, 2)
+    assert_bits(a, ref, "audio")
+    assert (a[1:, :, 0] == a[1:, :, 1]).all() and (a[0, :, 0] != a[0, :, 1]).any()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_batch_of_distinct_stations_vs_oracle(mode):
+    """Several stations in one batch (different tones and RDS payloads), a few blocks each; every stream must equal
+    the oracle run on that stream alone: nothing leaks between lanes, tiles or chunks."""
+    S, B = 5, 3
+    raw = np.stack([synth.synth_station(s * 13, B, mode) for s in range(S)])
+    with fmrx.Batch(S, mode=mode, profile=1, max_blocks=B) as rx:
+        res = rx.process(raw, want_float=True)
+        offs = rx.rds_offsets() if mode == 0 else None
+        for s in range(S):
+            ch = Chain(mode, 1)
+            audio, cap, bits, events, text = ch.run(raw[s], taps=("audio_f",))
+            assert_bits(res["audio"][s].ravel(), audio, f"stream {s} int16")
+            assert_bits(res["audio_f"][s], np.stack(cap["audio_f"]), f"stream {s} float audio")
+            if mode == 0:
+                for b in range(B):
+                    assert np.array_equal(res["rds_bits"][s, b, :res["rds_n_bits"][s, b]], bits[b]), f"stream {s} block {b} bits"
+                got = [tuple(int(v) for v in e) for b in range(B) for e in res["rds_events"][s, b, :res["rds_n_events"][s, b]]]
+                assert got == events and offs[s] == ch.rds_offset
+                assert rx.rds_text(res, s) == text
+
+
+def test_large_batch_chunked_pipeline_consistency():
+    """128 streams take the chunked copy/compute pipeline (4 chunks over two compute streams); stations repeat with
+    period 8, so streams s and s+8k must be bit-identical, and stream 0..7 must equal the oracle."""
+    S, B = 128, 2
+    base = np.stack([synth.synth_station(s, B, 0) for s in range(8)])
+    raw = np.tile(base, (S // 8, 1))
+    with fmrx.Batch(S, mode=0, profile=1, max_blocks=B) as rx:
+        res = rx.process(raw)
+    a = res["audio"].reshape(S // 8, 8, -1)
+    assert (a == a[0]).all(), "replicated stations diverged across chunks"
+    assert (res["rds_bits"].reshape(S // 8, 8, -1) == res["rds_bits"].reshape(S // 8, 8, -1)[0]).all()
+    for s in (0, 3, 7):
+        audio, _, bits, _, _ = Chain(0, 1).run(base[s])
+        assert_bits(res["audio"][s].ravel(), audio, f"station {s}")
+        assert np.array_equal(np.concatenate([res["rds_bits"][s, b, :res["rds_n_bits"][s, b]] for b in range(B)]), np.concatenate(bits))
+
+
+def test_state_checkpoint_resume():
+    raw = synth.synth_iq(5, 0, seed=9)
+    blk = lambda k: raw[k * 307200:(k + 1) * 307200]
+    with fmrx.Batch(1, mode=0, profile=1) as a, fmrx.Batch(1, mode=0, profile=1) as b:
+        for k in range(3):
+            a.process(blk(k))
+        blob = a.get_state()
+        b.set_state(blob)
+        assert b.block_id == 3
+        for k in (3, 4):
+            ra, rb = a.process(blk(k)), b.process(blk(k))
+            assert_bits(ra["audio"], rb["audio"], "audio after resume")
+            assert np.array_equal(ra["rds_events"], rb["rds_events"]) and np.array_equal(ra["rds_bits"], rb["rds_bits"])
+        a.reset()
+        assert_bits(a.process(blk(0))["audio"][0, 0], Chain(0, 1).block(blk(0)), "after reset")
+
+
+def test_properties_at_full_block_size():
+    """Size-independent properties: block-start zero of the discriminator (Q3), L+R == mono (exact: (m+s)/2+(m-s)/2 is
+    not bit-exact in general, so compare against the taps), silence in -> silence out, determinism."""
+    raw = synth.synth_iq(2, 0, seed=4)
+    with fmrx.Batch(2, mode=0, profile=1, max_blocks=2) as rx:
+        r1 = rx.process(np.stack([raw, np.full_like(raw, 128)]), want_float=True)
+        demod, mono, st = rx.tap("demod"), rx.tap("mono"), rx.tap("stereo")
+        assert (demod[:, :, 0] == 0).all()
+        lr = r1["audio_f"].reshape(2, 2, 3072, 2)
+        assert_bits(lr[..., 0], ((mono + st) / np.float32(2)).astype(np.float32), "L"); assert_bits(lr[..., 1], ((mono - st) / np.float32(2)).astype(np.float32), "R")
+        assert (r1["audio"][1] == 0).all() and (demod[1] == 0).all(), "u8 128 = exactly 0.0 -> zero-denominator branch -> silence"
+        rx.reset()
+        r2 = rx.process(np.stack([raw, np.full_like(raw, 128)]), want_float=True)
+        assert_bits(r1["audio"], r2["audio"], "determinism")
+
+
+def test_fma_numerics_within_tolerance_mono():
+    """FMRX_NUMERICS_FMA: mono audio stays within 1e-5 relative RMS / +-1 LSB (the stereo difference needs the exact
+    pilot path; that one is kept exact in both settings)."""
+    raw = synth.synth_iq(3, 0, seed=6)
+    with fmrx.Batch(1, mode=0, profile=0, max_blocks=3, numerics=fmrx.NUMERICS_FMA) as rx:
+        res = rx.process(raw, want_float=True)
+    ch = Chain(0, 0)
+    audio, cap, *_ = ch.run(raw, taps=("audio_f",))
+    assert rel_rms(res["audio_f"][0], np.stack(cap["audio_f"])) < TOL
+    assert np.abs(res["audio"][0].ravel().astype(int) - audio.astype(int)).max() <= 1

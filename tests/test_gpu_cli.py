@@ -1,0 +1,47 @@
+"""GPU: the fm_radio executable's process contract against the reference executable's recorded stdout / stderr."""
+import subprocess
+
+import numpy as np
+import pytest
+
+import fmrx
+from fmrx import synth
+from util import assert_bits
+
+pytestmark = pytest.mark.gpu
+
+
+def run_cli(args, raw):
+    r = subprocess.run([fmrx.CLI_PATH] + args, input=raw.tobytes(), capture_output=True, timeout=600)
+    return np.frombuffer(r.stdout, np.int16), r.stderr.decode(), r.returncode
+
+
+@pytest.mark.parametrize("mode,extra", [(0, []), (0, ["--blocks", "3"]), (1, [])])
+def test_cli_matches_reference_binary(golden, mode, extra):
+    g = golden[f"chain_mode{mode}"]
+    nblk = int(g["nblk"])
+    raw = synth.synth_iq(nblk, mode, seed=int(g["seed"]))
+    tail = np.zeros(1000, np.uint8)  # a trailing partial block is ignored (Q9, normalised)
+    audio, err, rc = run_cli((["1"] if mode == 1 else []) + extra, np.concatenate([raw, tail]))
+    assert rc == 0, err
+    assert_bits(audio, g["binary_audio"], "stdout vs reference fm_radio")
+    lines = err.splitlines()
+    assert lines[0] == str(1 + (mode == 1)) and lines[1] == f"Operating in mode {mode}" and lines[2] == f"rf_Fs = {2500000 if mode else 2400000}"
+    assert lines[-1].startswith("Run: gnuplot")
+    if mode == 0:
+        body = "\n".join(lines[3:-1]) + "\n"
+        assert body == str(g["binary_frame_text"])
+
+
+def test_cli_rejects_bad_modes_like_the_reference():
+    for arg, msg in (("0", "Wrong mode 0"), ("2", "Wrong mode 2"), ("x", "Wrong mode 0")):
+        _, err, rc = run_cli([arg], np.zeros(0, np.uint8))
+        assert rc == 1 and msg in err
+
+
+def test_cli_intent_profile(golden):
+    g = golden["chain_mode0"]
+    raw = synth.synth_iq(int(g["nblk"]), 0, seed=int(g["seed"]))
+    audio, err, rc = run_cli(["--profile", "intent", "--quiet"], raw)
+    assert rc == 0 and "Syndrome" not in err
+    assert_bits(audio, g["intent_audio"], "intent profile stdout")
