@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the batched FM receive chain (BASELINE.json config 5) on N B200s of one node.
+
+    python bench.py [--gpus N --steps K --warmup W]                      (N > 1: launched by torch.distributed.run)
+    python bench.py --impl reference [--gpus N --steps K --warmup W]     (the reference's own CPU code, rank 0 only)
+
+Workload (config.workload = "batch4096_mode0_stereo_rds"): `--stations` (4096) independent synthetic FM stations PER
+GPU (weak scaling; stations are independent, so ranks share nothing and there is no collective on the data path),
+mode 0 = 2.4 Msps 8-bit IQ -> mono + stereo + RDS, `intent` profile (stereo computed in every block), one 307200-byte
+block (64 ms of signal) per station per step, filter / PLL / decoder state carried from step to step.  The same
+synthesised block is replayed every step (the arithmetic is data-independent); the input of one step is 1.26 GB, ten
+times the L2, so no L2 flush is needed.
+
+metric  : complex IQ samples consumed per second, whole job, in Msps;  real-time streams = value / 2.4.
+value   : inputs already resident in HBM, timed with CUDA events on the library's compute stream, max over ranks.
+e2e     : the same K steps through fmrx_batch_process with pinned HOST buffers (H2D of the IQ bytes and D2H of audio +
+          RDS results inside the timed region).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "real-time-software-defined-radio_b200"))
+
+BLOCK_BYTES = 307200
+BLOCK_IQ = 153600
+NIF, NAUD, NRDS, NT = 15360, 3072, 3648, 151
+# algorithmic MACs per station-block and whether the stage keeps the reference's two roundings per tap
+STAGE_MACS = {
+    "frontend": (NIF * NT * 2, True), "mono": (NAUD * NT, True), "pilot_bpf": (NIF * NT, True), "stereo_bpf": (NIF * NT, True),
+    "rds_bpf": (NIF * NT, False), "rds_sq_bpf": (NIF * NT, False), "stereo_lpf": (NAUD * NT, True), "rds_mix_lpf": (NIF * NT, False),
+    "rds_resample": (NRDS * NT, False), "rds_rrc": (NRDS * NT, False),
+}
+# algorithmic HBM bytes per station-block for the kernel split actually used (u8 in, fp32 intermediates, int16 out)
+STAGE_BYTES = {
+    "frontend": BLOCK_BYTES + 4 * NIF, "mono": 4 * NIF + 4 * NAUD, "pilot_bpf": 8 * NIF, "stereo_bpf": 8 * NIF, "rds_bpf": 8 * NIF,
+    "rds_sq_bpf": 8 * NIF, "pll": 16 * NIF, "stereo_lpf": 8 * NIF + 4 * NAUD, "combine": 8 * NAUD + 12 * NAUD * 2 // 2, "rds_mix_lpf": 12 * NIF,
+    "rds_resample": 4 * NIF + 4 * NRDS, "rds_rrc": 8 * NRDS, "rds_decode": 4 * NRDS,
+}
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons of one GPU, sampled every 200 ms while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "", 1).isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "power_w_max": max(pw) if pw else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the reference's CPU implementation, timed on the host cores (cpu_baseline leg and --impl reference)
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_reference_run(n_blocks, procs, mode=0):
+    """P independent processes of the reference path over `n_blocks` blocks each.  Uses the unmodified reference
+    executable (oracle/_ref/fm_radio, kind "reference") when it was built, else the oracle port's chain (kind "port").
+    Returns (Msps aggregate, kind, seconds)."""
+    from fmrx import synth
+
+    raw = synth.synth_iq(n_blocks, mode, seed=1)
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "fm_radio")
+    tmpdir = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    path = os.path.join(tmpdir, f"fmrx_bench_{os.getpid()}.raw")
+    raw.tofile(path)
+    try:
+        if os.path.exists(ref_bin):
+            kind = "reference"
+            cmd = [ref_bin] + (["1"] if mode == 1 else [])
+            t0 = time.perf_counter()
+            ps = [subprocess.Popen(cmd, stdin=open(path, "rb"), stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for _ in range(procs)]
+            for p in ps:
+                p.wait()
+            dt = time.perf_counter() - t0
+        else:
+            kind = "port"
+            code = ("import sys,numpy as np;sys.path.insert(0,%r);from oracle import Chain;c=Chain(%d,1);"
+                    "raw=np.fromfile(%r,np.uint8);[c.block(raw[b*307200:(b+1)*307200]) for b in range(%d)]" % (ROOT, mode, path, n_blocks))
+            subprocess.run([sys.executable, "-c", "import sys;sys.path.insert(0,%r);from oracle import load_port;load_port()" % ROOT], check=True)
+            t0 = time.perf_counter()
+            ps = [subprocess.Popen([sys.executable, "-c", code], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for _ in range(procs)]
+            for p in ps:
+                p.wait()
+            dt = time.perf_counter() - t0
+    finally:
+        os.unlink(path)
+    return procs * n_blocks * BLOCK_IQ / dt / 1e6, kind, dt
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    procs, nblk = host_cores(), args.cpu_blocks
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_reference_run(max(2, nblk // 4), procs)
+    t_total, units, kind = 0.0, 0, "reference"
+    for _ in range(args.steps):
+        msps, kind, dt = cpu_reference_run(nblk, procs)
+        t_total += dt
+        units += procs * nblk * BLOCK_IQ
+    value = units / t_total / 1e6
+    sample = f"{procs} concurrent processes x {nblk} blocks (mode 0: mono+stereo+RDS) per step, input from tmpfs, stdout to /dev/null"
+    line = {
+        "impl": "reference", "metric": "IQ Msps (complex samples/s, whole job)", "value": round(value, 3), "unit": "Msps", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * t_total / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "batch4096_mode0_stereo_rds", "reference_sample": sample, "realtime_streams": round(value / 2.4, 2)},
+        "cpu_baseline": {"value": round(value, 3), "unit": "Msps", "cores": procs, "kind": kind, "sample": sample},
+        "e2e": {"value": round(value, 3), "unit": "Msps", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the GPU arm
+# ---------------------------------------------------------------------------------------------------------------------
+def run_fmrx_arm(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    import fmrx
+    from fmrx import synth
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    S, B = args.stations, args.blocks
+    stations = range(rank * S, rank * S + S)
+    t0 = time.perf_counter()
+    d_iq = synth.synth_batch_torch(stations, B, 0, dev, chunk=64)
+    torch.cuda.synchronize()
+    t_synth = time.perf_counter() - t0
+
+    rx = fmrx.Batch(S, mode=0, profile=fmrx.PROFILE_INTENT, max_blocks=B, device=local_rank)
+    na = rx.n_audio
+    d_audio = torch.empty((S, B, 2 * na), dtype=torch.int16, device=dev)
+    d_bits = torch.zeros((S, B, fmrx.MAX_BITS), dtype=torch.uint8, device=dev)
+    d_nbits = torch.zeros((S, B), dtype=torch.int32, device=dev)
+    d_ev = torch.zeros((S, B, fmrx.MAX_EVENTS, 4), dtype=torch.int32, device=dev)
+    d_nev = torch.zeros((S, B), dtype=torch.int32, device=dev)
+
+    def ptr(t, typ):
+        return C.cast(C.c_void_p(t.data_ptr()), typ)
+
+    dout = fmrx.Outputs(ptr(d_audio, fmrx.i16p), None, ptr(d_bits, fmrx.u8p), ptr(d_nbits, fmrx.i32p), ptr(d_ev, fmrx.evp), ptr(d_nev, fmrx.i32p))
+
+    # ---- parity spot check on the first block of a few stations, against the oracle on the very same bytes
+    parity = "skipped"
+    if rank == 0 and not args.no_check:
+        from oracle import Chain
+
+        rx.process_device(d_iq.data_ptr(), B, dout)
+        rx.sync()
+        for s in sorted({0, 1, min(63, S - 1), S - 1}):
+            raw = d_iq[s].cpu().numpy()
+            audio, _, bits, events, _ = Chain(0, 1).run(raw)
+            assert np.array_equal(d_audio[s].cpu().numpy().ravel(), audio), f"station {s}: audio differs from the oracle"
+            got = np.concatenate([d_bits[s, b, :int(d_nbits[s, b])].cpu().numpy() for b in range(B)])
+            assert np.array_equal(got, np.concatenate(bits)), f"station {s}: RDS bits differ from the oracle"
+        parity = "audio bit-exact, RDS bits equal vs oracle on stations {0,1,63,S-1}"
+    rx.reset()
+
+    stream = torch.cuda.ExternalStream(fmrx.lib().fmrx_batch_cuda_stream(rx.h), device=dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    # ---- device-resident throughput
+    for _ in range(args.warmup):
+        rx.process_device(d_iq.data_ptr(), B, dout)
+    rx.sync()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    rx.profile(True)
+    l0 = rx.launches
+    ev0.record(stream)
+    for _ in range(args.steps):
+        rx.process_device(d_iq.data_ptr(), B, dout)
+    ev1.record(stream)
+    rx.sync()
+    barrier()
+    ms_dev = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = rx.launches - l0
+    stage = rx.stage_times()
+    rx.profile(False)
+    clocks = sampler.stop() if sampler else None
+    units = world * S * B * BLOCK_IQ * args.steps
+    value = units / (ms_dev * 1e-3) / 1e6
+
+    # ---- end to end: pinned host buffers in and out, copies inside the timed region
+    h_iq = torch.empty((S, B * BLOCK_BYTES), dtype=torch.uint8, pin_memory=True)
+    h_iq.copy_(d_iq)
+    h_audio = torch.empty((S, B, 2 * na), dtype=torch.int16, pin_memory=True)
+    h_bits = torch.zeros((S, B, fmrx.MAX_BITS), dtype=torch.uint8, pin_memory=True)
+    h_nbits = torch.zeros((S, B), dtype=torch.int32, pin_memory=True)
+    h_ev = torch.zeros((S, B, fmrx.MAX_EVENTS, 4), dtype=torch.int32, pin_memory=True)
+    h_nev = torch.zeros((S, B), dtype=torch.int32, pin_memory=True)
+    hout = fmrx.Outputs(ptr(h_audio, fmrx.i16p), None, ptr(h_bits, fmrx.u8p), ptr(h_nbits, fmrx.i32p), ptr(h_ev, fmrx.evp), ptr(h_nev, fmrx.i32p))
+    h2d = h_iq.numel()
+    d2h = h_audio.numel() * 2 + h_bits.numel() + h_nbits.numel() * 4 + h_ev.numel() * 4 + h_nev.numel() * 4
+    rx.reset()
+    for _ in range(max(1, args.warmup)):
+        rx.process_into(h_iq.data_ptr(), B, hout)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        rx.process_into(h_iq.data_ptr(), B, hout)  # synchronous: returns after the last D2H of the step has landed
+    torch.cuda.synchronize()
+    s_e2e = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_value = units / s_e2e / 1e6
+    if rank == 0 and not args.no_check:
+        assert (h_audio.numpy() != 0).any(), "end-to-end path produced no audio"
+
+    if rank != 0:
+        return
+    # ---- FP32 roofline of the dominant kernel, measured in this run (MEASURED_PEAKS.json has no FP32 figure)
+    peak_ffma = fmrx.measure_fp32_peak(0, local_rank)      # T FMA/s  -> 2 flop each
+    peak_muladd = fmrx.measure_fp32_peak(1, local_rank)    # T lane-ops/s, 1 flop each (the reference-exact tap)
+    hbm_peak, hbm_src = measured_peaks()
+    per = {}
+    for name, (ms, cnt) in stage.items():
+        if cnt == 0:
+            continue
+        ent = {"ms_per_step": round(ms / args.steps, 4), "share": round(ms / sum(v[0] for v in stage.values()), 4)}
+        if name in STAGE_MACS:
+            macs, exact = STAGE_MACS[name]
+            tf = 2.0 * macs * S * B * args.steps / (ms * 1e-3) / 1e12
+            pk = peak_muladd if exact else 2.0 * peak_ffma
+            ent.update({"tflops": round(tf, 2), "fp32_peak_tflops": round(pk, 2), "frac_fp32": round(tf / pk, 4), "rounding": "mul+add (reference-exact)" if exact else "fma"})
+        gbs = STAGE_BYTES[name] * S * B * args.steps / (ms * 1e-3) / 1e9
+        ent.update({"hbm_gbs": round(gbs, 1), "frac_hbm": round(gbs / hbm_peak, 4)})
+        per[name] = ent
+    top = max((n for n in per if n in STAGE_MACS), key=lambda n: per[n]["ms_per_step"])
+    roofline = {
+        "bound": "fp32", "kernel": top, "achieved": per[top]["tflops"], "peak": per[top]["fp32_peak_tflops"], "unit": "TFLOP/s", "frac": per[top]["frac_fp32"],
+        "traffic": None,
+        "peak_source": "measured in this run by fmrx_measure_fp32_peak: %.2f T FFMA/s (x2 flop), %.2f T FMUL+FADD lane-ops/s; a stage that keeps the "
+                       "reference's two roundings per tap is bounded by the latter" % (peak_ffma, peak_muladd),
+        "hbm": {"achieved": per[top]["hbm_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": per[top]["frac_hbm"], "peak_source": hbm_src},
+        "stages": per,
+    }
+    cores = host_cores()
+    cpu_msps, cpu_kind, cpu_dt = cpu_reference_run(args.cpu_blocks, cores)
+    line = {
+        "metric": "IQ Msps (complex samples/s, whole job)", "value": round(value, 1), "unit": "Msps", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms_dev / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "batch4096_mode0_stereo_rds", "stations_per_gpu": S, "blocks_per_step": B, "mode": 0, "profile": "intent", "paths": "mono+stereo+rds",
+                   "numerics": "audio path reference-exact (mul+add), RDS path fma", "realtime_streams": int(value / 2.4), "e2e_realtime_streams": int(e2e_value / 2.4),
+                   "l2": "input per step %.2f GB >> 126 MB L2, no flush needed" % (S * B * BLOCK_BYTES / 1e9), "input_reuse": "same synthesised block replayed each step, state carried",
+                   "synth_seconds": round(t_synth, 2), "parity_spot_check": parity,
+                   "e2e_timer": "host clock around K synchronous fmrx_batch_process calls, barrier + synchronize on both sides, max over ranks"},
+        "e2e": {"value": round(e2e_value, 1), "unit": "Msps", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": {"value": round(cpu_msps, 3), "unit": "Msps", "cores": cores, "kind": cpu_kind,
+                         "sample": f"{cores} concurrent processes x {args.cpu_blocks} blocks of the same mode-0 workload ({cpu_dt:.1f} s wall)"},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="fmrx", choices=["fmrx", "reference"])
+    ap.add_argument("--stations", type=int, default=4096, help="stations per GPU")
+    ap.add_argument("--blocks", type=int, default=1, help="blocks per station per step")
+    ap.add_argument("--cpu-blocks", type=int, default=16, help="blocks per process of the CPU baseline sample")
+    ap.add_argument("--no-check", action="store_true")
+    args = ap.parse_args()
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # convenience: `python bench.py --gpus N` re-launches itself under torch.distributed.run
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_fmrx_arm(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -549,6 +549,7 @@ int fmrx_batch_create(const fmrx_config *cfg, fmrx_batch **out) {
         CU(b->dalloc(b->rres, S * NB * NRDS)); CU(b->dalloc(b->rrrc, S * NB * NRDS));
         CU(b->dalloc(b->bits, S * NB * FMRX_MAX_BITS)); CU(b->dalloc(b->nbits, S * NB)); CU(b->dalloc(b->nev, S * NB)); CU(b->dalloc(b->ev, S * NB * FMRX_MAX_EVENTS));
         CU(cudaMemset(b->bits, 0, S * NB * FMRX_MAX_BITS));
+        CU(cudaMemset(b->ev, 0, S * NB * FMRX_MAX_EVENTS * sizeof(fmrx_rds_event)));
     }
     CU(cudaStreamCreateWithFlags(&b->s_in, cudaStreamNonBlocking)); CU(cudaStreamCreateWithFlags(&b->s_out, cudaStreamNonBlocking));
     for (auto &s : b->s_cmp) CU(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
