@@ -67,7 +67,7 @@ __device__ __forceinline__ float form(float a, float b, bool in_block) {
 // value of the FIR input at logical position p (relative to the start of block b) of stream-row xs / x2s
 template <int KIND>
 __device__ __forceinline__ float source(const FirDev &a, const float *xs, const float *x2s, const float *zs, int b, int p) {
-    if (p >= a.n) return 0.0f;
+    if (p >= a.n || p < -kHist) return 0.0f;  // outside the filter's support: tile padding only
     long long q;
     bool in_block = p >= 0;
     if (in_block) {
@@ -154,7 +154,7 @@ __device__ __forceinline__ float u8_to_f32(unsigned v) {
 
 template <bool RAW>
 __device__ __forceinline__ float2 source_iq(const IqDev &a, int s, int b, int p) {
-    if (p >= a.n) return make_float2(0.0f, 0.0f);
+    if (p >= a.n || p < -kHist) return make_float2(0.0f, 0.0f);  // outside the filter's support: tile padding only
     if (p < 0 && b == 0) return make_float2(a.zii[(long long)s * kHist + kHist + p], a.ziq[(long long)s * kHist + kHist + p]);
     const long long q = (long long)b * a.n + p - (p < 0 ? 1 : 0);
     if (RAW) {
