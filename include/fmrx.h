@@ -144,7 +144,11 @@ int fmrx_batch_process(fmrx_batch *, const uint8_t *iq, int n_blocks, const fmrx
 /* device -> device, asynchronous on the handle's stream; fmrx_batch_sync() waits. */
 int fmrx_batch_process_device(fmrx_batch *, const uint8_t *iq_device, int n_blocks, const fmrx_outputs *out_device);
 int fmrx_batch_sync(fmrx_batch *);
-void *fmrx_batch_cuda_stream(fmrx_batch *);         /* cudaStream_t of the compute stream */
+void *fmrx_batch_cuda_stream(fmrx_batch *);         /* cudaStream_t on which a call's outputs are completed */
+/* the device-resident path is a three-stage pipeline over three streams: phase 0 = front end + filters ahead of the
+ * PLLs, 1 = the PLLs, 2 = everything after them (+ output copies).  Consecutive fmrx_batch_process_device calls overlap:
+ * call k's PLLs run beside call k+1's phase 0 and call k-1's phase 2. */
+void *fmrx_batch_cuda_stream_phase(fmrx_batch *, int phase);
 long long fmrx_batch_launch_count(const fmrx_batch *); /* kernels launched by this handle so far */
 /* per-stream initial_offset of the RDS decoder (host int32[S]) */
 int fmrx_batch_rds_offsets(fmrx_batch *, int32_t *offsets);

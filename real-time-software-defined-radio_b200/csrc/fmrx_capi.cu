@@ -293,6 +293,15 @@ struct fmrx_batch {
     fmrx_rds_event *ev = nullptr;
     cudaStream_t s_in = nullptr, s_out = nullptr, s_cmp[2] = {nullptr, nullptr};
     cudaEvent_t e_in[kMaxChunks]{}, e_done[kMaxChunks]{}, e_out[kMaxChunks]{};
+    // device-resident pipeline: filters before the PLLs, the PLLs, and everything after them run on three streams, so
+    // that step k's (latency-bound, few-warp) PLL kernel overlaps step k+1's front end and step k-1's back end.  The
+    // signals crossing a phase boundary are double-buffered (`set`).
+    cudaStream_t s_a = nullptr, s_p = nullptr, s_c = nullptr;
+    cudaEvent_t ev_a[2]{}, ev_p[2]{}, ev_c[2]{};
+    bool ev_c_valid[2] = {false, false};
+    long long calls = 0;
+    int last_set = 0;
+    size_t set_if = 0, set_au = 0;  // elements per set of an IF-rate / audio-rate signal
     std::vector<void *> allocs;
     // optional per-stage device timing (fmrx_batch_profile): event pairs around every stage of every enqueued chain
     bool profiling = false;
@@ -308,6 +317,8 @@ struct fmrx_batch {
         for (void *p : allocs) cudaFree(p);
         for (auto e : prof_pool) cudaEventDestroy(e);
         for (int i = 0; i < kMaxChunks; ++i) { if (e_in[i]) cudaEventDestroy(e_in[i]); if (e_done[i]) cudaEventDestroy(e_done[i]); if (e_out[i]) cudaEventDestroy(e_out[i]); }
+        for (int i = 0; i < 2; ++i) { if (ev_a[i]) cudaEventDestroy(ev_a[i]); if (ev_p[i]) cudaEventDestroy(ev_p[i]); if (ev_c[i]) cudaEventDestroy(ev_c[i]); }
+        for (auto st : {s_a, s_p, s_c}) if (st) cudaStreamDestroy(st);
         if (s_in) cudaStreamDestroy(s_in);
         if (s_out) cudaStreamDestroy(s_out);
         for (auto s : s_cmp) if (s) cudaStreamDestroy(s);
@@ -332,6 +343,8 @@ int init_state(fmrx_batch *b) {
     CU(cudaMemcpyAsync(b->rds_pll_st, pll.data(), pll.size() * 4, cudaMemcpyHostToDevice, b->s_cmp[0]));
     CU(cudaStreamSynchronize(b->s_cmp[0]));
     b->block_id = 0;
+    b->calls = 0;
+    b->ev_c_valid[0] = b->ev_c_valid[1] = false;
     return FMRX_OK;
 }
 
@@ -348,13 +361,19 @@ struct StageScope {
 };
 #define STAGE(id) StageScope stage_scope_##id(b, st, id)
 
-// enqueue the whole chain for streams [s0, s0+ns) x nblk blocks on `st`
-int enqueue_chain(fmrx_batch *b, const uint8_t *iq, long long ld_iq, int s0, int ns, int nblk, const fmrx_outputs &o, cudaStream_t st) {
+// enqueue the whole chain for streams [s0, s0+ns) x nblk blocks: phase A (everything before the PLLs) on stA, the PLLs
+// on stP, phase C (everything after) on stC.  With three distinct streams the phases are chained by ev_a/ev_p of `set`.
+int enqueue_chain(fmrx_batch *b, const uint8_t *iq, long long ld_iq, int s0, int ns, int nblk, const fmrx_outputs &o, int set,
+                  cudaStream_t stA, cudaStream_t stP, cudaStream_t stC) {
     const long long before = launch_counter();
     const long long ldif = (long long)b->NB * NIF, lda = (long long)b->NB * b->n_audio, ldr = (long long)b->NB * NRDS;
-    auto IF = [&](float *p) { return p + (long long)s0 * ldif; };
+    auto IF = [&](float *p) { return p + (long long)s0 * ldif; };                                // single-buffered
+    auto IF2 = [&](float *p) { return p + (long long)set * (long long)b->set_if + (long long)s0 * ldif; };  // crosses a phase boundary
     auto AU = [&](float *p) { return p + (long long)s0 * lda; };
+    auto AU2 = [&](float *p) { return p + (long long)set * (long long)b->set_au + (long long)s0 * lda; };
     auto RD = [&](float *p) { return p + (long long)s0 * ldr; };
+    const bool piped = stA != stP;
+    cudaStream_t st = stA;
     const int ex = b->exact ? 1 : 0;
     // ---- rf_thread: unpack + deinterleave + LPF/10 + discriminator (src/fm_radio.cpp:66-84)
     FrontendJob f{};
@@ -376,43 +395,47 @@ int enqueue_chain(fmrx_batch *b, const uint8_t *iq, long long ld_iq, int s0, int
         STAGE(FMRX_STAGE_MONO);
         if (b->cfg.mode == 1) {
             ResampleJob r{};
-            r.x = IF(b->demod); r.y = AU(b->mono); r.zi = b->zi_mono + (long long)s0 * b->nzi_a; r.h = b->d_h_mono; r.ldx = ldif; r.ldy = lda;
+            r.x = IF(b->demod); r.y = AU2(b->mono); r.zi = b->zi_mono + (long long)s0 * b->nzi_a; r.h = b->d_h_mono; r.ldx = ldif; r.ldy = lda;
             r.n = NIF; r.n_ref = NIF; r.ny = b->n_audio; r.n_blocks = nblk; r.n_streams = ns; r.ntaps = b->audio_taps; r.nzi = b->nzi_a;
             r.decim = b->decim_a; r.up = b->up; r.gain_up = 0; r.exact = ex;
             LAUNCH(launch_resample(r, st));
         } else {
-            LAUNCH(fir(IF(b->demod), nullptr, AU(b->mono), b->zi_mono + (long long)s0 * b->nzi_a, b->nzi_a, b->h_mono.data(), ldif, lda, NIF, 5, SRC_PLAIN, ex, nblk));
+            LAUNCH(fir(IF(b->demod), nullptr, AU2(b->mono), b->zi_mono + (long long)s0 * b->nzi_a, b->nzi_a, b->h_mono.data(), ldif, lda, NIF, 5, SRC_PLAIN, ex, nblk));
         }
     }
     if (b->audio_on) {
         if (stereo_live) {
             STAGE(FMRX_STAGE_PILOT_BPF);
-            LAUNCH(fir(IF(b->demod), nullptr, IF(b->pilot), b->zi_pilot + (long long)s0 * b->nzi_a, b->nzi_a, b->h_pilot, ldif, ldif, NIF, 1, SRC_PLAIN, 1, st_blocks));
+            LAUNCH(fir(IF(b->demod), nullptr, IF2(b->pilot), b->zi_pilot + (long long)s0 * b->nzi_a, b->nzi_a, b->h_pilot, ldif, ldif, NIF, 1, SRC_PLAIN, 1, st_blocks));
         }
         if (stereo_live) {
             STAGE(FMRX_STAGE_STEREO_BPF);
-            LAUNCH(fir(IF(b->demod), nullptr, IF(b->sbpf), b->zi_sbpf + (long long)s0 * b->nzi_a, b->nzi_a, b->h_sbpf, ldif, ldif, NIF, 1, SRC_PLAIN, ex, st_blocks));
+            LAUNCH(fir(IF(b->demod), nullptr, IF2(b->sbpf), b->zi_sbpf + (long long)s0 * b->nzi_a, b->nzi_a, b->h_sbpf, ldif, ldif, NIF, 1, SRC_PLAIN, ex, st_blocks));
         }
     }
     // ---- rds_thread, filters before the PLL (:395, :400's BPF)
     if (b->rds_on) {
-        { STAGE(FMRX_STAGE_RDS_BPF); LAUNCH(fir(IF(b->demod), nullptr, IF(b->rbpf), b->zi_rbpf + (long long)s0 * kHist, kHist, b->h_rbpf, ldif, ldif, NIF, 1, SRC_PLAIN, 0, nblk)); }
+        { STAGE(FMRX_STAGE_RDS_BPF); LAUNCH(fir(IF(b->demod), nullptr, IF2(b->rbpf), b->zi_rbpf + (long long)s0 * kHist, kHist, b->h_rbpf, ldif, ldif, NIF, 1, SRC_PLAIN, 0, nblk)); }
         STAGE(FMRX_STAGE_RDS_SQ_BPF);
-        LAUNCH(fir(IF(b->rbpf), nullptr, IF(b->rsq), b->zi_sq + (long long)s0 * kHist, kHist, b->h_sq, ldif, ldif, NIF, 1, SRC_SQUARE, 0, nblk));
+        LAUNCH(fir(IF2(b->rbpf), nullptr, IF2(b->rsq), b->zi_sq + (long long)s0 * kHist, kHist, b->h_sq, ldif, ldif, NIF, 1, SRC_SQUARE, 0, nblk));
     }
     // ---- both PLLs, one lane per (stream, loop) (:233/:262 and :400)
+    if (piped) { CU(cudaEventRecord(b->ev_a[set], stA)); CU(cudaStreamWaitEvent(stP, b->ev_a[set], 0)); }
+    st = stP;
     {
         const PllParams pa{19e3f, 240e3f, 2.0f, 0.0f, 0.01f};
         const PllParams pr{114000.0f, 240000.0f, 0.5f, b->rds_phase, 0.001f};
         const bool a_on = b->audio_on && stereo_live;
         STAGE(FMRX_STAGE_PLL);
         if (a_on && b->rds_on && st_blocks == nblk) {
-            LAUNCH(launch_pll_blocks(IF(b->pilot), IF(b->nco), pa, b->pll_st + (long long)s0 * 6, IF(b->rsq), IF(b->rnco), pr, b->rds_pll_st + (long long)s0 * 6, ldif, ns, NIF, nblk, st));
+            LAUNCH(launch_pll_blocks(IF2(b->pilot), IF2(b->nco), pa, b->pll_st + (long long)s0 * 6, IF2(b->rsq), IF2(b->rnco), pr, b->rds_pll_st + (long long)s0 * 6, ldif, ns, NIF, nblk, st));
         } else {
-            if (a_on) LAUNCH(launch_pll_blocks(IF(b->pilot), IF(b->nco), pa, b->pll_st + (long long)s0 * 6, nullptr, nullptr, pa, nullptr, ldif, ns, NIF, st_blocks, st));
-            if (b->rds_on) LAUNCH(launch_pll_blocks(IF(b->rsq), IF(b->rnco), pr, b->rds_pll_st + (long long)s0 * 6, nullptr, nullptr, pr, nullptr, ldif, ns, NIF, nblk, st));
+            if (a_on) LAUNCH(launch_pll_blocks(IF2(b->pilot), IF2(b->nco), pa, b->pll_st + (long long)s0 * 6, nullptr, nullptr, pa, nullptr, ldif, ns, NIF, st_blocks, st));
+            if (b->rds_on) LAUNCH(launch_pll_blocks(IF2(b->rsq), IF2(b->rnco), pr, b->rds_pll_st + (long long)s0 * 6, nullptr, nullptr, pr, nullptr, ldif, ns, NIF, nblk, st));
         }
     }
+    if (piped) { CU(cudaEventRecord(b->ev_p[set], stP)); CU(cudaStreamWaitEvent(stC, b->ev_p[set], 0)); }
+    st = stC;
     // ---- stereo mix + LPF, combine, quantise (:240-252 / :269-299)
     if (b->audio_on) {
         const float *stereo = nullptr;
@@ -420,26 +443,26 @@ int enqueue_chain(fmrx_batch *b, const uint8_t *iq, long long ld_iq, int s0, int
             STAGE(FMRX_STAGE_STEREO_LPF);
             if (st_blocks < nblk) CU(cudaMemset2DAsync(AU(b->stereo), lda * 4, 0, (size_t)nblk * b->n_audio * 4, ns, st));
             if (b->cfg.mode == 1) {
-                LAUNCH(launch_multiply(IF(b->sbpf), IF(b->nco), IF(b->mixed), ldif, st_blocks * NIF, ns, st));
+                LAUNCH(launch_multiply(IF2(b->sbpf), IF2(b->nco), IF(b->mixed), ldif, st_blocks * NIF, ns, st));
                 ResampleJob r{};  // convolveWithDecimMode1(stereo_filt, mixed, stereo_coeff, stereo_initial, 5, 24), :245 (Q14)
                 r.x = IF(b->mixed); r.y = AU(b->stereo); r.zi = b->zi_stereo + (long long)s0 * b->nzi_a; r.h = b->d_h_stereo; r.ldx = ldif; r.ldy = lda;
                 r.n = NIF; r.n_ref = NIF; r.ny = b->n_audio; r.n_blocks = st_blocks; r.n_streams = ns; r.ntaps = b->audio_taps; r.nzi = b->nzi_a;
                 r.decim = 5; r.up = b->up; r.gain_up = 0; r.exact = ex;
                 LAUNCH(launch_resample(r, st));
             } else {
-                LAUNCH(fir(IF(b->sbpf), IF(b->nco), AU(b->stereo), b->zi_stereo + (long long)s0 * b->nzi_a, b->nzi_a, b->h_stereo.data(), ldif, lda, NIF, 5, SRC_MIX_LATE, ex, st_blocks));
+                LAUNCH(fir(IF2(b->sbpf), IF2(b->nco), AU(b->stereo), b->zi_stereo + (long long)s0 * b->nzi_a, b->nzi_a, b->h_stereo.data(), ldif, lda, NIF, 5, SRC_MIX_LATE, ex, st_blocks));
             }
             stereo = AU(b->stereo);
         }
         STAGE(FMRX_STAGE_COMBINE);
         CombineJob c{};
-        c.mono = AU(b->mono); c.stereo = stereo; c.audio = b->audio + (long long)s0 * lda * 2; c.audio_f = b->audio_f + (long long)s0 * lda * 2;
+        c.mono = AU2(b->mono); c.stereo = stereo; c.audio = b->audio + (long long)s0 * lda * 2; c.audio_f = b->audio_f + (long long)s0 * lda * 2;
         c.ld = lda; c.n_total = nblk * b->n_audio; c.n_streams = ns; c.mult = b->mult;
         LAUNCH(launch_combine(c, st));
     }
     // ---- rds_thread after the PLL (:404-411) and frame_thread
     if (b->rds_on) {
-        { STAGE(FMRX_STAGE_RDS_MIX_LPF); LAUNCH(fir(IF(b->rnco), IF(b->rbpf), IF(b->rlpf), b->zi_lpf + (long long)s0 * kHist, kHist, b->h_lpf3k, ldif, ldif, NIF, 1, SRC_MIX_HALF, 0, nblk)); }
+        { STAGE(FMRX_STAGE_RDS_MIX_LPF); LAUNCH(fir(IF2(b->rnco), IF2(b->rbpf), IF(b->rlpf), b->zi_lpf + (long long)s0 * kHist, kHist, b->h_lpf3k, ldif, ldif, NIF, 1, SRC_MIX_HALF, 0, nblk)); }
         ResampleJob r{};
         r.x = IF(b->rlpf); r.y = RD(b->rres); r.zi = b->zi_anti + (long long)s0 * (kTaps * 19 - 1); r.h = b->d_h_anti; r.ldx = ldif; r.ldy = ldr;
         r.n = NIF; r.n_ref = NIF + 1; r.ny = NRDS; r.n_blocks = nblk; r.n_streams = ns; r.ntaps = kTaps * 19; r.nzi = kTaps * 19 - 1;
@@ -452,6 +475,7 @@ int enqueue_chain(fmrx_batch *b, const uint8_t *iq, long long ld_iq, int s0, int
     }
     (void)o;
     b->launches += launch_counter() - before;
+    b->last_set = set;
     return FMRX_OK;
 }
 
@@ -516,6 +540,7 @@ int fmrx_batch_create(const fmrx_config *cfg, fmrx_batch **out) {
     b->rds_phase = (float)((double)phase_adj - kPi / 1.4);                              // :400
 
     const size_t S = b->S, NB = b->NB;
+    b->set_if = S * NB * NIF; b->set_au = S * NB * b->n_audio;
     // ---- carried state: one blob
     struct Seg { void **p; size_t bytes; };
     std::vector<Seg> segs = {
@@ -539,13 +564,13 @@ int fmrx_batch_create(const fmrx_config *cfg, fmrx_batch **out) {
     CU(b->dalloc(b->d_iq, S * NB * FMRX_BLOCK_BYTES));
     CU(b->dalloc(b->demod, S * NB * NIF));
     if (b->audio_on) {
-        CU(b->dalloc(b->mono, S * NB * b->n_audio)); CU(b->dalloc(b->pilot, S * NB * NIF)); CU(b->dalloc(b->nco, S * NB * NIF));
-        CU(b->dalloc(b->sbpf, S * NB * NIF)); CU(b->dalloc(b->stereo, S * NB * b->n_audio));
+        CU(b->dalloc(b->mono, 2 * S * NB * b->n_audio)); CU(b->dalloc(b->pilot, 2 * S * NB * NIF)); CU(b->dalloc(b->nco, 2 * S * NB * NIF));
+        CU(b->dalloc(b->sbpf, 2 * S * NB * NIF)); CU(b->dalloc(b->stereo, S * NB * b->n_audio));
         if (cfg->mode == 1) CU(b->dalloc(b->mixed, S * NB * NIF));
         CU(b->dalloc(b->audio, S * NB * b->n_audio * 2)); CU(b->dalloc(b->audio_f, S * NB * b->n_audio * 2));
     }
     if (b->rds_on) {
-        CU(b->dalloc(b->rbpf, S * NB * NIF)); CU(b->dalloc(b->rsq, S * NB * NIF)); CU(b->dalloc(b->rnco, S * NB * NIF)); CU(b->dalloc(b->rlpf, S * NB * NIF));
+        CU(b->dalloc(b->rbpf, 2 * S * NB * NIF)); CU(b->dalloc(b->rsq, 2 * S * NB * NIF)); CU(b->dalloc(b->rnco, 2 * S * NB * NIF)); CU(b->dalloc(b->rlpf, S * NB * NIF));
         CU(b->dalloc(b->rres, S * NB * NRDS)); CU(b->dalloc(b->rrrc, S * NB * NRDS));
         CU(b->dalloc(b->bits, S * NB * FMRX_MAX_BITS)); CU(b->dalloc(b->nbits, S * NB)); CU(b->dalloc(b->nev, S * NB)); CU(b->dalloc(b->ev, S * NB * FMRX_MAX_EVENTS));
         CU(cudaMemset(b->bits, 0, S * NB * FMRX_MAX_BITS));
@@ -553,6 +578,19 @@ int fmrx_batch_create(const fmrx_config *cfg, fmrx_batch **out) {
     }
     CU(cudaStreamCreateWithFlags(&b->s_in, cudaStreamNonBlocking)); CU(cudaStreamCreateWithFlags(&b->s_out, cudaStreamNonBlocking));
     for (auto &s : b->s_cmp) CU(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    {
+        // the PLL kernel is a few hundred single-warp CTAs that run for the whole step: give its stream the highest
+        // priority so those CTAs are placed as soon as any slot frees up instead of queueing behind the FIR grids
+        int least = 0, greatest = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CU(cudaStreamCreateWithPriority(&b->s_p, cudaStreamNonBlocking, greatest));
+        CU(cudaStreamCreateWithPriority(&b->s_c, cudaStreamNonBlocking, greatest < least ? greatest + 1 : least));
+        CU(cudaStreamCreateWithPriority(&b->s_a, cudaStreamNonBlocking, least));
+    }
+    for (int i = 0; i < 2; ++i) {
+        CU(cudaEventCreateWithFlags(&b->ev_a[i], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&b->ev_p[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&b->ev_c[i], cudaEventDisableTiming));
+    }
     for (int i = 0; i < kMaxChunks; ++i) {
         CU(cudaEventCreateWithFlags(&b->e_in[i], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&b->e_done[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&b->e_out[i], cudaEventDisableTiming));
@@ -566,11 +604,16 @@ int fmrx_batch_create(const fmrx_config *cfg, fmrx_batch **out) {
 void fmrx_batch_destroy(fmrx_batch *b) { delete b; }
 int fmrx_batch_audio_per_block(const fmrx_batch *b) { return b ? b->n_audio : 0; }
 long long fmrx_batch_launch_count(const fmrx_batch *b) { return b ? b->launches : 0; }
-void *fmrx_batch_cuda_stream(fmrx_batch *b) { return b ? (void *)b->s_cmp[0] : nullptr; }
+void *fmrx_batch_cuda_stream(fmrx_batch *b) { return b ? (void *)b->s_c : nullptr; }
+void *fmrx_batch_cuda_stream_phase(fmrx_batch *b, int phase) {
+    if (!b) return nullptr;
+    return (void *)(phase == 0 ? b->s_a : phase == 1 ? b->s_p : b->s_c);
+}
 
 int fmrx_batch_reset(fmrx_batch *b) {
     if (!b) return fail(FMRX_ERR_ARG, "null handle");
     CU(cudaSetDevice(b->cfg.device));
+    if (int e = fmrx_batch_sync(b)) return e;
     return init_state(b);
 }
 
@@ -578,6 +621,7 @@ int fmrx_batch_sync(fmrx_batch *b) {
     if (!b) return fail(FMRX_ERR_ARG, "null handle");
     CU(cudaSetDevice(b->cfg.device));
     CU(cudaStreamSynchronize(b->s_in)); CU(cudaStreamSynchronize(b->s_cmp[0])); CU(cudaStreamSynchronize(b->s_cmp[1])); CU(cudaStreamSynchronize(b->s_out));
+    CU(cudaStreamSynchronize(b->s_a)); CU(cudaStreamSynchronize(b->s_p)); CU(cudaStreamSynchronize(b->s_c));
     return FMRX_OK;
 }
 
@@ -587,8 +631,14 @@ int fmrx_batch_process_device(fmrx_batch *b, const uint8_t *iq_device, int n_blo
     CU(cudaSetDevice(b->cfg.device));
     fmrx_outputs none{};
     const fmrx_outputs &o = out_device ? *out_device : none;
-    if (int e = enqueue_chain(b, iq_device, (long long)n_blocks * FMRX_BLOCK_BYTES, 0, b->S, n_blocks, o, b->s_cmp[0])) return e;
-    if (int e = copy_outputs(b, 0, b->S, n_blocks, o, cudaMemcpyDeviceToDevice, b->s_cmp[0])) return e;
+    const int set = (int)(b->calls & 1);
+    // phase A of this call overwrites the buffer set phase C of the call before last was reading
+    if (b->ev_c_valid[set]) CU(cudaStreamWaitEvent(b->s_a, b->ev_c[set], 0));
+    if (int e = enqueue_chain(b, iq_device, (long long)n_blocks * FMRX_BLOCK_BYTES, 0, b->S, n_blocks, o, set, b->s_a, b->s_p, b->s_c)) return e;
+    if (int e = copy_outputs(b, 0, b->S, n_blocks, o, cudaMemcpyDeviceToDevice, b->s_c)) return e;
+    CU(cudaEventRecord(b->ev_c[set], b->s_c));
+    b->ev_c_valid[set] = true;
+    b->calls += 1;
     b->block_id += n_blocks;
     b->last_blocks = n_blocks;
     return FMRX_OK;
@@ -600,6 +650,7 @@ int fmrx_batch_process(fmrx_batch *b, const uint8_t *iq, int n_blocks, const fmr
     CU(cudaSetDevice(b->cfg.device));
     fmrx_outputs none{};
     const fmrx_outputs &o = out ? *out : none;
+    if (b->calls) { if (int e = fmrx_batch_sync(b)) return e; }  // drain the device-resident pipeline first
     // chunk the stream dimension so copies and kernels overlap; small batches go through in one piece
     const int chunks = b->S >= 64 ? (b->S >= 512 ? kMaxChunks : 4) : 1;
     const long long row = (long long)n_blocks * FMRX_BLOCK_BYTES;
@@ -610,7 +661,7 @@ int fmrx_batch_process(fmrx_batch *b, const uint8_t *iq, int n_blocks, const fmr
         CU(cudaMemcpyAsync(b->d_iq + (size_t)s0 * row, iq + (size_t)s0 * row, (size_t)ns * row, cudaMemcpyHostToDevice, b->s_in));
         CU(cudaEventRecord(b->e_in[c], b->s_in));
         CU(cudaStreamWaitEvent(cs, b->e_in[c], 0));
-        if (int e = enqueue_chain(b, b->d_iq, row, s0, ns, n_blocks, o, cs)) return e;
+        if (int e = enqueue_chain(b, b->d_iq, row, s0, ns, n_blocks, o, 0, cs, cs, cs)) return e;
         CU(cudaEventRecord(b->e_done[c], cs));
         CU(cudaStreamWaitEvent(b->s_out, b->e_done[c], 0));
         if (int e = copy_outputs(b, s0, ns, n_blocks, o, cudaMemcpyDeviceToHost, b->s_out)) return e;
@@ -645,7 +696,10 @@ int fmrx_batch_tap(fmrx_batch *b, int which, float *dst) {
     CU(cudaSetDevice(b->cfg.device));
     if (int e = fmrx_batch_sync(b)) return e;
     const size_t len = fmrx_batch_tap_len(b, which), w = len * b->last_blocks * 4;
-    CU(cudaMemcpy2D(dst, w, src[which], len * b->NB * 4, w, b->S, cudaMemcpyDeviceToHost));
+    const bool dbl = which == FMRX_TAP_MONO || which == FMRX_TAP_PILOT || which == FMRX_TAP_NCO || which == FMRX_TAP_STEREO_BPF || which == FMRX_TAP_RDS_BPF ||
+                     which == FMRX_TAP_RDS_SQ || which == FMRX_TAP_RDS_NCO;
+    const float *base = src[which] + (dbl ? (size_t)b->last_set * (which == FMRX_TAP_MONO ? b->set_au : b->set_if) : 0);
+    CU(cudaMemcpy2D(dst, w, base, len * b->NB * 4, w, b->S, cudaMemcpyDeviceToHost));
     return FMRX_OK;
 }
 

@@ -152,6 +152,12 @@ __device__ __forceinline__ float u8_to_f32(unsigned v) {
     return fmaf(__uint_as_float(0x4B000000u | v), 0.0078125f, -65537.0f);
 }
 
+// byte K of a packed word -> float: one PRMT builds 0x4B0000bb, one FMA finishes (same exact result as u8_to_f32)
+template <int K>
+__device__ __forceinline__ float u8_lane_to_f32(unsigned packed) {
+    return fmaf(__uint_as_float(__byte_perm(packed, 0x4B000000u, 0x7440 | K)), 0.0078125f, -65537.0f);
+}
+
 template <bool RAW>
 __device__ __forceinline__ float2 source_iq(const IqDev &a, int s, int b, int p) {
     if (p >= a.n || p < -kHist) return make_float2(0.0f, 0.0f);  // outside the filter's support: tile padding only
@@ -179,7 +185,33 @@ __global__ void __launch_bounds__(CT + 32) fir151_iq_kernel(const IqDev a, const
     __shared__ float2 edge[CT + 1];  // edge[t+1] = last output of thread t; edge[0] = output just before the tile
     const int s = blockIdx.z, b = blockIdx.y, n0 = blockIdx.x * TO;
     const int P0 = D * n0 - OFF;
-    for (int i = threadIdx.x; i < G::SPAN; i += CT + 32) smq[G::phys(i)] = source_iq<RAW>(a, s, b, P0 + i);
+    if (RAW && (((uintptr_t)a.raw | (uintptr_t)a.ldx | (uintptr_t)(2 * a.n)) & 3) == 0) {
+        // Fast ingest: two complex samples (4 bytes) per lane per load, every load of the tile issued before the first
+        // one is consumed (memory-level parallelism PAIRS/160 = 33 per thread), then unpack + STS.  Pairs that touch
+        // the history (p < 0) or the block end go through the generic per-sample path.
+        constexpr int PAIRS = (G::SPAN + 1) / 2, NT = CT + 32, ITER = (PAIRS + NT - 1) / NT;
+        const uint8_t *row = a.raw + (long long)s * a.ldx + 2LL * b * a.n;
+        unsigned v[ITER];
+#pragma unroll
+        for (int it = 0; it < ITER; ++it) {
+            const int p = P0 + 2 * (threadIdx.x + it * NT);
+            v[it] = (p >= 0 && p + 1 < a.n && threadIdx.x + it * NT < PAIRS) ? __ldg(reinterpret_cast<const unsigned *>(row + 2 * p)) : 0u;
+        }
+#pragma unroll
+        for (int it = 0; it < ITER; ++it) {
+            const int j = threadIdx.x + it * NT, i = 2 * j, p = P0 + i;
+            if (j >= PAIRS) continue;
+            if (p >= 0 && p + 1 < a.n) {
+                smq[G::phys(i)] = make_float2(u8_lane_to_f32<0>(v[it]), u8_lane_to_f32<1>(v[it]));
+                if (i + 1 < G::SPAN) smq[G::phys(i + 1)] = make_float2(u8_lane_to_f32<2>(v[it]), u8_lane_to_f32<3>(v[it]));
+            } else {
+                smq[G::phys(i)] = source_iq<RAW>(a, s, b, p);
+                if (i + 1 < G::SPAN) smq[G::phys(i + 1)] = source_iq<RAW>(a, s, b, p + 1);
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < G::SPAN; i += CT + 32) smq[G::phys(i)] = source_iq<RAW>(a, s, b, P0 + i);
+    }
     __syncthreads();
 
     float ai[R], aq[R];

@@ -90,6 +90,7 @@ SIGNATURES = {
     "fmrx_batch_process_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "fmrx_batch_sync": (C.c_int, [C.c_void_p]),
     "fmrx_batch_cuda_stream": (C.c_void_p, [C.c_void_p]),
+    "fmrx_batch_cuda_stream_phase": (C.c_void_p, [C.c_void_p, C.c_int]),
     "fmrx_batch_launch_count": (C.c_longlong, [C.c_void_p]),
     "fmrx_batch_rds_offsets": (C.c_int, [C.c_void_p, i32p]),
     "fmrx_batch_tap_len": (C.c_int, [C.c_void_p, C.c_int]),
