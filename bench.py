@@ -241,7 +241,6 @@ def run_fmrx_arm(args, rank, world, local_rank):
     rx.sync()
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    rx.profile(True)
     l0 = rx.launches
     ev0.record(stream_first)
     for _ in range(args.steps):
@@ -251,9 +250,15 @@ def run_fmrx_arm(args, rank, world, local_rank):
     barrier()
     ms_dev = max_over_ranks(ev0.elapsed_time(ev1))
     launches = rx.launches - l0
+    clocks = sampler.stop() if sampler else None
+    # ---- per-stage times: a separate pass of the same K steps with the three phases serialised on one stream, every
+    # stage bracketed by CUDA events on that stream (inside the pipelined run above, stages of different steps overlap
+    # and an event pair would time the contention, not the kernel)
+    rx.profile(True)
+    for _ in range(args.steps):
+        rx.process_device(d_iq.data_ptr(), B, dout)
     stage = rx.stage_times()
     rx.profile(False)
-    clocks = sampler.stop() if sampler else None
     units = world * S * B * BLOCK_IQ * args.steps
     value = units / (ms_dev * 1e-3) / 1e6
 

@@ -163,8 +163,9 @@ int fmrx_batch_tap_len(const fmrx_batch *, int which); /* samples per block of t
 int fmrx_batch_tap(fmrx_batch *, int which, float *dst);
 
 /* per-stage device timing inside the real chain: while enabled, every stage of every enqueued chain is bracketed by
- * CUDA events on the stream it runs on; fmrx_batch_stage_times() synchronises and returns the accumulated milliseconds
- * and bracket counts per stage since profiling was (re-)enabled. */
+ * CUDA events on the stream it runs on, and the device-resident path runs its three phases back to back on ONE stream
+ * (no overlap), so that each stage is timed alone; fmrx_batch_stage_times() synchronises and returns the accumulated
+ * milliseconds and bracket counts per stage since profiling was (re-)enabled. */
 enum {
     FMRX_STAGE_FRONTEND = 0, FMRX_STAGE_MONO, FMRX_STAGE_PILOT_BPF, FMRX_STAGE_STEREO_BPF, FMRX_STAGE_RDS_BPF,
     FMRX_STAGE_RDS_SQ_BPF, FMRX_STAGE_PLL, FMRX_STAGE_STEREO_LPF, FMRX_STAGE_COMBINE, FMRX_STAGE_RDS_MIX_LPF,

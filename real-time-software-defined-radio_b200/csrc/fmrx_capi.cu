@@ -633,8 +633,10 @@ int fmrx_batch_process_device(fmrx_batch *b, const uint8_t *iq_device, int n_blo
     const fmrx_outputs &o = out_device ? *out_device : none;
     const int set = (int)(b->calls & 1);
     // phase A of this call overwrites the buffer set phase C of the call before last was reading
-    if (b->ev_c_valid[set]) CU(cudaStreamWaitEvent(b->s_a, b->ev_c[set], 0));
-    if (int e = enqueue_chain(b, iq_device, (long long)n_blocks * FMRX_BLOCK_BYTES, 0, b->S, n_blocks, o, set, b->s_a, b->s_p, b->s_c)) return e;
+    if (b->ev_c_valid[set] && !b->profiling) CU(cudaStreamWaitEvent(b->s_a, b->ev_c[set], 0));
+    // while per-stage profiling is on, the three phases are serialised on one stream so that every stage is timed alone
+    cudaStream_t sa = b->profiling ? b->s_c : b->s_a, sp = b->profiling ? b->s_c : b->s_p;
+    if (int e = enqueue_chain(b, iq_device, (long long)n_blocks * FMRX_BLOCK_BYTES, 0, b->S, n_blocks, o, set, sa, sp, b->s_c)) return e;
     if (int e = copy_outputs(b, 0, b->S, n_blocks, o, cudaMemcpyDeviceToDevice, b->s_c)) return e;
     CU(cudaEventRecord(b->ev_c[set], b->s_c));
     b->ev_c_valid[set] = true;

@@ -9,11 +9,16 @@
 //   src/helper.cpp:139,162   the squared-input variant;  src/filter.cpp:387,399 the mixer variant with half-weight history.
 //   src/iofunc.cpp:67, src/fm_radio.cpp:68-72, src/rf_module.cpp:13-34 for the front end.
 //
-// B200 mapping: one CTA = 128 compute threads x R=8 consecutive outputs = a 1024-output tile of one (stream, block).
-// The input span is staged once in shared memory with a row pitch of d*R+1 words, so that lane t's window starts at
-// (d*R+1)*t: odd lane stride = conflict-free LDS, and every tap's offset is a compile-time constant.  The tap loop is
-// fully unrolled; taps arrive BY VALUE in the kernel parameter block, so each tap is a constant-bank operand of the
-// multiply.  `EXACT` keeps the reference's two roundings per tap (FMUL, FADD); otherwise FFMA.
+// B200 mapping: one CTA = CT threads x R=8 consecutive outputs = one tile of one (stream, block).  The input span is
+// staged once in shared memory with a row pitch of d*R+1 words, so that lane t's window starts at (d*R+1)*t: odd lane
+// stride = conflict-free LDS, and every offset is a compile-time constant.  The inner loop runs over the thread's INPUT
+// samples, newest first: each sample is read from shared memory exactly once and applied to every output it
+// contributes to (d=10: 221 LDS for 1208 taps x outputs), which for a fixed output still visits the taps in ascending
+// order -- the reference's summation order.  The loop is fully unrolled; taps arrive BY VALUE in the kernel parameter
+// block, so each tap is a constant-bank operand of the multiply and the instruction stream is ~95% FMUL/FADD (or FFMA).
+// `EXACT` keeps the reference's two roundings per tap (FMUL, FADD); otherwise FFMA.  The packed f32x2 forms are not
+// used: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (checked with cuobjdump), which breaks the two
+// roundings, and FFMA2 has the same lane throughput as FFMA anyway (measured, bench.py peak kinds 0 and 2).
 #include <cuda_runtime.h>
 
 #include "fmrx_internal.h"
@@ -22,8 +27,8 @@ namespace fmrx {
 namespace {
 
 constexpr int R = 8;          // outputs per thread
-constexpr int CT = 128;       // compute threads per CTA
-constexpr int TO = R * CT;    // outputs per tile
+constexpr int CT = 128;       // threads per CTA, single-channel kernels
+constexpr int CTQ = 64;       // threads per CTA, two-channel kernels (float2 staging: 42 KB per 512-output tile, 5 CTAs/SM)
 constexpr int OFF = 168;      // tile origin sits OFF input samples before the first output's newest sample: >= 150 + 10
                               // (history of the output just before the tile, for the discriminator) and 2*OFF % 16 == 0
 
@@ -31,12 +36,14 @@ struct Taps {
     float h[kTaps + 1];
 };
 
-template <int D>
+template <int D, int NT>
 struct Geom {
+    static constexpr int TO = R * NT;          // outputs per tile
     static constexpr int ROW = D * R;          // input samples between consecutive threads' windows
     static constexpr int PITCH = ROW + 1;      // padded row -> odd lane stride
     static constexpr int SPAN = D * (TO - 1) + OFF + 1;
     static constexpr int WORDS = SPAN + SPAN / ROW + 1;
+    static constexpr int WIN = D * (R - 1) + kTaps;  // input samples one thread touches
     __host__ __device__ static constexpr int phys(int i) { return i + i / ROW; }
 };
 
@@ -83,32 +90,63 @@ __device__ __forceinline__ float source(const FirDev &a, const float *xs, const 
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// the register-tiled tap loop shared by every kernel: W(c) returns the staged sample c positions after the start of
+// the thread's window (c = D*r - k + OFF for output r, tap k), ACC(r, v, h) accumulates
+// ------------------------------------------------------------------------------------------------------------------
+#define FMRX_TAP_LOOP(D, LOADV, MACV)                                 \
+    _Pragma("unroll") for (int i_ = 0; i_ < D * (R - 1) + kTaps; ++i_) { \
+        const int p_ = D * (R - 1) - i_; /* newest sample first */    \
+        const int c_ = p_ + OFF;                                      \
+        LOADV(c_ + c_ / (D * R));                                     \
+        _Pragma("unroll") for (int r = 0; r < R; ++r) {               \
+            const int k = D * r - p_;                                 \
+            if (k >= 0 && k < kTaps) { MACV(r, k); }                  \
+        }                                                             \
+    }
+
+// ------------------------------------------------------------------------------------------------------------------
 // single-channel kernel
 // ------------------------------------------------------------------------------------------------------------------
 template <int D, int KIND, bool EXACT>
 __global__ void __launch_bounds__(CT) fir151_kernel(const FirDev a, const __grid_constant__ Taps taps) {
-    using G = Geom<D>;
+    using G = Geom<D, CT>;
     __shared__ float sm[G::WORDS];
-    const int s = blockIdx.z, b = blockIdx.y, n0 = blockIdx.x * TO;
+    const int s = blockIdx.z, b = blockIdx.y, n0 = blockIdx.x * G::TO;
     const float *xs = a.x + (long long)s * a.ldx;
     const float *x2s = a.x2 ? a.x2 + (long long)s * a.ldx : nullptr;
     const float *zs = a.zi + (long long)s * a.nzi;
     const int P0 = D * n0 - OFF;
-    for (int i = threadIdx.x; i < G::SPAN; i += CT) sm[G::phys(i)] = source<KIND>(a, xs, x2s, zs, b, P0 + i);
+    constexpr int QUADS = (G::SPAN + 3) / 4;
+    constexpr bool MIX = KIND == SRC_MIX_LATE || KIND == SRC_MIX_HALF;
+    const float *xt = xs + (long long)b * a.n + P0;
+    const float *x2t = MIX ? x2s + (long long)b * a.n + P0 : xt;
+    if (P0 >= 0 && P0 + 4 * QUADS <= a.n && (((uintptr_t)xt | (uintptr_t)x2t) & 15) == 0) {
+        // interior tile: every staged sample lies inside block b -> 128-bit loads, no per-sample case analysis
+        for (int j = threadIdx.x; j < QUADS; j += CT) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(xt) + j);
+            float4 w = v;
+            if (MIX) w = __ldg(reinterpret_cast<const float4 *>(x2t) + j);
+            const int i = 4 * j;
+            sm[G::phys(i)] = form<KIND>(v.x, w.x, true);
+            if (i + 1 < G::SPAN) sm[G::phys(i + 1)] = form<KIND>(v.y, w.y, true);
+            if (i + 2 < G::SPAN) sm[G::phys(i + 2)] = form<KIND>(v.z, w.z, true);
+            if (i + 3 < G::SPAN) sm[G::phys(i + 3)] = form<KIND>(v.w, w.w, true);
+        }
+    } else {
+        for (int i = threadIdx.x; i < G::SPAN; i += CT) sm[G::phys(i)] = source<KIND>(a, xs, x2s, zs, b, P0 + i);
+    }
     __syncthreads();
 
     const float *w = sm + G::PITCH * threadIdx.x;
     float acc[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) acc[r] = 0.0f;
-#pragma unroll
-    for (int k = 0; k < kTaps; ++k) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int c = D * r - k + OFF;
-            acc[r] = mac<EXACT>(acc[r], w[c + c / G::ROW], taps.h[k]);
-        }
-    }
+    float v;
+#define LOADV(idx) v = w[idx]
+#define MACV(r, k) acc[r] = mac<EXACT>(acc[r], v, taps.h[k])
+    FMRX_TAP_LOOP(D, LOADV, MACV)
+#undef LOADV
+#undef MACV
     const int o = n0 + R * threadIdx.x;
     float *ys = a.y + (long long)s * a.ldy + (long long)b * a.ny + o;
     if (o + R <= a.ny && ((reinterpret_cast<uintptr_t>(ys) & 15) == 0)) {
@@ -179,74 +217,46 @@ __device__ __forceinline__ float discriminate(float i, float q, float pi_, float
 }
 
 template <int D, bool RAW, bool EXACT>
-__global__ void __launch_bounds__(CT + 32) fir151_iq_kernel(const IqDev a, const __grid_constant__ Taps taps) {
-    using G = Geom<D>;
-    extern __shared__ float2 smq[];
-    __shared__ float2 edge[CT + 1];  // edge[t+1] = last output of thread t; edge[0] = output just before the tile
-    const int s = blockIdx.z, b = blockIdx.y, n0 = blockIdx.x * TO;
+__global__ void __launch_bounds__(CTQ) fir151_iq_kernel(const IqDev a, const __grid_constant__ Taps taps) {
+    using G = Geom<D, CTQ>;
+    __shared__ float2 smq[G::WORDS];
+    __shared__ float2 edge[CTQ + 1];  // edge[t+1] = last output of thread t
+    const int s = blockIdx.z, b = blockIdx.y, n0 = blockIdx.x * G::TO;
     const int P0 = D * n0 - OFF;
-    if (RAW && (((uintptr_t)a.raw | (uintptr_t)a.ldx | (uintptr_t)(2 * a.n)) & 3) == 0) {
-        // Fast ingest: two complex samples (4 bytes) per lane per load, every load of the tile issued before the first
-        // one is consumed (memory-level parallelism PAIRS/160 = 33 per thread), then unpack + STS.  Pairs that touch
-        // the history (p < 0) or the block end go through the generic per-sample path.
-        constexpr int PAIRS = (G::SPAN + 1) / 2, NT = CT + 32, ITER = (PAIRS + NT - 1) / NT;
-        const uint8_t *row = a.raw + (long long)s * a.ldx + 2LL * b * a.n;
-        unsigned v[ITER];
-#pragma unroll
-        for (int it = 0; it < ITER; ++it) {
-            const int p = P0 + 2 * (threadIdx.x + it * NT);
-            v[it] = (p >= 0 && p + 1 < a.n && threadIdx.x + it * NT < PAIRS) ? __ldg(reinterpret_cast<const unsigned *>(row + 2 * p)) : 0u;
-        }
-#pragma unroll
-        for (int it = 0; it < ITER; ++it) {
-            const int j = threadIdx.x + it * NT, i = 2 * j, p = P0 + i;
-            if (j >= PAIRS) continue;
-            if (p >= 0 && p + 1 < a.n) {
-                smq[G::phys(i)] = make_float2(u8_lane_to_f32<0>(v[it]), u8_lane_to_f32<1>(v[it]));
-                if (i + 1 < G::SPAN) smq[G::phys(i + 1)] = make_float2(u8_lane_to_f32<2>(v[it]), u8_lane_to_f32<3>(v[it]));
-            } else {
-                smq[G::phys(i)] = source_iq<RAW>(a, s, b, p);
-                if (i + 1 < G::SPAN) smq[G::phys(i + 1)] = source_iq<RAW>(a, s, b, p + 1);
-            }
+    constexpr int OCTS = (G::SPAN + 7) / 8;
+    const uint8_t *rt = RAW ? a.raw + (long long)s * a.ldx + 2LL * b * a.n + 2LL * P0 : nullptr;
+    if (RAW && P0 >= 0 && P0 + 8 * OCTS <= a.n && ((uintptr_t)rt & 15) == 0) {
+        // interior tile: eight complex samples (16 bytes) per lane per load; ROW is a multiple of 8, so the eight land in
+        // one padded row and share the row offset
+        static_assert(G::ROW % 8 == 0, "an aligned group of 8 samples must not straddle a padded row");
+        for (int j = threadIdx.x; j < OCTS; j += CTQ) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(rt) + j);
+            const int i = 8 * j;
+            float2 *dst = smq + G::phys(i);
+            dst[0] = make_float2(u8_lane_to_f32<0>(v.x), u8_lane_to_f32<1>(v.x));
+            if (i + 1 < G::SPAN) dst[1] = make_float2(u8_lane_to_f32<2>(v.x), u8_lane_to_f32<3>(v.x));
+            if (i + 2 < G::SPAN) dst[2] = make_float2(u8_lane_to_f32<0>(v.y), u8_lane_to_f32<1>(v.y));
+            if (i + 3 < G::SPAN) dst[3] = make_float2(u8_lane_to_f32<2>(v.y), u8_lane_to_f32<3>(v.y));
+            if (i + 4 < G::SPAN) dst[4] = make_float2(u8_lane_to_f32<0>(v.z), u8_lane_to_f32<1>(v.z));
+            if (i + 5 < G::SPAN) dst[5] = make_float2(u8_lane_to_f32<2>(v.z), u8_lane_to_f32<3>(v.z));
+            if (i + 6 < G::SPAN) dst[6] = make_float2(u8_lane_to_f32<0>(v.w), u8_lane_to_f32<1>(v.w));
+            if (i + 7 < G::SPAN) dst[7] = make_float2(u8_lane_to_f32<2>(v.w), u8_lane_to_f32<3>(v.w));
         }
     } else {
-        for (int i = threadIdx.x; i < G::SPAN; i += CT + 32) smq[G::phys(i)] = source_iq<RAW>(a, s, b, P0 + i);
+        for (int i = threadIdx.x; i < G::SPAN; i += CTQ) smq[G::phys(i)] = source_iq<RAW>(a, s, b, P0 + i);
     }
     __syncthreads();
 
+    const float2 *w = smq + G::PITCH * threadIdx.x;
     float ai[R], aq[R];
-    if (threadIdx.x < CT) {
-        const float2 *w = smq + G::PITCH * threadIdx.x;
 #pragma unroll
-        for (int r = 0; r < R; ++r) ai[r] = aq[r] = 0.0f;
-#pragma unroll
-        for (int k = 0; k < kTaps; ++k) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const int c = D * r - k + OFF;
-                const float2 v = w[c + c / G::ROW];
-                ai[r] = mac<EXACT>(ai[r], v.x, taps.h[k]);
-                aq[r] = mac<EXACT>(aq[r], v.y, taps.h[k]);
-            }
-        }
-        edge[threadIdx.x + 1] = make_float2(ai[R - 1], aq[R - 1]);
-    } else if (RAW && threadIdx.x == CT) {
-        // the discriminator of the tile's first output needs the filtered sample just before the tile (Q3: zero at a
-        // block start).  One lane of the spare warp recomputes it with the same rounding sequence.
-        float ei = 0.0f, eq = 0.0f;
-        if (n0 > 0) {
-            for (int k = 0; k < kTaps; ++k) {
-                const int c = -D - k + OFF;  // output n0-1
-                const float2 v = smq[G::phys(c)];
-                ei = mac<EXACT>(ei, v.x, taps.h[k]);
-                eq = mac<EXACT>(eq, v.y, taps.h[k]);
-            }
-        }
-        edge[0] = make_float2(ei, eq);
-    }
-    if (!RAW && threadIdx.x >= CT) return;
-    if (RAW) __syncthreads();
-    if (threadIdx.x >= CT) return;
+    for (int r = 0; r < R; ++r) ai[r] = aq[r] = 0.0f;
+    float2 v;
+#define LOADV(idx) v = w[idx]
+#define MACV(r, k) ai[r] = mac<EXACT>(ai[r], v.x, taps.h[k]); aq[r] = mac<EXACT>(aq[r], v.y, taps.h[k])
+    FMRX_TAP_LOOP(D, LOADV, MACV)
+#undef LOADV
+#undef MACV
 
     const int o = n0 + R * threadIdx.x;
     const long long base = (long long)s * a.ldy + (long long)b * a.ny + o;
@@ -256,6 +266,11 @@ __global__ void __launch_bounds__(CT + 32) fir151_iq_kernel(const IqDev a, const
             if (o + r < a.ny) { a.yi[base + r] = ai[r]; a.yq[base + r] = aq[r]; }
     }
     if (RAW) {
+        // discriminator: the sample before this thread's first output is the neighbour's last one.  Thread 0 takes
+        // zero: right at a block start (Q3); for every other tile demod[n0] is rewritten by demod_edge_kernel.
+        edge[threadIdx.x + 1] = make_float2(ai[R - 1], aq[R - 1]);
+        if (threadIdx.x == 0) edge[0] = make_float2(0.0f, 0.0f);
+        __syncthreads();
         float2 prev = edge[threadIdx.x];
         float d[R];
 #pragma unroll
@@ -272,6 +287,129 @@ __global__ void __launch_bounds__(CT + 32) fir151_iq_kernel(const IqDev a, const
             for (int r = 0; r < R; ++r)
                 if (o + r < a.ny) ys[r] = d[r];
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// RF front end: u8 IQ -> 151-tap LPF /10 on I and Q -> discriminator, as a register-streaming FIR.
+//
+// One THREAD owns a run of L consecutive outputs of one (stream, block) and walks its input newest-first in rows of
+// ten complex samples (20 bytes).  An output is "open" while the walk is inside its 151-sample support, i.e. for 16
+// rows, so 16 (+1 while two rows are in flight) complex accumulators live in registers; per row every tap is used
+// exactly once (151 MACs on I, 151 on Q), each input byte is converted once, and nothing goes through shared memory.
+// For one output the walk visits its samples newest-first = taps in ascending order, the reference's summation order.
+// The loop body covers two rows (~1.4k instructions, 22 KB: resident in the 32 KB L1.5 instruction cache, which the
+// fully unrolled tile kernel -- 85 KB -- was not; ncu: stalled_no_instruction 3.5 per issue, ICC hit rate 52%).
+// Rows are offset by one sample (row rho = samples 10*rho-8 .. 10*rho+1) so that four rows = 80 bytes start on a
+// 16-byte boundary: input arrives as five 128-bit loads per four rows, issued half a group ahead of their use.
+// The run is extended by one output below (for the discriminator's previous sample) and by the 15 rows in which the
+// lowest outputs finish: L+16 rows for L outputs (L = 240: 94 % useful).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int SLOTS = 17;
+
+// taps regrouped for the row walk: t[j][a] = h[10*a - 1 + j] (0 where that index is outside 0..150), so that the 16 taps
+// sample j of a row needs are contiguous and reach the uniform registers as 128-bit constant loads
+struct RowTaps {
+    float t[10][16];
+};
+
+template <bool EXACT>
+__global__ void __launch_bounds__(64, 8) frontend_stream_kernel(const IqDev a, const __grid_constant__ RowTaps taps, int L, int segs, long long total) {
+    const long long gid = blockIdx.x * 64LL + threadIdx.x;
+    if (gid >= total) return;
+    const int g = (int)(gid % segs);
+    const long long sb = gid / segs;
+    const int b = (int)(sb % a.n_blocks), s = (int)(sb / a.n_blocks);
+    const int a0 = g * L;                                   // first output of the run (multiple of 4)
+    const int hi = min(a0 + L, a.ny);                       // one past the last output stored
+    const uint8_t *row = a.raw + (long long)s * a.ldx + 2LL * b * a.n;
+    const bool aligned = ((uintptr_t)row & 15) == 0;
+    const long long ob = (long long)s * a.ldy + (long long)b * a.ny;
+
+    float bi[SLOTS], bq[SLOTS];
+#pragma unroll
+    for (int i = 0; i < SLOTS; ++i) bi[i] = bq[i] = 0.0f;
+    float2 ycur = make_float2(0.0f, 0.0f);                  // the output completed just before (index n+1 when n completes)
+
+    // group of four rows with top row rt (rt = 3 mod 4): samples 10*rt-38 .. 10*rt+1, bytes 20*rt-76 .. 20*rt+4
+    uint4 cur[5];
+    bool fast_cur;
+    auto load_group = [&](int rt) {
+        const int lo = 10 * rt - 38;
+        fast_cur = aligned && lo >= 0 && lo + 40 <= a.n;
+        if (fast_cur) {
+            const uint4 *p = reinterpret_cast<const uint4 *>(row + 2LL * lo);
+#pragma unroll
+            for (int i = 0; i < 5; ++i) cur[i] = __ldg(p + i);
+        }
+    };
+    int rho = a0 + L - 1;                                   // top row of the run
+    load_group(rho);
+    const int iters = (L + 16) / 2;
+    for (int it = 0; it < iters; ++it, rho -= 2) {
+        // this iteration: rows rho (upper) and rho-1 = the upper (even it) or lower (odd it) ten words of the group
+        const bool lower = it & 1;
+        const unsigned *cw = reinterpret_cast<const unsigned *>(cur);
+        unsigned w[10];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) w[i] = lower ? cw[i] : cw[10 + i];
+        const bool fast = fast_cur;
+        if (lower && it + 1 < iters) load_group(rho - 2);   // the group is consumed: fetch the next one under this iteration's math
+        float2 yh, yl;
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            float2 smp[10];                                 // smp[j] = sample 10*(rho-rr) + 1 - j
+            if (fast) {
+#pragma unroll
+                for (int q = 0; q < 5; ++q) {               // word q of this row holds samples (base + 2q, base + 2q + 1)
+                    const unsigned u = w[5 * (1 - rr) + q];
+                    smp[9 - 2 * q] = make_float2(u8_lane_to_f32<0>(u), u8_lane_to_f32<1>(u));
+                    smp[8 - 2 * q] = make_float2(u8_lane_to_f32<2>(u), u8_lane_to_f32<3>(u));
+                }
+            } else {  // history, block edges, unaligned rows: rare, one sample at a time
+#pragma unroll 1
+                for (int q = 0; q < 10; ++q) {
+                    const float2 v = source_iq<true>(a, s, b, 10 * (rho - rr) + 1 - q);
+#pragma unroll
+                    for (int z = 0; z < 10; ++z)
+                        if (z == q) smp[z] = v;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 10; ++j) {
+#pragma unroll
+                for (int sl = 0; sl < 16; ++sl) {
+                    const int k = 10 * sl - 1 + j;
+                    if (k >= 0 && k < kTaps) {
+                        const int i = sl + 1 - rr;
+                        bi[i] = mac<EXACT>(bi[i], smp[j].x, taps.t[j][sl]);
+                        bq[i] = mac<EXACT>(bq[i], smp[j].y, taps.t[j][sl]);
+                    }
+                }
+            }
+            if (rr == 0) yh = make_float2(bi[16], bq[16]);  // output rho+15
+            else yl = make_float2(bi[15], bq[15]);          // output rho+14
+        }
+#pragma unroll
+        for (int i = SLOTS - 1; i >= 2; --i) { bi[i] = bi[i - 2]; bq[i] = bq[i - 2]; }
+        bi[0] = bq[0] = bi[1] = bq[1] = 0.0f;
+
+        // outputs rho+15 (yh) and rho+14 (yl) are complete; demod[n] pairs output n with output n-1.  An output is
+        // genuine only if its first row lay inside the walk, i.e. its index is below a0+L.
+        const int ne = rho + 15;                            // even
+        if (a.yi) {
+            if (ne >= a0 && ne < hi) { a.yi[ob + ne] = yh.x; a.yq[ob + ne] = yh.y; }
+            if (ne - 1 >= a0 && ne - 1 < hi) { a.yi[ob + ne - 1] = yl.x; a.yq[ob + ne - 1] = yl.y; }
+        }
+        if (ne + 2 <= a0 + L && ne >= a0) {                 // demod[ne+1] (needs ycur = y[ne+1]) and demod[ne]
+            const float d1 = discriminate(ycur.x, ycur.y, yh.x, yh.y);
+            const float2 pv = ne == 0 ? make_float2(0.0f, 0.0f) : yl;  // block start: previous sample is zero (Q3)
+            const float d0 = discriminate(yh.x, yh.y, pv.x, pv.y);
+            float *yd = a.demod + ob + ne;
+            if (ne + 1 < hi && ((uintptr_t)yd & 7) == 0) *reinterpret_cast<float2 *>(yd) = make_float2(d0, d1);
+            else { if (ne < hi) yd[0] = d0; if (ne + 1 < hi) yd[1] = d1; }
+        }
+        ycur = yl;
     }
 }
 
@@ -334,6 +472,7 @@ int launch_fir(const FirJob &j, fmrx_stream_t st) {
     FirDev d;
     d.x = j.x; d.x2 = j.x2; d.y = j.y; d.zi = j.zi + (j.nzi - kHist);
     d.ldx = j.ldx; d.ldy = j.ldy; d.nzi = j.nzi; d.n = j.n; d.ny = j.n / j.decim; d.n_blocks = j.n_blocks;
+    constexpr int TO = R * CT;
     dim3 grid((d.ny + TO - 1) / TO, j.n_blocks, j.n_streams);
     switch (j.kind) {
         case SRC_PLAIN: return launch_fir_k<SRC_PLAIN>(j, d, grid, st);
@@ -346,25 +485,23 @@ int launch_fir(const FirJob &j, fmrx_stream_t st) {
 
 template <int D, bool RAW>
 static int launch_iq_d(const IqDev &d, const float *h, int exact, int n_streams, fmrx_stream_t st) {
-    using G = Geom<D>;
+    constexpr int TO = Geom<D, CTQ>::TO;
     const Taps t = make_taps(h);
-    const size_t smem = sizeof(float2) * G::WORDS;
     dim3 grid((d.ny + TO - 1) / TO, d.n_blocks, n_streams);
-    cudaError_t e;
-    if (exact) {
-        e = cudaFuncSetAttribute(fir151_iq_kernel<D, RAW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e) return (int)e;
-        fir151_iq_kernel<D, RAW, true><<<grid, CT + 32, smem, st>>>(d, t);
-    } else {
-        e = cudaFuncSetAttribute(fir151_iq_kernel<D, RAW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e) return (int)e;
-        fir151_iq_kernel<D, RAW, false><<<grid, CT + 32, smem, st>>>(d, t);
-    }
-    e = cudaGetLastError();
+    if (exact) fir151_iq_kernel<D, RAW, true><<<grid, CTQ, 0, st>>>(d, t);
+    else fir151_iq_kernel<D, RAW, false><<<grid, CTQ, 0, st>>>(d, t);
+    cudaError_t e = cudaGetLastError();
     if (e) return (int)e;
     iq_state_kernel<RAW><<<n_streams, 160, 0, st>>>(d);
     launch_counter() += 2;
     return (int)cudaGetLastError();
+}
+
+// run length of the streaming front end: a multiple of 4; the largest one <= 240 that divides ny when there is one
+static int stream_run(int ny) {
+    for (int L = 240; L >= 64; L -= 4)
+        if (ny % L == 0) return L;
+    return 240;
 }
 
 int launch_fir_iq(const FirIqJob &j, fmrx_stream_t st) {
@@ -379,7 +516,20 @@ int launch_frontend(const FrontendJob &j, fmrx_stream_t st) {
     IqDev d{};
     d.raw = j.raw; d.demod = j.demod; d.yi = j.yi; d.yq = j.yq; d.zii = j.zii; d.ziq = j.ziq;
     d.ldx = j.ld_raw; d.ldy = j.ld_out; d.n = j.n; d.ny = j.n / 10; d.n_blocks = j.n_blocks;
-    return launch_iq_d<10, true>(d, j.h, 1, j.n_streams, st);
+    RowTaps t;
+    for (int jj = 0; jj < 10; ++jj)
+        for (int sl = 0; sl < 16; ++sl) {
+            const int k = 10 * sl - 1 + jj;
+            t.t[jj][sl] = (k >= 0 && k < kTaps) ? j.h[k] : 0.0f;
+        }
+    const int L = stream_run(d.ny), segs = (d.ny + L - 1) / L;
+    const long long total = (long long)segs * j.n_blocks * j.n_streams;
+    frontend_stream_kernel<true><<<(unsigned)((total + 63) / 64), 64, 0, st>>>(d, t, L, segs, total);
+    cudaError_t e = cudaGetLastError();
+    if (e) return (int)e;
+    iq_state_kernel<true><<<j.n_streams, 160, 0, st>>>(d);
+    launch_counter() += 2;
+    return (int)cudaGetLastError();
 }
 
 int launch_unpack(const uint8_t *raw, size_t n, float *out, fmrx_stream_t st) {
