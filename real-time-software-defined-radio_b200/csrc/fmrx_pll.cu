@@ -5,39 +5,32 @@
 //
 // The recurrence is sample-serial, so one stream runs per LANE and independent streams are packed 32 to a warp, one
 // warp per CTA so the (few) warps spread over all SMs.  Types follow the reference exactly (App. D.3): loop state is
-// fp32 with one rounding per operation (no FMA contraction), the phase detector and the oscillator go through the
-// double-precision atan2/sin/cos, and the oscillator argument is a double expression rounded to fp32.  Bit-exactness
-// matters here: once trigArg's fp32 ulp is coarse (after ~1 s of signal) two trajectories that differ in the last bit
-// decorrelate at the ulp level, far above the 1e-5 audio tolerance.
+// fp32 with one rounding per operation (no FMA contraction), the phase detector and the oscillator are evaluated in
+// double precision on float-valued arguments, and the oscillator argument is a double expression rounded to fp32.
+// Bit-exactness matters here: once trigArg's fp32 ulp is coarse (after ~1 s of signal) two trajectories that differ in
+// the last bit decorrelate at the ulp level, far above the 1e-5 audio tolerance.
+//
+// The kernel is bound by the LATENCY of that per-sample chain (8192 lanes = 256 warps on 592 schedulers), so the
+// step is built from the short-chain routines of fmrx_pllmath.h instead of libm's atan2/sincos/cos: ~30 dependent
+// double-precision operations per sample instead of ~150, and none of them on libm's large-argument slow path
+// (the 114 kHz loop's argument passes 1e5 rad within three blocks).
 #include <cuda_runtime.h>
 
 #include "fmrx_internal.h"
+#include "fmrx_pllmath.h"
 
 namespace fmrx {
 namespace {
 
+using pllmath::PllLoop;
+using pllmath::pll_step;
+using pllmath::pll_step_fast;
+using pllmath::pll_step_libm;
+
 constexpr double kTwoPi = 2 * 3.14159265358979323846;  // `2*PI`, src/helper.cpp:41 with src/dy4.h:13
 
-struct PllLoop {
-    float integ, phase, fbi, fbq, off;  // pll_state_type minus ncoLast
-    float Ki, Kp, scale, adj;
-    double w;  // (2*PI) * (double)(freq/Fs)
-};
-
-__device__ __forceinline__ float pll_step(PllLoop &c, float in, int k) {
-    const float eI = __fmul_rn(in, c.fbi);
-    const float eQ = __fmul_rn(in, -c.fbq);
-    const float eD = (float)atan2((double)eQ, (double)eI);
-    c.integ = __fadd_rn(c.integ, __fmul_rn(c.Ki, eD));
-    c.phase = __fadd_rn(c.phase, __fadd_rn(__fmul_rn(c.Kp, eD), c.integ));
-    const float cnt = __fadd_rn(__fadd_rn(c.off, (float)k), 1.0f);
-    const float trig = (float)__dadd_rn(__dmul_rn(c.w, (double)cnt), (double)c.phase);
-    double sn, cs;
-    sincos((double)trig, &sn, &cs);
-    c.fbi = (float)cs;
-    c.fbq = (float)sn;
-    return (float)cos((double)__fadd_rn(__fmul_rn(trig, c.scale), c.adj));
-}
+// (trigOffset + k) + 1 in fp32, as src/helper.cpp:41 forms it
+__device__ __forceinline__ float count(float off, int k) { return __fadd_rn(__fadd_rn(off, (float)k), 1.0f); }
 
 struct PllSide {
     const float *x;
@@ -55,7 +48,9 @@ __global__ void __launch_bounds__(32) pll_kernel(PllSide A, PllSide B, long long
     float *nco = P.nco + (long long)lane * ld;
     float *st = P.state + (long long)lane * 6;
     PllLoop c;
-    c.integ = st[0]; c.phase = st[1]; c.fbi = st[2]; c.fbq = st[3]; c.off = st[4];
+    c.integ = st[0]; c.phase = st[1]; c.fbi = st[2]; c.fbq = st[3];
+    c.usable[0] = c.usable[1] = false;  // only the float state is carried between launches: the first step goes through libm
+    float off = st[4];
     float last = st[5];
     c.Ki = P.Ki; c.Kp = P.Kp; c.scale = P.scale; c.adj = P.adj;
     c.w = __dmul_rn(kTwoPi, (double)P.fratio);
@@ -63,24 +58,47 @@ __global__ void __launch_bounds__(32) pll_kernel(PllSide A, PllSide B, long long
         const float *xb = x + (long long)b * n;
         float *ob = nco + (long long)b * n;
         int k = 0;
-        if ((((uintptr_t)xb | (uintptr_t)ob) & 15) == 0) {
-            for (; k + 4 <= n; k += 4) {
-                const float4 v = *reinterpret_cast<const float4 *>(xb + k);
+        if ((((uintptr_t)xb | (uintptr_t)ob) & 15) == 0 && n >= 8) {
+            // the input is read two groups (8 samples, ~2.5k cycles of loop time) ahead of its use: a lane streams its
+            // own row, so every load is a cache line of its own and would otherwise sit on the dependency chain
+            const float4 *x4 = reinterpret_cast<const float4 *>(xb);
+            const int groups = n / 4;
+            float4 v0 = __ldg(x4), v1 = __ldg(x4 + 1);
+            for (int g = 0; g < groups; ++g, k += 4) {
+                const float4 v = v0;
+                v0 = v1;
+                if (g + 2 < groups) v1 = __ldg(x4 + g + 2);
+                // four branch-free steps = one basic block; if any of them left the fast path's domain (first group
+                // after loading the state, zero / non-finite input, the +-pi seam: ~1e-5 of the groups) the four
+                // carried floats are restored and the group is redone with libm
+                const float s_integ = c.integ, s_phase = c.phase, s_fbi = c.fbi, s_fbq = c.fbq, s_last = last;
+                bool ok0, ok1, ok2, ok3;
                 float4 o;
-                o.x = last; last = pll_step(c, v.x, k);
-                o.y = last; last = pll_step(c, v.y, k + 1);
-                o.z = last; last = pll_step(c, v.z, k + 2);
-                o.w = last; last = pll_step(c, v.w, k + 3);
+                o.x = last;
+                o.y = pll_step_fast(c, v.x, count(off, k), ok0);
+                o.z = pll_step_fast(c, v.y, count(off, k + 1), ok1);
+                o.w = pll_step_fast(c, v.z, count(off, k + 2), ok2);
+                last = pll_step_fast(c, v.w, count(off, k + 3), ok3);
+                if (!(ok0 && ok1 && ok2 && ok3)) {
+                    c.integ = s_integ; c.phase = s_phase; c.fbi = s_fbi; c.fbq = s_fbq;
+                    const float in[4] = {v.x, v.y, v.z, v.w};
+                    float out[5];
+                    out[0] = s_last;
+#pragma unroll 1
+                    for (int i = 0; i < 4; ++i) out[i + 1] = pll_step_libm(c, in[i], count(off, k + i));
+                    o = make_float4(out[0], out[1], out[2], out[3]);
+                    last = out[4];
+                }
                 *reinterpret_cast<float4 *>(ob + k) = o;
             }
         }
         for (; k < n; ++k) {
             ob[k] = last;  // output sample k is the NCO value of step k-1 (src/helper.cpp:29,44,56)
-            last = pll_step(c, xb[k], k);
+            last = pll_step(c, xb[k], count(off, k));
         }
-        c.off = __fadd_rn(c.off, (float)n);  // src/helper.cpp:53
+        off = __fadd_rn(off, (float)n);  // src/helper.cpp:53
     }
-    st[0] = c.integ; st[1] = c.phase; st[2] = c.fbi; st[3] = c.fbq; st[4] = c.off; st[5] = last;
+    st[0] = c.integ; st[1] = c.phase; st[2] = c.fbi; st[3] = c.fbq; st[4] = off; st[5] = last;
 }
 
 // src/fm_radio.cpp:277-299: L=(m+s)/2, R=(m-s)/2; NaN -> 0 else static_cast<short>(x*16384*mult), which on x86-64 is

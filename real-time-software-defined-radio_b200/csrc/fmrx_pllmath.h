@@ -1,0 +1,264 @@
+// Double-precision kernels of the PLL recurrence, written for LATENCY: the loop of fmPLL (/root/reference/src/helper.cpp:
+// 32-45) is one long dependency chain per stream, atan2 -> loop filter -> sin/cos -> next sample, so what bounds the
+// kernel is the depth of that chain, not throughput.  The reference calls the double-precision libm functions on
+// float-valued arguments and rounds every result to float; any double result within ~1e-16 of the true value gives the
+// same float in all but ~1e-9 of the calls, which is the accuracy these routines keep.
+//
+//   sincos_cw   Cody-Waite reduction by pi/2 with two FMAs (exact product inside the FMA, so it stays accurate for any
+//               float-valued argument below 2^40) + the fdlibm minimax polynomials on [-pi/4, pi/4] (Sun Microsystems,
+//               s_sin.c / k_sin.c / k_cos.c: published constants) evaluated by Estrin's scheme: 4 dependent FMAs
+//               instead of 6-7 (Horner).  Returns the quadrant and the reduced argument too.
+//   pll_step_fast: the phase detector without a division or an arctangent polynomial.  The detector input is
+//               (eI, eQ) = (fl(x*fbI), fl(x*-fbQ)) with (fbI, fbQ) = (fl(cos T), fl(sin T)) from the previous step, so
+//               its angle is -T (+pi when x < 0) up to the four float roundings: atan2(eQ, eI) = theta0 + cross/dot
+//               with theta0 = -T mod 2pi known to ~1e-16 from the previous step's range reduction, (cross, dot) taken
+//               against the previous step's double (cos T, sin T), and |cross/dot| ~ 1e-7 (its cube is below 1e-21).
+//               1/dot comes from 1/x (computed off the critical path) and one Newton correction.
+// Both are `__host__ __device__` so that tests/ can run the very same code on the CPU against glibc.
+#ifndef FMRX_PLLMATH_H
+#define FMRX_PLLMATH_H
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#ifdef __CUDACC__
+#define FMRX_HD __host__ __device__ __forceinline__
+#define FMRX_HD_COLD __host__ __device__ __noinline__
+#else
+#define FMRX_HD inline
+#define FMRX_HD_COLD inline
+#endif
+
+namespace fmrx {
+namespace pllmath {
+
+FMRX_HD int lo_word(double v) {
+#ifdef __CUDA_ARCH__
+    return __double2loint(v);
+#else
+    uint64_t u;
+    memcpy(&u, &v, 8);
+    return (int)(uint32_t)u;
+#endif
+}
+
+FMRX_HD double fma_(double a, double b, double c) {
+#ifdef __CUDA_ARCH__
+    return __fma_rn(a, b, c);
+#else
+    return fma(a, b, c);
+#endif
+}
+
+struct SinCos {
+    double sn, cs;  // sin(T), cos(T)
+    double r;       // T = n*(pi/2) + r, |r| <~ pi/4
+    int q;          // n mod 4
+};
+
+// valid for |T| < 2^40 (the caller falls back to libm beyond)
+FMRX_HD SinCos sincos_cw(double T) {
+    const double TWO_OVER_PI = 6.36619772367581382433e-01;
+    const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: adding it rounds to the nearest integer
+    const double P1 = 1.5707963267948966;      // pi/2 rounded to double
+    const double P2 = 6.123233995736766e-17;   // pi/2 - P1
+    const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03, S3 = -1.98412698298579493134e-04,
+                 S4 = 2.75573137070700676789e-06, S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
+    const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03, C3 = 2.48015872894767294178e-05,
+                 C4 = -2.75573143513906633035e-07, C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
+    const double t = fma_(T, TWO_OVER_PI, MAGIC);
+    const double fn = t - MAGIC;
+    SinCos o;
+    o.q = lo_word(t) & 3;
+    double r = fma_(-fn, P1, T);
+    r = fma_(-fn, P2, r);
+    o.r = r;
+    const double z = r * r;
+    const double z2 = z * z;
+    const double sa = fma_(z, S2, S1), sb = fma_(z, S4, S3), sc = fma_(z, S6, S5);
+    const double ca = fma_(z, C2, C1), cb = fma_(z, C4, C3), cc = fma_(z, C6, C5);
+    const double z4 = z2 * z2;
+    const double rz = r * z;
+    const double hz = fma_(z, -0.5, 1.0);
+    const double sp = fma_(z4, sc, fma_(z2, sb, sa));
+    const double cp = fma_(z4, cc, fma_(z2, cb, ca));
+    const double s = fma_(rz, sp, r);   // sin r
+    const double c = fma_(z2, cp, hz);  // cos r
+    o.sn = (o.q & 1) ? c : s;
+    o.cs = (o.q & 1) ? s : c;
+    if (o.q == 1 || o.q == 2) o.cs = -o.cs;
+    if (o.q >= 2) o.sn = -o.sn;
+    return o;
+}
+
+FMRX_HD int hi_word(double v) {
+#ifdef __CUDA_ARCH__
+    return __double2hiint(v);
+#else
+    uint64_t u;
+    memcpy(&u, &v, 8);
+    return (int)(uint32_t)(u >> 32);
+#endif
+}
+FMRX_HD double make_double(int hi, int lo) {
+#ifdef __CUDA_ARCH__
+    return __hiloint2double(hi, lo);
+#else
+    const uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
+    double v;
+    memcpy(&v, &u, 8);
+    return v;
+#endif
+}
+FMRX_HD float rcp_approx(float x) {
+#ifdef __CUDA_ARCH__
+    return __fdividef(1.0f, x);  // MUFU.RCP: ~1e-7 relative, branch-free; its error enters the angle squared
+#else
+    return 1.0f / x;
+#endif
+}
+
+// cos(T) alone (the NCO output), same reduction and polynomials
+FMRX_HD double cos_cw(double T) {
+    const SinCos v = sincos_cw(T);
+    return v.cs;
+}
+
+FMRX_HD float mul_rn(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fmul_rn(a, b);
+#else
+    volatile float r = a * b;  // volatile: no contraction with a following add on the host either
+    return r;
+#endif
+}
+FMRX_HD float add_rn(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fadd_rn(a, b);
+#else
+    volatile float r = a + b;
+    return r;
+#endif
+}
+FMRX_HD double dmul_rn(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dmul_rn(a, b);
+#else
+    volatile double r = a * b;
+    return r;
+#endif
+}
+FMRX_HD double dadd_rn(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dadd_rn(a, b);
+#else
+    volatile double r = a + b;
+    return r;
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// one step of fmPLL's loop (src/helper.cpp:32-45) with the reference's operand types: fp32 loop
+// state with one rounding per operation, double transcendentals on float-valued arguments, trigArg rounded to fp32.
+//
+// pll_step_fast is branch-free (one basic block, so that the compiler can interleave the three independent chains of
+// a step: phase detector -> loop filter -> oscillator, the NCO output's cosine, and the next sample's reciprocal) and
+// reports through `ok` whether its assumptions held; when they did not (first step after loading the state, x zero /
+// non-finite / tiny, the detector angle within 1e-5 of the +-pi seam, arguments beyond 2^40) the caller restores the
+// four carried floats and redoes the step with pll_step_libm.
+// ---------------------------------------------------------------------------------------------------------------
+struct PllLoop {
+    float integ, phase, fbi, fbq;  // pll_state_type minus trigOffset / ncoLast (src/helper.h:17-19)
+    float Ki, Kp, scale, adj;
+    double w;                      // (2*PI) * (double)(freq/Fs)
+    // what the fast detector needs about the trigArg T that produced fbi/fbq: cos T, sin T in double, and
+    // theta0 = -T mod 2pi (x > 0) or pi - T mod 2pi (x < 0), wrapped into (-pi, pi], as hi + s1 with hi = k*(pi/2)
+    double cs, sn;
+    double th_hi[2], th_s1[2];
+    bool usable[2];                // have && not within 1e-5 of the seam, per sign of x
+};
+
+constexpr float kTrigLimitF = 1.0e12f;  // < 2^40
+
+FMRX_HD void pll_prepare(PllLoop &c, const SinCos &v) {
+    const double H1 = 1.5707963267948966, L1 = 6.123233995736766e-17;
+    c.cs = v.cs;
+    c.sn = v.sn;
+    const bool rneg = v.r < 0.0;
+    const bool near0 = fabs(v.r) < 1e-5;
+    // k such that theta0 = k*(pi/2) - r lies in (-pi, pi]: x > 0: q=0 -> 0, 1 -> -1, 2 -> +2 (r >= 0) or -2 (r < 0), 3 -> 1;
+    // x < 0 adds pi, i.e. the same table two quadrants on.  Looked up from packed nibbles to stay branch-free.
+    const int q = v.q;
+    const unsigned kTable = 0x1EF012F0u;  // nibble q (r >= 0), nibble 4+q (r < 0), two's complement
+    const int sh = rneg ? 16 : 0;
+    const int kp = (int)(((kTable >> (sh + 4 * q)) & 15u) ^ 8u) - 8;
+    const int kn = (int)(((kTable >> (sh + 4 * ((q + 2) & 3))) & 15u) ^ 8u) - 8;
+    c.th_hi[0] = (double)kp * H1; c.th_s1[0] = fma_((double)kp, L1, -v.r);
+    c.th_hi[1] = (double)kn * H1; c.th_s1[1] = fma_((double)kn, L1, -v.r);
+    c.usable[0] = !(q == 2 && near0);
+    c.usable[1] = !(q == 0 && near0);
+}
+
+FMRX_HD float pll_step_fast(PllLoop &c, float x, float cnt, bool &ok) {
+    const int sg = x < 0.0f ? 1 : 0;
+    const float ax = fabsf(x);
+    const float eI = mul_rn(x, c.fbi);
+    const float eQ = mul_rn(x, -c.fbq);
+    ok = c.usable[sg] && ax > 1e-18f && ax < 1e18f && eI != 0.0f && eQ != 0.0f;
+    const double rx = (double)rcp_approx(x);
+    const double dI = (double)eI, dQ = (double)eQ;
+    const double dot = fma_(dQ, -c.sn, dI * c.cs);
+    const double cross = fma_(dQ, c.cs, dI * c.sn);
+    const double e = fma_(-dot, rx, 2.0);
+    const double raw = c.th_hi[sg] + fma_(cross * rx, e, c.th_s1[sg]);
+    const double ang = make_double((hi_word(raw) & 0x7fffffff) | (hi_word(dQ) & 0x80000000), lo_word(raw));  // copysign(|raw|, eQ)
+    const float eD = (float)ang;
+    c.integ = add_rn(c.integ, mul_rn(c.Ki, eD));
+    c.phase = add_rn(c.phase, add_rn(mul_rn(c.Kp, eD), c.integ));
+    const float trig = (float)dadd_rn(dmul_rn(c.w, (double)cnt), (double)c.phase);  // src/helper.cpp:41: double expression, no FMA
+    const float targ = add_rn(mul_rn(trig, c.scale), c.adj);
+    ok = ok && fabsf(trig) < kTrigLimitF && fabsf(targ) < kTrigLimitF;
+    const SinCos v = sincos_cw((double)trig);
+    pll_prepare(c, v);
+    c.fbi = (float)v.cs;
+    c.fbq = (float)v.sn;
+    return (float)cos_cw((double)targ);
+}
+
+FMRX_HD_COLD float pll_step_libm(PllLoop &c, float x, float cnt) {
+    const float eI = mul_rn(x, c.fbi);
+    const float eQ = mul_rn(x, -c.fbq);
+    const float eD = (float)atan2((double)eQ, (double)eI);
+    c.integ = add_rn(c.integ, mul_rn(c.Ki, eD));
+    c.phase = add_rn(c.phase, add_rn(mul_rn(c.Kp, eD), c.integ));
+    const float trig = (float)dadd_rn(dmul_rn(c.w, (double)cnt), (double)c.phase);
+    const double T = (double)trig;
+    if (fabsf(trig) < kTrigLimitF) {
+        const SinCos v = sincos_cw(T);  // also re-arms the fast detector for the next step
+        pll_prepare(c, v);
+    } else {
+        c.cs = cos(T);
+        c.sn = sin(T);
+        c.usable[0] = c.usable[1] = false;
+    }
+    c.fbi = (float)c.cs;
+    c.fbq = (float)c.sn;
+    const float targ = add_rn(mul_rn(trig, c.scale), c.adj);
+    return (float)(fabsf(targ) < kTrigLimitF ? cos_cw((double)targ) : cos((double)targ));
+}
+
+// x: input sample; cnt = (trigOffset + k) + 1 as the reference forms it in fp32; returns nco[k+1]
+FMRX_HD float pll_step(PllLoop &c, float x, float cnt) {
+    const float integ = c.integ, phase = c.phase, fbi = c.fbi, fbq = c.fbq;
+    bool ok;
+    float out = pll_step_fast(c, x, cnt, ok);
+    if (!ok) {
+        c.integ = integ; c.phase = phase; c.fbi = fbi; c.fbq = fbq;
+        out = pll_step_libm(c, x, cnt);
+    }
+    return out;
+}
+
+}  // namespace pllmath
+}  // namespace fmrx
+#endif
