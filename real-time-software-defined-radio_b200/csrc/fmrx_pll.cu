@@ -22,8 +22,10 @@
 namespace fmrx {
 namespace {
 
-using pllmath::PllLoop;
-using pllmath::pll_step;
+using pllmath::PllCarry;
+using pllmath::PllCoef;
+using pllmath::PllFast;
+using pllmath::PllLibmOut;
 using pllmath::pll_step_fast;
 using pllmath::pll_step_libm;
 
@@ -47,13 +49,19 @@ __global__ void __launch_bounds__(32) pll_kernel(PllSide A, PllSide B, long long
     const float *x = P.x + (long long)lane * ld;
     float *nco = P.nco + (long long)lane * ld;
     float *st = P.state + (long long)lane * 6;
-    PllLoop c;
-    c.integ = st[0]; c.phase = st[1]; c.fbi = st[2]; c.fbq = st[3];
-    c.usable[0] = c.usable[1] = false;  // only the float state is carried between launches: the first step goes through libm
+    PllCarry c{st[0], st[1], st[2], st[3]};
+    PllFast f;
+    pllmath::pll_disarm(f);  // only the float state is carried between launches: the first group goes through libm
     float off = st[4];
     float last = st[5];
-    c.Ki = P.Ki; c.Kp = P.Kp; c.scale = P.scale; c.adj = P.adj;
-    c.w = __dmul_rn(kTwoPi, (double)P.fratio);
+    const PllCoef p{P.Ki, P.Kp, P.scale, P.adj, __dmul_rn(kTwoPi, (double)P.fratio)};
+    // the libm path, out of line: one step, everything by value
+    auto slow = [&](float xin, float cnt) {
+        const PllLibmOut o = pll_step_libm(c, p, xin, cnt);
+        c = o.c;
+        pllmath::pll_rearm(f, o.trig);
+        return o.nco;
+    };
     for (int b = 0; b < n_blocks; ++b) {
         const float *xb = x + (long long)b * n;
         float *ob = nco + (long long)b * n;
@@ -71,30 +79,29 @@ __global__ void __launch_bounds__(32) pll_kernel(PllSide A, PllSide B, long long
                 // four branch-free steps = one basic block; if any of them left the fast path's domain (first group
                 // after loading the state, zero / non-finite input, the +-pi seam: ~1e-5 of the groups) the four
                 // carried floats are restored and the group is redone with libm
-                const float s_integ = c.integ, s_phase = c.phase, s_fbi = c.fbi, s_fbq = c.fbq, s_last = last;
+                const PllCarry saved = c;
+                const float s_last = last;
                 bool ok0, ok1, ok2, ok3;
                 float4 o;
                 o.x = last;
-                o.y = pll_step_fast(c, v.x, count(off, k), ok0);
-                o.z = pll_step_fast(c, v.y, count(off, k + 1), ok1);
-                o.w = pll_step_fast(c, v.z, count(off, k + 2), ok2);
-                last = pll_step_fast(c, v.w, count(off, k + 3), ok3);
+                o.y = pll_step_fast(c, f, p, v.x, count(off, k), ok0);
+                o.z = pll_step_fast(c, f, p, v.y, count(off, k + 1), ok1);
+                o.w = pll_step_fast(c, f, p, v.z, count(off, k + 2), ok2);
+                last = pll_step_fast(c, f, p, v.w, count(off, k + 3), ok3);
                 if (!(ok0 && ok1 && ok2 && ok3)) {
-                    c.integ = s_integ; c.phase = s_phase; c.fbi = s_fbi; c.fbq = s_fbq;
-                    const float in[4] = {v.x, v.y, v.z, v.w};
-                    float out[5];
-                    out[0] = s_last;
-#pragma unroll 1
-                    for (int i = 0; i < 4; ++i) out[i + 1] = pll_step_libm(c, in[i], count(off, k + i));
-                    o = make_float4(out[0], out[1], out[2], out[3]);
-                    last = out[4];
+                    c = saved;
+                    o.x = s_last;
+                    o.y = slow(v.x, count(off, k));
+                    o.z = slow(v.y, count(off, k + 1));
+                    o.w = slow(v.z, count(off, k + 2));
+                    last = slow(v.w, count(off, k + 3));
                 }
                 *reinterpret_cast<float4 *>(ob + k) = o;
             }
         }
         for (; k < n; ++k) {
             ob[k] = last;  // output sample k is the NCO value of step k-1 (src/helper.cpp:29,44,56)
-            last = pll_step(c, xb[k], count(off, k));
+            last = slow(xb[k], count(off, k));
         }
         off = __fadd_rn(off, (float)n);  // src/helper.cpp:53
     }

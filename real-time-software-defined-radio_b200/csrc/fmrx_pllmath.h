@@ -167,23 +167,30 @@ FMRX_HD double dadd_rn(double a, double b) {
 // non-finite / tiny, the detector angle within 1e-5 of the +-pi seam, arguments beyond 2^40) the caller restores the
 // four carried floats and redoes the step with pll_step_libm.
 // ---------------------------------------------------------------------------------------------------------------
-struct PllLoop {
-    float integ, phase, fbi, fbq;  // pll_state_type minus trigOffset / ncoLast (src/helper.h:17-19)
+struct PllCarry {  // pll_state_type minus trigOffset / ncoLast (src/helper.h:17-19)
+    float integ, phase, fbi, fbq;
+};
+struct PllCoef {
     float Ki, Kp, scale, adj;
-    double w;                      // (2*PI) * (double)(freq/Fs)
-    // what the fast detector needs about the trigArg T that produced fbi/fbq: cos T, sin T in double, and
-    // theta0 = -T mod 2pi (x > 0) or pi - T mod 2pi (x < 0), wrapped into (-pi, pi], as hi + s1 with hi = k*(pi/2)
+    double w;  // (2*PI) * (double)(freq/Fs)
+};
+// what the fast detector needs about the trigArg T that produced fbi/fbq: cos T, sin T in double, and
+// theta0 = -T mod 2pi (x > 0) or pi - T mod 2pi (x < 0), wrapped into (-pi, pi], as hi + s1 with hi = k*(pi/2).
+// Separate scalars: an array indexed by the sign of x would live in local memory.
+struct PllFast {
     double cs, sn;
-    double th_hi[2], th_s1[2];
-    bool usable[2];                // have && not within 1e-5 of the seam, per sign of x
+    double th_hi_p, th_s1_p, th_hi_n, th_s1_n;
+    bool usable_p, usable_n;  // armed and not within 1e-5 of the seam, for x > 0 / x < 0
 };
 
 constexpr float kTrigLimitF = 1.0e12f;  // < 2^40
 
-FMRX_HD void pll_prepare(PllLoop &c, const SinCos &v) {
+FMRX_HD void pll_disarm(PllFast &f) { f.usable_p = f.usable_n = false; }
+
+FMRX_HD void pll_prepare(PllFast &f, const SinCos &v) {
     const double H1 = 1.5707963267948966, L1 = 6.123233995736766e-17;
-    c.cs = v.cs;
-    c.sn = v.sn;
+    f.cs = v.cs;
+    f.sn = v.sn;
     const bool rneg = v.r < 0.0;
     const bool near0 = fabs(v.r) < 1e-5;
     // k such that theta0 = k*(pi/2) - r lies in (-pi, pi]: x > 0: q=0 -> 0, 1 -> -1, 2 -> +2 (r >= 0) or -2 (r < 0), 3 -> 1;
@@ -193,68 +200,77 @@ FMRX_HD void pll_prepare(PllLoop &c, const SinCos &v) {
     const int sh = rneg ? 16 : 0;
     const int kp = (int)(((kTable >> (sh + 4 * q)) & 15u) ^ 8u) - 8;
     const int kn = (int)(((kTable >> (sh + 4 * ((q + 2) & 3))) & 15u) ^ 8u) - 8;
-    c.th_hi[0] = (double)kp * H1; c.th_s1[0] = fma_((double)kp, L1, -v.r);
-    c.th_hi[1] = (double)kn * H1; c.th_s1[1] = fma_((double)kn, L1, -v.r);
-    c.usable[0] = !(q == 2 && near0);
-    c.usable[1] = !(q == 0 && near0);
+    f.th_hi_p = (double)kp * H1; f.th_s1_p = fma_((double)kp, L1, -v.r);
+    f.th_hi_n = (double)kn * H1; f.th_s1_n = fma_((double)kn, L1, -v.r);
+    f.usable_p = !(q == 2 && near0);
+    f.usable_n = !(q == 0 && near0);
 }
 
-FMRX_HD float pll_step_fast(PllLoop &c, float x, float cnt, bool &ok) {
-    const int sg = x < 0.0f ? 1 : 0;
+// re-arm the fast detector from the float trigArg of the step just taken
+FMRX_HD void pll_rearm(PllFast &f, float trig) {
+    if (fabsf(trig) < kTrigLimitF) pll_prepare(f, sincos_cw((double)trig));
+    else pll_disarm(f);
+}
+
+// x: input sample; cnt = (trigOffset + k) + 1 as the reference forms it in fp32; returns nco[k+1]
+FMRX_HD float pll_step_fast(PllCarry &c, PllFast &f, const PllCoef &p, float x, float cnt, bool &ok) {
+    const bool neg = x < 0.0f;
     const float ax = fabsf(x);
     const float eI = mul_rn(x, c.fbi);
     const float eQ = mul_rn(x, -c.fbq);
-    ok = c.usable[sg] && ax > 1e-18f && ax < 1e18f && eI != 0.0f && eQ != 0.0f;
+    ok = (neg ? f.usable_n : f.usable_p) && ax > 1e-18f && ax < 1e18f && eI != 0.0f && eQ != 0.0f;
     const double rx = (double)rcp_approx(x);
     const double dI = (double)eI, dQ = (double)eQ;
-    const double dot = fma_(dQ, -c.sn, dI * c.cs);
-    const double cross = fma_(dQ, c.cs, dI * c.sn);
+    const double dot = fma_(dQ, -f.sn, dI * f.cs);
+    const double cross = fma_(dQ, f.cs, dI * f.sn);
     const double e = fma_(-dot, rx, 2.0);
-    const double raw = c.th_hi[sg] + fma_(cross * rx, e, c.th_s1[sg]);
+    const double raw = (neg ? f.th_hi_n : f.th_hi_p) + fma_(cross * rx, e, neg ? f.th_s1_n : f.th_s1_p);
     const double ang = make_double((hi_word(raw) & 0x7fffffff) | (hi_word(dQ) & 0x80000000), lo_word(raw));  // copysign(|raw|, eQ)
     const float eD = (float)ang;
-    c.integ = add_rn(c.integ, mul_rn(c.Ki, eD));
-    c.phase = add_rn(c.phase, add_rn(mul_rn(c.Kp, eD), c.integ));
-    const float trig = (float)dadd_rn(dmul_rn(c.w, (double)cnt), (double)c.phase);  // src/helper.cpp:41: double expression, no FMA
-    const float targ = add_rn(mul_rn(trig, c.scale), c.adj);
+    c.integ = add_rn(c.integ, mul_rn(p.Ki, eD));
+    c.phase = add_rn(c.phase, add_rn(mul_rn(p.Kp, eD), c.integ));
+    const float trig = (float)dadd_rn(dmul_rn(p.w, (double)cnt), (double)c.phase);  // src/helper.cpp:41: double expression, no FMA
+    const float targ = add_rn(mul_rn(trig, p.scale), p.adj);
     ok = ok && fabsf(trig) < kTrigLimitF && fabsf(targ) < kTrigLimitF;
     const SinCos v = sincos_cw((double)trig);
-    pll_prepare(c, v);
+    pll_prepare(f, v);
     c.fbi = (float)v.cs;
     c.fbq = (float)v.sn;
     return (float)cos_cw((double)targ);
 }
 
-FMRX_HD_COLD float pll_step_libm(PllLoop &c, float x, float cnt) {
+// the same step through libm, everything by value (a cold, out-of-line call on the device must not pin the caller's
+// state in local memory)
+struct PllLibmOut {
+    PllCarry c;
+    float nco, trig;
+};
+FMRX_HD_COLD PllLibmOut pll_step_libm(PllCarry c, PllCoef p, float x, float cnt) {
     const float eI = mul_rn(x, c.fbi);
     const float eQ = mul_rn(x, -c.fbq);
     const float eD = (float)atan2((double)eQ, (double)eI);
-    c.integ = add_rn(c.integ, mul_rn(c.Ki, eD));
-    c.phase = add_rn(c.phase, add_rn(mul_rn(c.Kp, eD), c.integ));
-    const float trig = (float)dadd_rn(dmul_rn(c.w, (double)cnt), (double)c.phase);
-    const double T = (double)trig;
-    if (fabsf(trig) < kTrigLimitF) {
-        const SinCos v = sincos_cw(T);  // also re-arms the fast detector for the next step
-        pll_prepare(c, v);
-    } else {
-        c.cs = cos(T);
-        c.sn = sin(T);
-        c.usable[0] = c.usable[1] = false;
-    }
-    c.fbi = (float)c.cs;
-    c.fbq = (float)c.sn;
-    const float targ = add_rn(mul_rn(trig, c.scale), c.adj);
-    return (float)(fabsf(targ) < kTrigLimitF ? cos_cw((double)targ) : cos((double)targ));
+    c.integ = add_rn(c.integ, mul_rn(p.Ki, eD));
+    c.phase = add_rn(c.phase, add_rn(mul_rn(p.Kp, eD), c.integ));
+    const float trig = (float)dadd_rn(dmul_rn(p.w, (double)cnt), (double)c.phase);
+    c.fbi = (float)cos((double)trig);
+    c.fbq = (float)sin((double)trig);
+    PllLibmOut o;
+    o.c = c;
+    o.trig = trig;
+    o.nco = (float)cos((double)add_rn(mul_rn(trig, p.scale), p.adj));
+    return o;
 }
 
-// x: input sample; cnt = (trigOffset + k) + 1 as the reference forms it in fp32; returns nco[k+1]
-FMRX_HD float pll_step(PllLoop &c, float x, float cnt) {
-    const float integ = c.integ, phase = c.phase, fbi = c.fbi, fbq = c.fbq;
+// host-side convenience (tests): one step with the per-step fallback
+FMRX_HD float pll_step(PllCarry &c, PllFast &f, const PllCoef &p, float x, float cnt) {
+    const PllCarry saved = c;
     bool ok;
-    float out = pll_step_fast(c, x, cnt, ok);
+    float out = pll_step_fast(c, f, p, x, cnt, ok);
     if (!ok) {
-        c.integ = integ; c.phase = phase; c.fbi = fbi; c.fbq = fbq;
-        out = pll_step_libm(c, x, cnt);
+        const PllLibmOut o = pll_step_libm(saved, p, x, cnt);
+        c = o.c;
+        out = o.nco;
+        pll_rearm(f, o.trig);
     }
     return out;
 }

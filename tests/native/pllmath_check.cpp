@@ -61,30 +61,30 @@ int main(int argc, char **argv) {
             const float freq = cfg ? 114000.0f : 19e3f, Fs = 240e3f, scale = cfg ? 0.5f : 2.0f, bw = cfg ? 0.001f : 0.01f;
             const float adj = cfg ? (float)((double)(float)(3.14159265358979323846 / 3.3 - 3.14159265358979323846 / 1.5) - 3.14159265358979323846 / 1.4) : 0.0f;
             for (int trial = 0; trial < 4; ++trial) {
-                PllLoop c{};
-                c.integ = 0; c.phase = 0; c.fbi = 1; c.fbq = 0; c.usable[0] = c.usable[1] = false;
-                c.Ki = (bw * bw) * 3.555f; c.Kp = bw * 2.666f; c.scale = scale; c.adj = adj;
-                c.w = (2 * 3.14159265358979323846) * (double)(freq / Fs);
-                RefLoop r{0, 0, 1, 0, c.Ki, c.Kp, scale, adj, c.w};
+                PllCarry c{0, 0, 1, 0};
+                PllFast f{};
+                pll_disarm(f);
+                PllCoef p{(bw * bw) * 3.555f, bw * 2.666f, scale, adj, (2 * 3.14159265358979323846) * (double)(freq / Fs)};
+                RefLoop r{0, 0, 1, 0, p.Ki, p.Kp, scale, adj, p.w};
                 float off = 0.0f;
                 std::normal_distribution<double> noise(0.0, trial == 3 ? 0.5 : 0.01);
                 const double amp = trial == 1 ? 1e-3 : trial == 2 ? 30.0 : 0.05, ph0 = 0.3 + trial, df = trial == 2 ? 3.0 : 0.0;
                 for (int b = 0; b < blocks; ++b) {
-                    c.usable[0] = c.usable[1] = false;  // a launch boundary: only the float state is carried
+                    pll_disarm(f);  // a launch boundary: only the float state is carried
                     for (int k = 0; k < N; ++k) {
                         const double t = ((double)b * N + k) / Fs;
                         float x = (float)(amp * cos(2 * 3.14159265358979323846 * (freq + df) * t + ph0) + amp * noise(rng));
                         if (trial == 3 && (k % 977) == 0) x = 0.0f;  // exact zeros exercise the libm path
                         const float cnt = add_rn(add_rn(off, (float)k), 1.0f);
-                        { bool ok; PllLoop probe = c; pll_step_fast(probe, x, cnt, ok); fast_steps += ok; }
-                        const float a = pll_step(c, x, cnt), g = ref_step(r, x, cnt);
+                        { bool ok; PllCarry pc = c; PllFast pf = f; pll_step_fast(pc, pf, p, x, cnt, ok); fast_steps += ok; }
+                        const float a = pll_step(c, f, p, x, cnt), g = ref_step(r, x, cnt);
                         ++total;
                         const bool same = a == g && c.integ == r.integ && c.phase == r.phase && c.fbi == r.fbi && c.fbq == r.fbq;
                         if (!same) {
                             ++mism;
                             max_nco_diff = fmax(max_nco_diff, fabs((double)a - (double)g));
                             // resynchronise so that one flip is counted once
-                            c.integ = r.integ; c.phase = r.phase; c.fbi = r.fbi; c.fbq = r.fbq; c.usable[0] = c.usable[1] = false;
+                            c.integ = r.integ; c.phase = r.phase; c.fbi = r.fbi; c.fbq = r.fbq; pll_disarm(f);
                         }
                     }
                     off = add_rn(off, (float)N);
