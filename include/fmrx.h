@@ -171,7 +171,10 @@ enum {
     FMRX_STAGE_RDS_SQ_BPF, FMRX_STAGE_PLL, FMRX_STAGE_STEREO_LPF, FMRX_STAGE_COMBINE, FMRX_STAGE_RDS_MIX_LPF,
     FMRX_STAGE_RDS_RESAMPLE, FMRX_STAGE_RDS_RRC, FMRX_STAGE_RDS_DECODE, FMRX_STAGE_COUNT
 };
-int fmrx_batch_profile(fmrx_batch *, int enable);
+int fmrx_batch_profile(fmrx_batch *, int enable); /* 0 off, 1 serialised per-stage timing, 2 timeline: keep the pipeline */
+/* start / end of every bracket recorded since profiling was enabled, in ms after the first bracket's start; returns the
+ * number of brackets written (<= cap) or a negative status.  Call before fmrx_batch_stage_times (which consumes them). */
+int fmrx_batch_timeline(fmrx_batch *, int cap, int32_t *stage, float *t0_ms, float *t1_ms);
 int fmrx_batch_stage_times(fmrx_batch *, double *ms /*[FMRX_STAGE_COUNT]*/, long long *count /*[FMRX_STAGE_COUNT] or NULL*/);
 
 /* opaque state blob (all filter histories, PLL states, decoder states, block counter) for checkpoint / resume */

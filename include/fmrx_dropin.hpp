@@ -1,0 +1,132 @@
+// fmrx_dropin.hpp — the reference's own C++ function names and signatures (src/filter.h:17-38, src/helper.h:17-25,
+// src/rf_module.h:20, src/iofunc.cpp:61-69 of m1nty/Real-Time-Software-Defined-Radio), implemented on the GPU through
+// the C-ABI of libfmrx.so.  A translation unit of the reference that includes this header instead of filter.h / helper.h /
+// rf_module.h and links -lfmrx runs the same per-block arithmetic on a B200, one block per call, with the caller-owned
+// state vectors (`zi`, pll_state_type) updated exactly as the reference updates them (state saved one sample late, Q1;
+// discriminator state reset on entry, Q3; half-weight mixer history, Q8; polyphase history index map, Q6).
+//
+// Differences from the reference, all deliberate:
+//  * outputs are ASSIGNED, not accumulated: y holds what the reference leaves in a y that was all zeros on entry (the
+//    reference `resize`s and `+=`s, so stale contents leak into its result unless the caller cleared them);
+//  * the FIR kernels are specialised for the reference's 151 taps (every call site in src/fm_radio.cpp uses 151; the
+//    polyphase resamplers take any length);
+//  * failures (no CUDA device, out of memory, unsupported size) throw std::runtime_error carrying fmrx_last_error();
+//    there is no CPU fallback.
+// For throughput use the batched entries of fmrx.h (many streams x blocks per launch); these wrappers exist so that the
+// reference's own call sites, and tests written against them, can be pointed at the GPU unchanged.
+#ifndef FMRX_DROPIN_HPP
+#define FMRX_DROPIN_HPP
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "fmrx.h"
+
+struct pll_state_type {  // src/helper.h:17-19
+    float integrator, phaseEst, feedbackI, feedbackQ, trigOffset, ncoLast;
+};
+
+namespace fmrx_dropin {
+inline void check(int status, const char *what) {
+    if (status != FMRX_OK) throw std::runtime_error(std::string(what) + ": " + fmrx_last_error());
+}
+}  // namespace fmrx_dropin
+
+// ---- src/filter.cpp:19-93 (host-side design, bit-identical taps)
+inline void impulseResponseLPF(float Fs, float Fc, unsigned short int num_taps, std::vector<float> &h) {
+    h.assign(num_taps, 0.0f);
+    fmrx_dropin::check(fmrx_design_lpf(Fs, Fc, num_taps, h.data()), "impulseResponseLPF");
+}
+inline void impulseResponseBPF(float Fb, float Fe, float Fs, int num_taps, std::vector<float> &h) {
+    h.assign(num_taps, 0.0f);
+    fmrx_dropin::check(fmrx_design_bpf(Fb, Fe, Fs, num_taps, h.data()), "impulseResponseBPF");
+}
+inline void impulseResponseRRC(const float &Fs, const int &num_taps, std::vector<float> &h) {
+    h.assign(num_taps, 0.0f);
+    fmrx_dropin::check(fmrx_design_rrc(Fs, num_taps, h.data()), "impulseResponseRRC");
+}
+
+// ---- src/iofunc.cpp:61-69, the conversion only (reading stdin stays with the caller)
+inline void unpackBlock(const std::vector<unsigned char> &raw, std::vector<float> &block_data) {
+    block_data.assign(raw.size(), 0.0f);
+    fmrx_dropin::check(fmrx_unpack_iq(raw.data(), raw.size(), block_data.data()), "unpackBlock");
+}
+
+// ---- src/filter.cpp:126-185
+inline void convolveWithDecimPointer(std::vector<float> &y, float *&x, const unsigned int block_size, const std::vector<float> &h,
+                                     std::vector<float> &zi, const int &decim_num) {
+    y.assign(block_size / decim_num, 0.0f);
+    fmrx_dropin::check(fmrx_fir_decim(y.data(), x, 1, 1, (int)block_size, h.data(), (int)h.size(), zi.data(), (int)zi.size(), decim_num, 1),
+                       "convolveWithDecimPointer");
+}
+inline void convolveWithDecim(std::vector<float> &y, const std::vector<float> &x, const std::vector<float> &h, std::vector<float> &zi,
+                              const int &decim_num) {
+    float *p = const_cast<float *>(x.data());
+    convolveWithDecimPointer(y, p, (unsigned)x.size(), h, zi, decim_num);
+}
+// ---- src/filter.cpp:187-219
+inline void convolveWithDecimIQ(std::vector<float> &y, const std::vector<float> &x, const std::vector<float> &h, std::vector<float> &zi,
+                                std::vector<float> &y1, const std::vector<float> &x1, std::vector<float> &zi1, const int &decim_num) {
+    y.assign(x.size() / decim_num, 0.0f);
+    y1.assign(x.size() / decim_num, 0.0f);
+    fmrx_dropin::check(fmrx_fir_decim_iq(y.data(), y1.data(), x.data(), x1.data(), 1, 1, (int)x.size(), h.data(), (int)h.size(), zi.data(),
+                                         zi1.data(), decim_num, 1),
+                       "convolveWithDecimIQ");
+}
+// ---- src/filter.cpp:222-339
+inline void convolveWithDecimMode1Pointer(std::vector<float> &y, float *&x, const unsigned int block_size, const std::vector<float> &h,
+                                          std::vector<float> &zi, const int &decim_num, const int &up_sample) {
+    y.assign((size_t)block_size * up_sample / decim_num, 0.0f);
+    fmrx_dropin::check(fmrx_resample(y.data(), 0, x, 1, 1, (int)block_size, h.data(), (int)h.size(), zi.data(), (int)zi.size(), decim_num,
+                                     up_sample, 0, 1),
+                       "convolveWithDecimMode1Pointer");
+}
+inline void convolveWithDecimMode1(std::vector<float> &y, const std::vector<float> &x, const std::vector<float> &h, std::vector<float> &zi,
+                                   const int &decim_num, const int &up_sample) {
+    float *p = const_cast<float *>(x.data());
+    convolveWithDecimMode1Pointer(y, p, (unsigned)x.size(), h, zi, decim_num, up_sample);
+}
+inline void convolveWithDecimMode1RDS(std::vector<float> &y, const std::vector<float> &x, const std::vector<float> &h,
+                                      std::vector<float> &zi, const int &decim_num, const int &up_sample) {
+    y.assign(x.size() * up_sample / decim_num, 0.0f);
+    fmrx_dropin::check(fmrx_resample(y.data(), 0, x.data(), 1, 1, (int)x.size(), h.data(), (int)h.size(), zi.data(), (int)zi.size(),
+                                     decim_num, up_sample, 1, 0),
+                       "convolveWithDecimMode1RDS");
+}
+// ---- src/filter.cpp:373-401 at its call site src/fm_radio.cpp:404: x = the (n+1)-long NCO vector of pllCombine,
+// x1 = the n-long RDS band signal; y gets n+1 elements like the reference's, the last of which the reference computes
+// from an out-of-bounds read and never consumes — it is returned as 0.
+inline void convolveWithDecimAndMixer(std::vector<float> &y, const std::vector<float> &x, const std::vector<float> &x1,
+                                      const std::vector<float> &h, std::vector<float> &zi, const int &decim_num) {
+    if (decim_num != 1) throw std::runtime_error("convolveWithDecimAndMixer: the reference only ever calls it with decim 1");
+    const int n = (int)x1.size();
+    y.assign(x.size(), 0.0f);
+    fmrx_dropin::check(fmrx_fir_mixer(y.data(), x.data(), x1.data(), 1, 1, n, h.data(), (int)h.size(), zi.data()), "convolveWithDecimAndMixer");
+}
+
+// ---- src/rf_module.cpp:13-34 (prev_phase is reset on entry by the reference, Q3: it is neither read nor written here)
+inline void fmDemodArctan(const std::vector<float> &I, const std::vector<float> &Q, std::vector<float> & /*prev_phase*/, float *&queue_block) {
+    fmrx_dropin::check(fmrx_demod(I.data(), Q.data(), 1, 1, (int)I.size(), queue_block), "fmDemodArctan");
+}
+
+// ---- src/helper.cpp:13-57
+inline void fmPLL(std::vector<float> &ncoOut, std::vector<float> &pllIn, float freq, float Fs, float ncoScale, float phaseAdjust,
+                  float normBandwidth, pll_state_type &pll_state) {
+    ncoOut.assign(pllIn.size(), 0.0f);
+    fmrx_dropin::check(fmrx_pll(ncoOut.data(), pllIn.data(), 1, 1, (int)pllIn.size(), freq, Fs, ncoScale, phaseAdjust, normBandwidth,
+                                &pll_state.integrator),
+                       "fmPLL");
+}
+// ---- src/helper.cpp:108-173: ncoOut keeps its untrimmed (n+1)-th element, as in the reference
+inline void pllCombine(std::vector<float> &y, const std::vector<float> &x, const std::vector<float> &h, std::vector<float> &zi,
+                       const int &decim_num, std::vector<float> &ncoOut, float freq, float Fs, float ncoScale, float phaseAdjust,
+                       float normBandwidth, pll_state_type &pll_state) {
+    if (decim_num != 1) throw std::runtime_error("pllCombine: the reference only ever calls it with decim 1");
+    y.assign(x.size(), 0.0f);
+    ncoOut.assign(x.size() + 1, 0.0f);
+    fmrx_dropin::check(fmrx_pll_combine(y.data(), ncoOut.data(), x.data(), 1, 1, (int)x.size(), h.data(), (int)h.size(), zi.data(), freq, Fs,
+                                        ncoScale, phaseAdjust, normBandwidth, &pll_state.integrator),
+                       "pllCombine");
+    ncoOut[x.size()] = pll_state.ncoLast;
+}
+#endif  // FMRX_DROPIN_HPP

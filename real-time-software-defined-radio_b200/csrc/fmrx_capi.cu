@@ -11,6 +11,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -305,6 +306,7 @@ struct fmrx_batch {
     std::vector<void *> allocs;
     // optional per-stage device timing (fmrx_batch_profile): event pairs around every stage of every enqueued chain
     bool profiling = false;
+    bool profile_pipelined = false;  // fmrx_batch_profile(.., 2): keep the three-stream pipeline while timing (timeline mode)
     std::vector<cudaEvent_t> prof_pool;
     size_t prof_used = 0;
     struct Mark { int stage; cudaEvent_t t0, t1; };
@@ -583,6 +585,7 @@ int fmrx_batch_create(const fmrx_config *cfg, fmrx_batch **out) {
         // priority so those CTAs are placed as soon as any slot frees up instead of queueing behind the FIR grids
         int least = 0, greatest = 0;
         CU(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        if (const char *e = getenv("FMRX_PIPE_PRIO")) { if (e[0] == '0') greatest = least; }  // experiment switch: equal priorities
         CU(cudaStreamCreateWithPriority(&b->s_p, cudaStreamNonBlocking, greatest));
         CU(cudaStreamCreateWithPriority(&b->s_c, cudaStreamNonBlocking, greatest < least ? greatest + 1 : least));
         CU(cudaStreamCreateWithPriority(&b->s_a, cudaStreamNonBlocking, least));
@@ -633,9 +636,10 @@ int fmrx_batch_process_device(fmrx_batch *b, const uint8_t *iq_device, int n_blo
     const fmrx_outputs &o = out_device ? *out_device : none;
     const int set = (int)(b->calls & 1);
     // phase A of this call overwrites the buffer set phase C of the call before last was reading
-    if (b->ev_c_valid[set] && !b->profiling) CU(cudaStreamWaitEvent(b->s_a, b->ev_c[set], 0));
+    if (b->ev_c_valid[set] && !(b->profiling && !b->profile_pipelined)) CU(cudaStreamWaitEvent(b->s_a, b->ev_c[set], 0));
     // while per-stage profiling is on, the three phases are serialised on one stream so that every stage is timed alone
-    cudaStream_t sa = b->profiling ? b->s_c : b->s_a, sp = b->profiling ? b->s_c : b->s_p;
+    const bool serial = b->profiling && !b->profile_pipelined;
+    cudaStream_t sa = serial ? b->s_c : b->s_a, sp = serial ? b->s_c : b->s_p;
     if (int e = enqueue_chain(b, iq_device, (long long)n_blocks * FMRX_BLOCK_BYTES, 0, b->S, n_blocks, o, set, sa, sp, b->s_c)) return e;
     if (int e = copy_outputs(b, 0, b->S, n_blocks, o, cudaMemcpyDeviceToDevice, b->s_c)) return e;
     CU(cudaEventRecord(b->ev_c[set], b->s_c));
@@ -729,6 +733,7 @@ int fmrx_batch_profile(fmrx_batch *b, int enable) {
     if (!b) return fail(FMRX_ERR_ARG, "null handle");
     if (int e = fmrx_batch_sync(b)) return e;
     b->profiling = enable != 0;
+    b->profile_pipelined = enable == 2;
     b->marks.clear();
     b->prof_used = 0;
     for (int i = 0; i < FMRX_STAGE_COUNT; ++i) { b->stage_ms[i] = 0; b->stage_launches[i] = 0; }
@@ -748,6 +753,20 @@ int fmrx_batch_stage_times(fmrx_batch *b, double *ms, long long *count) {
     b->prof_used = 0;
     for (int i = 0; i < FMRX_STAGE_COUNT; ++i) { ms[i] = b->stage_ms[i]; if (count) count[i] = b->stage_launches[i]; }
     return FMRX_OK;
+}
+
+int fmrx_batch_timeline(fmrx_batch *b, int cap, int32_t *stage, float *t0_ms, float *t1_ms) {
+    if (!b || !stage || !t0_ms || !t1_ms) return fail(FMRX_ERR_ARG, "null pointer");
+    if (int e = fmrx_batch_sync(b)) return e;
+    int n = 0;
+    for (auto &m : b->marks) {
+        if (n >= cap) break;
+        stage[n] = m.stage;
+        CU(cudaEventElapsedTime(&t0_ms[n], b->marks[0].t0, m.t0));
+        CU(cudaEventElapsedTime(&t1_ms[n], b->marks[0].t0, m.t1));
+        ++n;
+    }
+    return n;
 }
 
 int fmrx_pinned_alloc(void **ptr, size_t bytes) {

@@ -100,6 +100,7 @@ SIGNATURES = {
     "fmrx_batch_set_state": (C.c_int, [C.c_void_p, C.c_void_p]),
     "fmrx_batch_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "fmrx_batch_stage_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+    "fmrx_batch_timeline": (C.c_int, [C.c_void_p, C.c_int, i32p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "fmrx_pinned_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "fmrx_pinned_free": (C.c_int, [C.c_void_p]),
     "fmrx_measure_fp32_peak": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
@@ -297,7 +298,11 @@ class Batch:
             lib().fmrx_batch_destroy(self.h)
             self.h = C.c_void_p()
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown: module globals may already be gone
+            pass
 
     def __enter__(self):
         return self
@@ -364,7 +369,18 @@ class Batch:
         return "".join(out)
 
     def profile(self, enable=True):
+        """True / 1: per-stage timing with the phases serialised; 2: timeline mode (pipeline kept); False: off."""
         check(lib().fmrx_batch_profile(self.h, int(enable)))
+
+    def timeline(self, cap=4096):
+        """[(stage name, start ms, end ms)] of every bracket since profile(2) (pipelined timeline mode)."""
+        st = (C.c_int32 * cap)()
+        t0 = (C.c_float * cap)()
+        t1 = (C.c_float * cap)()
+        n = lib().fmrx_batch_timeline(self.h, cap, st, t0, t1)
+        if n < 0:
+            check(n)
+        return [(STAGES[st[i]], t0[i], t1[i]) for i in range(n)]
 
     def stage_times(self):
         """{stage: (total ms, brackets)} accumulated since profile(True)."""
