@@ -262,6 +262,13 @@ def run_fmrx_arm(args, rank, world, local_rank):
     units = world * S * B * BLOCK_IQ * args.steps
     value = units / (ms_dev * 1e-3) / 1e6
 
+    pll_sms, filter_sms = rx.partition()
+    if args.device_only:
+        if rank == 0:
+            print(json.dumps({"device_only": True, "value": round(value, 1), "unit": "Msps", "ms_per_step": round(ms_dev / args.steps, 4), "pll_sms": pll_sms,
+                              "filter_sms": filter_sms, "stages_ms": {k: round(v[0] / args.steps, 4) for k, v in stage.items() if v[1]}}), flush=True)
+        return
+
     # ---- end to end: pinned host buffers in and out, copies inside the timed region
     h_iq = torch.empty((S, B * BLOCK_BYTES), dtype=torch.uint8, pin_memory=True)
     h_iq.copy_(d_iq)
@@ -321,7 +328,8 @@ def run_fmrx_arm(args, rank, world, local_rank):
         "metric": "IQ Msps (complex samples/s, whole job)", "value": round(value, 1), "unit": "Msps", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_dev / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "batch4096_mode0_stereo_rds", "stations_per_gpu": S, "blocks_per_step": B, "mode": 0, "profile": "intent", "paths": "mono+stereo+rds",
-                   "numerics": "audio path reference-exact (mul+add), RDS path fma", "realtime_streams": int(value / 2.4), "e2e_realtime_streams": int(e2e_value / 2.4),
+                   "numerics": "audio path reference-exact (mul+add), RDS path fma",
+                   "sm_partition": {"pll_sms": pll_sms, "filter_sms": filter_sms} if pll_sms else "none (phases share the device)", "realtime_streams": int(value / 2.4), "e2e_realtime_streams": int(e2e_value / 2.4),
                    "l2": "input per step %.2f GB >> 126 MB L2, no flush needed" % (S * B * BLOCK_BYTES / 1e9), "input_reuse": "same synthesised block replayed each step, state carried",
                    "synth_seconds": round(t_synth, 2), "parity_spot_check": parity,
                    "e2e_timer": "host clock around K synchronous fmrx_batch_process calls, barrier + synchronize on both sides, max over ranks"},
@@ -347,6 +355,7 @@ def main():
     ap.add_argument("--blocks", type=int, default=1, help="blocks per station per step")
     ap.add_argument("--cpu-blocks", type=int, default=16, help="blocks per process of the CPU baseline sample")
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--device-only", action="store_true", help="tuning aid: device-resident number and stage times only (not a bench line)")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":

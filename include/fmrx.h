@@ -149,6 +149,9 @@ void *fmrx_batch_cuda_stream(fmrx_batch *);         /* cudaStream_t on which a c
  * PLLs, 1 = the PLLs, 2 = everything after them (+ output copies).  Consecutive fmrx_batch_process_device calls overlap:
  * call k's PLLs run beside call k+1's phase 0 and call k-1's phase 2. */
 void *fmrx_batch_cuda_stream_phase(fmrx_batch *, int phase);
+/* SMs the PLL phase / the filter phases of the device-resident pipeline own (green-context partition; both 0 when the
+ * phases share the whole device: small batches, FMRX_PLL_SMS=0, or a driver without green contexts) */
+int fmrx_batch_partition(const fmrx_batch *, int *pll_sms, int *filter_sms);
 long long fmrx_batch_launch_count(const fmrx_batch *); /* kernels launched by this handle so far */
 /* per-stream initial_offset of the RDS decoder (host int32[S]) */
 int fmrx_batch_rds_offsets(fmrx_batch *, int32_t *offsets);

@@ -137,7 +137,7 @@ int fmrx_resample(float *y, int ny_limit, const float *x, int n_streams, int n_b
     Dev<float> dx, dy, dz, dh;
     CU(dx.up(x, nx)); CU(dy.alloc(nyt)); CU(dz.up(zi, (size_t)n_streams * nzi)); CU(dh.up(h, ntaps));
     ResampleJob j{};
-    j.x = dx.p; j.y = dy.p; j.zi = dz.p; j.h = dh.p; j.ldx = (long long)n_blocks * n; j.ldy = (long long)n_blocks * ny;
+    j.x = dx.p; j.y = dy.p; j.zi = dz.p; j.h = dh.p; j.h_host = h; j.ldx = (long long)n_blocks * n; j.ldy = (long long)n_blocks * ny;
     j.n = n; j.n_ref = n; j.ny = ny; j.n_blocks = n_blocks; j.n_streams = n_streams; j.ntaps = ntaps; j.nzi = nzi; j.decim = decim; j.up = up;
     j.gain_up = gain_up; j.exact = exact;
     LAUNCH(launch_resample(j, nullptr));
@@ -297,9 +297,14 @@ struct fmrx_batch {
     // device-resident pipeline: filters before the PLLs, the PLLs, and everything after them run on three streams, so
     // that step k's (latency-bound, few-warp) PLL kernel overlaps step k+1's front end and step k-1's back end.  The
     // signals crossing a phase boundary are double-buffered (`set`).
-    cudaStream_t s_a = nullptr, s_p = nullptr, s_c = nullptr;
+    // When the batch is large enough to fill the device, the PLL stream lives in a green context with SMs of its own
+    // and the two filter streams in a second one with the rest (fmrx_partition.cu); s_ser is a whole-device stream for
+    // the serialised per-stage profiling pass.
+    cudaStream_t s_a = nullptr, s_p = nullptr, s_c = nullptr, s_ser = nullptr;
+    fmrx::SmPartition *part = nullptr;
     cudaEvent_t ev_a[2]{}, ev_p[2]{}, ev_c[2]{};
     bool ev_c_valid[2] = {false, false};
+    bool was_serial = false;
     long long calls = 0;
     int last_set = 0;
     size_t set_if = 0, set_au = 0;  // elements per set of an IF-rate / audio-rate signal
@@ -320,7 +325,8 @@ struct fmrx_batch {
         for (auto e : prof_pool) cudaEventDestroy(e);
         for (int i = 0; i < kMaxChunks; ++i) { if (e_in[i]) cudaEventDestroy(e_in[i]); if (e_done[i]) cudaEventDestroy(e_done[i]); if (e_out[i]) cudaEventDestroy(e_out[i]); }
         for (int i = 0; i < 2; ++i) { if (ev_a[i]) cudaEventDestroy(ev_a[i]); if (ev_p[i]) cudaEventDestroy(ev_p[i]); if (ev_c[i]) cudaEventDestroy(ev_c[i]); }
-        for (auto st : {s_a, s_p, s_c}) if (st) cudaStreamDestroy(st);
+        for (auto st : {s_a, s_p, s_c, s_ser}) if (st) cudaStreamDestroy(st);
+        fmrx::partition_destroy(part);
         if (s_in) cudaStreamDestroy(s_in);
         if (s_out) cudaStreamDestroy(s_out);
         for (auto s : s_cmp) if (s) cudaStreamDestroy(s);
@@ -466,7 +472,7 @@ int enqueue_chain(fmrx_batch *b, const uint8_t *iq, long long ld_iq, int s0, int
     if (b->rds_on) {
         { STAGE(FMRX_STAGE_RDS_MIX_LPF); LAUNCH(fir(IF2(b->rnco), IF2(b->rbpf), IF(b->rlpf), b->zi_lpf + (long long)s0 * kHist, kHist, b->h_lpf3k, ldif, ldif, NIF, 1, SRC_MIX_HALF, 0, nblk)); }
         ResampleJob r{};
-        r.x = IF(b->rlpf); r.y = RD(b->rres); r.zi = b->zi_anti + (long long)s0 * (kTaps * 19 - 1); r.h = b->d_h_anti; r.ldx = ldif; r.ldy = ldr;
+        r.x = IF(b->rlpf); r.y = RD(b->rres); r.zi = b->zi_anti + (long long)s0 * (kTaps * 19 - 1); r.h = b->d_h_anti; r.h_host = b->h_anti.data(); r.ldx = ldif; r.ldy = ldr;
         r.n = NIF; r.n_ref = NIF + 1; r.ny = NRDS; r.n_blocks = nblk; r.n_streams = ns; r.ntaps = kTaps * 19; r.nzi = kTaps * 19 - 1;
         r.decim = 80; r.up = 19; r.gain_up = 1; r.exact = 0;
         { STAGE(FMRX_STAGE_RDS_RESAMPLE); LAUNCH(launch_resample(r, st)); }
@@ -586,9 +592,22 @@ int fmrx_batch_create(const fmrx_config *cfg, fmrx_batch **out) {
         int least = 0, greatest = 0;
         CU(cudaDeviceGetStreamPriorityRange(&least, &greatest));
         if (const char *e = getenv("FMRX_PIPE_PRIO")) { if (e[0] == '0') greatest = least; }  // experiment switch: equal priorities
-        CU(cudaStreamCreateWithPriority(&b->s_p, cudaStreamNonBlocking, greatest));
-        CU(cudaStreamCreateWithPriority(&b->s_c, cudaStreamNonBlocking, greatest < least ? greatest + 1 : least));
-        CU(cudaStreamCreateWithPriority(&b->s_a, cudaStreamNonBlocking, least));
+        const int mid = greatest < least ? greatest + 1 : least;
+        // FMRX_PLL_SMS: SMs set aside for the PLL stream (0 = no partition); default 32 once the batch fills the device
+        int pll_sms = b->S >= 1024 && b->audio_on && b->rds_on ? 32 : 0;
+        if (const char *e = getenv("FMRX_PLL_SMS")) pll_sms = atoi(e);
+        if (pll_sms > 0) {
+            const int prio_big[2] = {least, mid};
+            cudaStream_t big[2] = {nullptr, nullptr};
+            b->part = fmrx::partition_create(cfg->device, pll_sms, greatest, &b->s_p, 2, prio_big, big);
+            if (b->part) { b->s_a = big[0]; b->s_c = big[1]; }
+        }
+        if (!b->part) {
+            CU(cudaStreamCreateWithPriority(&b->s_p, cudaStreamNonBlocking, greatest));
+            CU(cudaStreamCreateWithPriority(&b->s_c, cudaStreamNonBlocking, mid));
+            CU(cudaStreamCreateWithPriority(&b->s_a, cudaStreamNonBlocking, least));
+        }
+        CU(cudaStreamCreateWithFlags(&b->s_ser, cudaStreamNonBlocking));
     }
     for (int i = 0; i < 2; ++i) {
         CU(cudaEventCreateWithFlags(&b->ev_a[i], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&b->ev_p[i], cudaEventDisableTiming));
@@ -607,6 +626,11 @@ int fmrx_batch_create(const fmrx_config *cfg, fmrx_batch **out) {
 void fmrx_batch_destroy(fmrx_batch *b) { delete b; }
 int fmrx_batch_audio_per_block(const fmrx_batch *b) { return b ? b->n_audio : 0; }
 long long fmrx_batch_launch_count(const fmrx_batch *b) { return b ? b->launches : 0; }
+int fmrx_batch_partition(const fmrx_batch *b, int *pll_sms, int *filter_sms) {
+    if (!b || !pll_sms || !filter_sms) return fail(FMRX_ERR_ARG, "null pointer");
+    fmrx::partition_sizes(b->part, pll_sms, filter_sms);
+    return FMRX_OK;
+}
 void *fmrx_batch_cuda_stream(fmrx_batch *b) { return b ? (void *)b->s_c : nullptr; }
 void *fmrx_batch_cuda_stream_phase(fmrx_batch *b, int phase) {
     if (!b) return nullptr;
@@ -624,7 +648,7 @@ int fmrx_batch_sync(fmrx_batch *b) {
     if (!b) return fail(FMRX_ERR_ARG, "null handle");
     CU(cudaSetDevice(b->cfg.device));
     CU(cudaStreamSynchronize(b->s_in)); CU(cudaStreamSynchronize(b->s_cmp[0])); CU(cudaStreamSynchronize(b->s_cmp[1])); CU(cudaStreamSynchronize(b->s_out));
-    CU(cudaStreamSynchronize(b->s_a)); CU(cudaStreamSynchronize(b->s_p)); CU(cudaStreamSynchronize(b->s_c));
+    CU(cudaStreamSynchronize(b->s_a)); CU(cudaStreamSynchronize(b->s_p)); CU(cudaStreamSynchronize(b->s_c)); CU(cudaStreamSynchronize(b->s_ser));
     return FMRX_OK;
 }
 
@@ -639,10 +663,14 @@ int fmrx_batch_process_device(fmrx_batch *b, const uint8_t *iq_device, int n_blo
     if (b->ev_c_valid[set] && !(b->profiling && !b->profile_pipelined)) CU(cudaStreamWaitEvent(b->s_a, b->ev_c[set], 0));
     // while per-stage profiling is on, the three phases are serialised on one stream so that every stage is timed alone
     const bool serial = b->profiling && !b->profile_pipelined;
-    cudaStream_t sa = serial ? b->s_c : b->s_a, sp = serial ? b->s_c : b->s_p;
-    if (int e = enqueue_chain(b, iq_device, (long long)n_blocks * FMRX_BLOCK_BYTES, 0, b->S, n_blocks, o, set, sa, sp, b->s_c)) return e;
-    if (int e = copy_outputs(b, 0, b->S, n_blocks, o, cudaMemcpyDeviceToDevice, b->s_c)) return e;
-    CU(cudaEventRecord(b->ev_c[set], b->s_c));
+    if (serial != b->was_serial) {  // switching between the pipeline streams and the whole-device stream: drain first
+        if (int e = fmrx_batch_sync(b)) return e;
+        b->was_serial = serial;
+    }
+    cudaStream_t sa = serial ? b->s_ser : b->s_a, sp = serial ? b->s_ser : b->s_p, sc = serial ? b->s_ser : b->s_c;
+    if (int e = enqueue_chain(b, iq_device, (long long)n_blocks * FMRX_BLOCK_BYTES, 0, b->S, n_blocks, o, set, sa, sp, sc)) return e;
+    if (int e = copy_outputs(b, 0, b->S, n_blocks, o, cudaMemcpyDeviceToDevice, sc)) return e;
+    CU(cudaEventRecord(b->ev_c[set], sc));
     b->ev_c_valid[set] = true;
     b->calls += 1;
     b->block_id += n_blocks;

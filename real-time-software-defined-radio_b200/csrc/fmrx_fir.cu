@@ -9,12 +9,14 @@
 //   src/helper.cpp:139,162   the squared-input variant;  src/filter.cpp:387,399 the mixer variant with half-weight history.
 //   src/iofunc.cpp:67, src/fm_radio.cpp:68-72, src/rf_module.cpp:13-34 for the front end.
 //
-// B200 mapping: one CTA = CT threads x R=8 consecutive outputs = one tile of one (stream, block).  The input span is
-// staged once in shared memory with a row pitch of d*R+1 words, so that lane t's window starts at (d*R+1)*t: odd lane
-// stride = conflict-free LDS, and every offset is a compile-time constant.  The inner loop runs over the thread's INPUT
-// samples, newest first: each sample is read from shared memory exactly once and applied to every output it
-// contributes to (d=10: 221 LDS for 1208 taps x outputs), which for a fixed output still visits the taps in ascending
-// order -- the reference's summation order.  The loop is fully unrolled; taps arrive BY VALUE in the kernel parameter
+// B200 mapping: one CTA = NT threads x R=8 consecutive outputs = one tile of one (stream, block).  The input span is
+// staged once in shared memory, 128 bits at a time, with a row pitch of d*R+4 words: lane t's window starts at
+// (d*R+4)*t, which keeps every quad 16-byte aligned and makes the 128-bit loads of a quarter-warp cover all 32 banks
+// ((d*R+4)/4 is odd), so both the staging stores and the window loads are conflict-free (the first version used
+// scalar stores with a pitch of d*R+1: ncu showed a 4-way conflict on every staging store and 38% of the warp stalls
+// on the shared-memory scoreboard, profiles/r1k_*).  The inner loop runs over the thread's INPUT samples, newest
+// first: each sample is read from shared memory exactly once (one LDS.128 per four) and applied to every output it
+// contributes to, which for a fixed output still visits the taps in ascending order -- the reference's summation order.  The loop is fully unrolled; taps arrive BY VALUE in the kernel parameter
 // block, so each tap is a constant-bank operand of the multiply and the instruction stream is ~95% FMUL/FADD (or FFMA).
 // `EXACT` keeps the reference's two roundings per tap (FMUL, FADD); otherwise FFMA.  The packed f32x2 forms are not
 // used: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (checked with cuobjdump), which breaks the two
@@ -45,6 +47,20 @@ struct Geom {
     static constexpr int WORDS = SPAN + SPAN / ROW + 1;
     static constexpr int WIN = D * (R - 1) + kTaps;  // input samples one thread touches
     __host__ __device__ static constexpr int phys(int i) { return i + i / ROW; }
+};
+
+// quad-aligned geometry of the single-channel kernel
+template <int D, int NT>
+struct Geom4 {
+    static constexpr int TO = R * NT;
+    static constexpr int ROW = D * R;
+    static constexpr int PITCH = ROW + 4;
+    static_assert(ROW % 8 == 0 && OFF % 4 == 0, "rows and the tile origin must keep 128-bit alignment; (ROW+4)/4 must be odd");
+    static constexpr int SPAN = D * (TO - 1) + OFF + 1;
+    static constexpr int QUADS = (SPAN + 3) / 4;
+    static constexpr int WORDS = ((4 * QUADS + ROW - 1) / ROW) * PITCH;
+    static constexpr int QHI = (D * (R - 1) + OFF) / 4, QLO = (OFF - kHist) / 4;  // quads one thread touches
+    __host__ __device__ static constexpr int phys(int i) { return i + 4 * (i / ROW); }
 };
 
 template <bool EXACT>
@@ -107,46 +123,52 @@ __device__ __forceinline__ float source(const FirDev &a, const float *xs, const 
 // ------------------------------------------------------------------------------------------------------------------
 // single-channel kernel
 // ------------------------------------------------------------------------------------------------------------------
-template <int D, int KIND, bool EXACT>
-__global__ void __launch_bounds__(CT) fir151_kernel(const FirDev a, const __grid_constant__ Taps taps) {
-    using G = Geom<D, CT>;
-    __shared__ float sm[G::WORDS];
+template <int D, int KIND, bool EXACT, int NT>
+__global__ void __launch_bounds__(NT) fir151_kernel(const FirDev a, const __grid_constant__ Taps taps) {
+    using G = Geom4<D, NT>;
+    __shared__ __align__(16) float sm[G::WORDS];
     const int s = blockIdx.z, b = blockIdx.y, n0 = blockIdx.x * G::TO;
     const float *xs = a.x + (long long)s * a.ldx;
     const float *x2s = a.x2 ? a.x2 + (long long)s * a.ldx : nullptr;
     const float *zs = a.zi + (long long)s * a.nzi;
     const int P0 = D * n0 - OFF;
-    constexpr int QUADS = (G::SPAN + 3) / 4;
     constexpr bool MIX = KIND == SRC_MIX_LATE || KIND == SRC_MIX_HALF;
     const float *xt = xs + (long long)b * a.n + P0;
     const float *x2t = MIX ? x2s + (long long)b * a.n + P0 : xt;
-    if (P0 >= 0 && P0 + 4 * QUADS <= a.n && (((uintptr_t)xt | (uintptr_t)x2t) & 15) == 0) {
-        // interior tile: every staged sample lies inside block b -> 128-bit loads, no per-sample case analysis
-        for (int j = threadIdx.x; j < QUADS; j += CT) {
+    if (P0 >= 0 && P0 + 4 * G::QUADS <= a.n && (((uintptr_t)xt | (uintptr_t)x2t) & 15) == 0) {
+        // interior tile: every staged sample lies inside block b -> 128-bit loads and stores, no per-sample case analysis
+        for (int j = threadIdx.x; j < G::QUADS; j += NT) {
             const float4 v = __ldg(reinterpret_cast<const float4 *>(xt) + j);
             float4 w = v;
             if (MIX) w = __ldg(reinterpret_cast<const float4 *>(x2t) + j);
-            const int i = 4 * j;
-            sm[G::phys(i)] = form<KIND>(v.x, w.x, true);
-            if (i + 1 < G::SPAN) sm[G::phys(i + 1)] = form<KIND>(v.y, w.y, true);
-            if (i + 2 < G::SPAN) sm[G::phys(i + 2)] = form<KIND>(v.z, w.z, true);
-            if (i + 3 < G::SPAN) sm[G::phys(i + 3)] = form<KIND>(v.w, w.w, true);
+            *reinterpret_cast<float4 *>(sm + G::phys(4 * j)) =
+                make_float4(form<KIND>(v.x, w.x, true), form<KIND>(v.y, w.y, true), form<KIND>(v.z, w.z, true), form<KIND>(v.w, w.w, true));
         }
     } else {
-        for (int i = threadIdx.x; i < G::SPAN; i += CT) sm[G::phys(i)] = source<KIND>(a, xs, x2s, zs, b, P0 + i);
+        for (int i = threadIdx.x; i < 4 * G::QUADS; i += NT) sm[G::phys(i)] = source<KIND>(a, xs, x2s, zs, b, P0 + i);
     }
     __syncthreads();
 
+    // thread t's window starts at logical index ROW*t = word PITCH*t; c = p + OFF is the index inside the window of the
+    // sample p positions after output 0's newest one, and output r uses it with tap k = D*r - p
     const float *w = sm + G::PITCH * threadIdx.x;
     float acc[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) acc[r] = 0.0f;
-    float v;
-#define LOADV(idx) v = w[idx]
-#define MACV(r, k) acc[r] = mac<EXACT>(acc[r], v, taps.h[k])
-    FMRX_TAP_LOOP(D, LOADV, MACV)
-#undef LOADV
-#undef MACV
+#pragma unroll
+    for (int q = G::QHI; q >= G::QLO; --q) {
+        const float4 v = *reinterpret_cast<const float4 *>(w + G::phys(4 * q));
+        const float xv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 3; e >= 0; --e) {  // newest sample first
+            const int p_ = 4 * q + e - OFF;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int k = D * r - p_;
+                if (k >= 0 && k < kTaps) acc[r] = mac<EXACT>(acc[r], xv[e], taps.h[k]);
+            }
+        }
+    }
     const int o = n0 + R * threadIdx.x;
     float *ys = a.y + (long long)s * a.ldy + (long long)b * a.ny + o;
     if (o + R <= a.ny && ((reinterpret_cast<uintptr_t>(ys) & 15) == 0)) {
@@ -443,11 +465,20 @@ Taps make_taps(const float *h) {
     return t;
 }
 
+constexpr int CT_RRC = 152;  // 8 * 152 = 1216 outputs per tile: the 3648-sample RDS blocks are exactly three tiles
+
 template <int D, int KIND>
 int launch_fir_dk(const FirJob &j, const FirDev &d, dim3 grid, fmrx_stream_t st) {
     const Taps t = make_taps(j.h);
-    if (j.exact) fir151_kernel<D, KIND, true><<<grid, CT, 0, st>>>(d, t);
-    else fir151_kernel<D, KIND, false><<<grid, CT, 0, st>>>(d, t);
+    if (D == 1 && KIND == SRC_PLAIN && d.ny % (R * CT_RRC) == 0 && d.ny % (R * CT) != 0) {
+        constexpr int DD = D == 1 && KIND == SRC_PLAIN ? D : 1, KK = D == 1 && KIND == SRC_PLAIN ? KIND : SRC_PLAIN;  // instantiated once only
+        grid.x = d.ny / (R * CT_RRC);
+        if (j.exact) fir151_kernel<DD, KK, true, CT_RRC><<<grid, CT_RRC, 0, st>>>(d, t);
+        else fir151_kernel<DD, KK, false, CT_RRC><<<grid, CT_RRC, 0, st>>>(d, t);
+        return (int)cudaGetLastError();
+    }
+    if (j.exact) fir151_kernel<D, KIND, true, CT><<<grid, CT, 0, st>>>(d, t);
+    else fir151_kernel<D, KIND, false, CT><<<grid, CT, 0, st>>>(d, t);
     return (int)cudaGetLastError();
 }
 

@@ -65,12 +65,15 @@ struct ResampleJob {
     float *y;        // [S][ldy]
     float *zi;       // [S][nzi]
     const float *h;  // DEVICE taps [ntaps]
+    const float *h_host;  // the same taps in HOST memory, or null: lets the tiled fast path (fmrx_resample.cu) pass them by value
     long long ldx, ldy;
     // n = samples per block in memory; n_ref = the length the reference's vector had (differs only for the RDS resampler,
     // whose input is the 15361-long mixer output, src/fm_radio.cpp:404-408); ny = outputs per block actually produced
     int n, n_ref, ny, n_blocks, n_streams, ntaps, nzi, decim, up, gain_up, exact;
 };
 int launch_resample(const ResampleJob &j, fmrx_stream_t st);
+// register-tiled fast path for the RDS 19/80 geometry; returns -1 (nothing launched) when `j` is any other job
+int launch_resample_tiled(const ResampleJob &j, fmrx_stream_t st);
 
 struct PllParams {
     float freq, Fs, scale, phase_adj, bw;
@@ -97,6 +100,13 @@ int launch_rds_decode(const float *rrc, long long ld, int n_streams, int n_block
                       fmrx_rds_event *events, int32_t *n_events, int32_t *state, fmrx_stream_t st);
 
 int measure_fp32_peak(int device, int kind, int reps, double *tera);
+
+// SM partition (green contexts) for the device-resident pipeline, fmrx_partition.cu.  partition_create returns nullptr
+// when the driver cannot split the device; the caller then falls back to priority streams on the whole device.
+struct SmPartition;
+SmPartition *partition_create(int device, int want_small, int prio_small, fmrx_stream_t *s_small, int n_big, const int *prio_big, fmrx_stream_t *s_big);
+void partition_destroy(SmPartition *p);
+void partition_sizes(const SmPartition *p, int *small, int *big);
 
 }  // namespace fmrx
 #endif

@@ -182,17 +182,22 @@ __global__ void rds_decode_kernel(const float *rrc, long long ld, int n_streams,
 
 int launch_resample(const ResampleJob &j, fmrx_stream_t st) {
     ResDev d;
+    const int fast = launch_resample_tiled(j, st);  // the RDS 19/80 geometry; anything else falls through to the general kernel
+    if (fast > 0) return fast;
     d.x = j.x; d.y = j.y; d.zi = j.zi; d.h = j.h; d.ldx = j.ldx; d.ldy = j.ldy;
     d.n = j.n; d.n_ref = j.n_ref;
     d.ny = j.ny; d.n_blocks = j.n_blocks; d.ntaps = j.ntaps; d.nzi = j.nzi; d.decim = j.decim; d.up = j.up; d.gain_up = j.gain_up;
     dim3 grid((j.ny + 127) / 128, j.n_blocks, j.n_streams);
-    if (j.exact) resample_kernel<true><<<grid, 128, 0, st>>>(d);
-    else resample_kernel<false><<<grid, 128, 0, st>>>(d);
+    if (fast < 0) {
+        if (j.exact) resample_kernel<true><<<grid, 128, 0, st>>>(d);
+        else resample_kernel<false><<<grid, 128, 0, st>>>(d);
+        launch_counter() += 1;
+    }
     cudaError_t e = cudaGetLastError();
     if (e) return (int)e;
     dim3 sg((j.nzi + 255) / 256, j.n_streams);
     resample_state_kernel<<<sg, 256, 0, st>>>(d);
-    launch_counter() += 2;
+    launch_counter() += 1;
     return (int)cudaGetLastError();
 }
 

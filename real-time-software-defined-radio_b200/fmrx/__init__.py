@@ -98,6 +98,7 @@ SIGNATURES = {
     "fmrx_batch_state_bytes": (C.c_size_t, [C.c_void_p]),
     "fmrx_batch_get_state": (C.c_int, [C.c_void_p, C.c_void_p]),
     "fmrx_batch_set_state": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "fmrx_batch_partition": (C.c_int, [C.c_void_p, i32p, i32p]),
     "fmrx_batch_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "fmrx_batch_stage_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "fmrx_batch_timeline": (C.c_int, [C.c_void_p, C.c_int, i32p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
@@ -367,6 +368,12 @@ class Batch:
             ne = int(res["rds_n_events"][stream, b])
             out.append(rds_format_block(res["first_block"] + b, off, res["rds_events"][stream, b, :ne]))
         return "".join(out)
+
+    def partition(self):
+        """(SMs owned by the PLL phase, SMs owned by the filter phases); (0, 0) when the phases share the device."""
+        a, b = C.c_int32(), C.c_int32()
+        check(lib().fmrx_batch_partition(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def profile(self, enable=True):
         """True / 1: per-stage timing with the phases serialised; 2: timeline mode (pipeline kept); False: off."""
