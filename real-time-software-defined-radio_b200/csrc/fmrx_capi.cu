@@ -264,6 +264,7 @@ constexpr int NIF = FMRX_IF_PER_BLOCK;
 constexpr int NRDS = FMRX_RDS_PER_BLOCK;
 constexpr double kPi = 3.14159265358979323846;
 constexpr int kMaxChunks = 8;
+constexpr int kSets = 3;       // rotating buffer sets of the device-resident pipeline
 
 }  // namespace
 
@@ -296,14 +297,16 @@ struct fmrx_batch {
     cudaEvent_t e_in[kMaxChunks]{}, e_done[kMaxChunks]{}, e_out[kMaxChunks]{};
     // device-resident pipeline: filters before the PLLs, the PLLs, and everything after them run on three streams, so
     // that step k's (latency-bound, few-warp) PLL kernel overlaps step k+1's front end and step k-1's back end.  The
-    // signals crossing a phase boundary are double-buffered (`set`).
+    // signals crossing a phase boundary are kept in kSets rotating buffer sets (`set`): with two, phase A of call k+2
+    // waits for phase C of call k, which waits for call k's PLLs -- every other step the PLL partition idled for the length
+    // of phase A (fmrx_batch_timeline); with three the only steady-state limit is the slowest phase.
     // When the batch is large enough to fill the device, the PLL stream lives in a green context with SMs of its own
     // and the two filter streams in a second one with the rest (fmrx_partition.cu); s_ser is a whole-device stream for
     // the serialised per-stage profiling pass.
     cudaStream_t s_a = nullptr, s_p = nullptr, s_c = nullptr, s_ser = nullptr;
     fmrx::SmPartition *part = nullptr;
-    cudaEvent_t ev_a[2]{}, ev_p[2]{}, ev_c[2]{};
-    bool ev_c_valid[2] = {false, false};
+    cudaEvent_t ev_a[kSets]{}, ev_p[kSets]{}, ev_c[kSets]{};
+    bool ev_c_valid[kSets] = {};
     bool was_serial = false;
     long long calls = 0;
     int last_set = 0;
@@ -324,7 +327,7 @@ struct fmrx_batch {
         for (void *p : allocs) cudaFree(p);
         for (auto e : prof_pool) cudaEventDestroy(e);
         for (int i = 0; i < kMaxChunks; ++i) { if (e_in[i]) cudaEventDestroy(e_in[i]); if (e_done[i]) cudaEventDestroy(e_done[i]); if (e_out[i]) cudaEventDestroy(e_out[i]); }
-        for (int i = 0; i < 2; ++i) { if (ev_a[i]) cudaEventDestroy(ev_a[i]); if (ev_p[i]) cudaEventDestroy(ev_p[i]); if (ev_c[i]) cudaEventDestroy(ev_c[i]); }
+        for (int i = 0; i < kSets; ++i) { if (ev_a[i]) cudaEventDestroy(ev_a[i]); if (ev_p[i]) cudaEventDestroy(ev_p[i]); if (ev_c[i]) cudaEventDestroy(ev_c[i]); }
         for (auto st : {s_a, s_p, s_c, s_ser}) if (st) cudaStreamDestroy(st);
         fmrx::partition_destroy(part);
         if (s_in) cudaStreamDestroy(s_in);
@@ -352,7 +355,7 @@ int init_state(fmrx_batch *b) {
     CU(cudaStreamSynchronize(b->s_cmp[0]));
     b->block_id = 0;
     b->calls = 0;
-    b->ev_c_valid[0] = b->ev_c_valid[1] = false;
+    for (bool &v : b->ev_c_valid) v = false;
     return FMRX_OK;
 }
 
@@ -572,13 +575,13 @@ int fmrx_batch_create(const fmrx_config *cfg, fmrx_batch **out) {
     CU(b->dalloc(b->d_iq, S * NB * FMRX_BLOCK_BYTES));
     CU(b->dalloc(b->demod, S * NB * NIF));
     if (b->audio_on) {
-        CU(b->dalloc(b->mono, 2 * S * NB * b->n_audio)); CU(b->dalloc(b->pilot, 2 * S * NB * NIF)); CU(b->dalloc(b->nco, 2 * S * NB * NIF));
-        CU(b->dalloc(b->sbpf, 2 * S * NB * NIF)); CU(b->dalloc(b->stereo, S * NB * b->n_audio));
+        CU(b->dalloc(b->mono, kSets * S * NB * b->n_audio)); CU(b->dalloc(b->pilot, kSets * S * NB * NIF)); CU(b->dalloc(b->nco, kSets * S * NB * NIF));
+        CU(b->dalloc(b->sbpf, kSets * S * NB * NIF)); CU(b->dalloc(b->stereo, S * NB * b->n_audio));
         if (cfg->mode == 1) CU(b->dalloc(b->mixed, S * NB * NIF));
         CU(b->dalloc(b->audio, S * NB * b->n_audio * 2)); CU(b->dalloc(b->audio_f, S * NB * b->n_audio * 2));
     }
     if (b->rds_on) {
-        CU(b->dalloc(b->rbpf, 2 * S * NB * NIF)); CU(b->dalloc(b->rsq, 2 * S * NB * NIF)); CU(b->dalloc(b->rnco, 2 * S * NB * NIF)); CU(b->dalloc(b->rlpf, S * NB * NIF));
+        CU(b->dalloc(b->rbpf, kSets * S * NB * NIF)); CU(b->dalloc(b->rsq, kSets * S * NB * NIF)); CU(b->dalloc(b->rnco, kSets * S * NB * NIF)); CU(b->dalloc(b->rlpf, S * NB * NIF));
         CU(b->dalloc(b->rres, S * NB * NRDS)); CU(b->dalloc(b->rrrc, S * NB * NRDS));
         CU(b->dalloc(b->bits, S * NB * FMRX_MAX_BITS)); CU(b->dalloc(b->nbits, S * NB)); CU(b->dalloc(b->nev, S * NB)); CU(b->dalloc(b->ev, S * NB * FMRX_MAX_EVENTS));
         CU(cudaMemset(b->bits, 0, S * NB * FMRX_MAX_BITS));
@@ -609,7 +612,7 @@ int fmrx_batch_create(const fmrx_config *cfg, fmrx_batch **out) {
         }
         CU(cudaStreamCreateWithFlags(&b->s_ser, cudaStreamNonBlocking));
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kSets; ++i) {
         CU(cudaEventCreateWithFlags(&b->ev_a[i], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&b->ev_p[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&b->ev_c[i], cudaEventDisableTiming));
     }
@@ -658,8 +661,8 @@ int fmrx_batch_process_device(fmrx_batch *b, const uint8_t *iq_device, int n_blo
     CU(cudaSetDevice(b->cfg.device));
     fmrx_outputs none{};
     const fmrx_outputs &o = out_device ? *out_device : none;
-    const int set = (int)(b->calls & 1);
-    // phase A of this call overwrites the buffer set phase C of the call before last was reading
+    const int set = (int)(b->calls % kSets);
+    // phase A of this call overwrites the buffer set phase C of the call kSets back was reading
     if (b->ev_c_valid[set] && !(b->profiling && !b->profile_pipelined)) CU(cudaStreamWaitEvent(b->s_a, b->ev_c[set], 0));
     // while per-stage profiling is on, the three phases are serialised on one stream so that every stage is timed alone
     const bool serial = b->profiling && !b->profile_pipelined;

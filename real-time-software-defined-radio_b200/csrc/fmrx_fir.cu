@@ -49,18 +49,23 @@ struct Geom {
     __host__ __device__ static constexpr int phys(int i) { return i + i / ROW; }
 };
 
-// quad-aligned geometry of the single-channel kernel
-template <int D, int NT>
+// quad-aligned geometry of the single-channel kernel: a thread computes RO consecutive outputs per pass and makes
+// PASSES passes (pass h = rows t + h*NT), so a tile is RO*PASSES*NT outputs whatever the split.  The exact
+// (FMUL + FADD) kernels use RO = 4 x 2 passes: their unrolled body for 8 outputs is 40 KB of code, more than the
+// instruction cache holds (ncu, profiles/r1k: icc hit rate 78%, stalled_no_instruction 2.6-8.1 per issue against 0.18
+// for the 23 KB FFMA body); one 4-output body run twice is 21 KB.
+template <int D, int NT, int RO, int PASSES>
 struct Geom4 {
-    static constexpr int TO = R * NT;
-    static constexpr int ROW = D * R;
-    static constexpr int PITCH = ROW + 4;
-    static_assert(ROW % 8 == 0 && OFF % 4 == 0, "rows and the tile origin must keep 128-bit alignment; (ROW+4)/4 must be odd");
+    static constexpr int TO = RO * PASSES * NT;
+    static constexpr int ROW = D * RO;
+    static_assert(ROW % 4 == 0 && OFF % 4 == 0, "rows and the tile origin must keep 128-bit alignment");
+    static constexpr int PAD = (ROW / 4) % 2 == 0 ? 4 : 8;  // (ROW + PAD) / 4 odd: a quarter-warp's LDS.128 covers all 32 banks
+    static constexpr int PITCH = ROW + PAD;
     static constexpr int SPAN = D * (TO - 1) + OFF + 1;
     static constexpr int QUADS = (SPAN + 3) / 4;
     static constexpr int WORDS = ((4 * QUADS + ROW - 1) / ROW) * PITCH;
-    static constexpr int QHI = (D * (R - 1) + OFF) / 4, QLO = (OFF - kHist) / 4;  // quads one thread touches
-    __host__ __device__ static constexpr int phys(int i) { return i + 4 * (i / ROW); }
+    static constexpr int QHI = (D * (RO - 1) + OFF) / 4, QLO = (OFF - kHist) / 4;  // quads one thread touches per pass
+    __host__ __device__ static constexpr int phys(int i) { return i + PAD * (i / ROW); }
 };
 
 template <bool EXACT>
@@ -125,7 +130,8 @@ __device__ __forceinline__ float source(const FirDev &a, const float *xs, const 
 // ------------------------------------------------------------------------------------------------------------------
 template <int D, int KIND, bool EXACT, int NT>
 __global__ void __launch_bounds__(NT) fir151_kernel(const FirDev a, const __grid_constant__ Taps taps) {
-    using G = Geom4<D, NT>;
+    constexpr int RO = EXACT ? 4 : 8, PASSES = R / RO;
+    using G = Geom4<D, NT, RO, PASSES>;
     __shared__ __align__(16) float sm[G::WORDS];
     const int s = blockIdx.z, b = blockIdx.y, n0 = blockIdx.x * G::TO;
     const float *xs = a.x + (long long)s * a.ldx;
@@ -136,48 +142,59 @@ __global__ void __launch_bounds__(NT) fir151_kernel(const FirDev a, const __grid
     const float *xt = xs + (long long)b * a.n + P0;
     const float *x2t = MIX ? x2s + (long long)b * a.n + P0 : xt;
     if (P0 >= 0 && P0 + 4 * G::QUADS <= a.n && (((uintptr_t)xt | (uintptr_t)x2t) & 15) == 0) {
-        // interior tile: every staged sample lies inside block b -> 128-bit loads and stores, no per-sample case analysis
-        for (int j = threadIdx.x; j < G::QUADS; j += NT) {
-            const float4 v = __ldg(reinterpret_cast<const float4 *>(xt) + j);
-            float4 w = v;
-            if (MIX) w = __ldg(reinterpret_cast<const float4 *>(x2t) + j);
-            *reinterpret_cast<float4 *>(sm + G::phys(4 * j)) =
-                make_float4(form<KIND>(v.x, w.x, true), form<KIND>(v.y, w.y, true), form<KIND>(v.z, w.z, true), form<KIND>(v.w, w.w, true));
+        // interior tile: every staged sample lies inside block b -> 128-bit loads and stores, no per-sample case
+        // analysis; the loop is unrolled so that all of a thread's loads are in flight before the first store
+        constexpr int ITERS = (G::QUADS + NT - 1) / NT;
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) {
+            const int j = threadIdx.x + it * NT;
+            if (j < G::QUADS) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(xt) + j);
+                float4 w = v;
+                if (MIX) w = __ldg(reinterpret_cast<const float4 *>(x2t) + j);
+                *reinterpret_cast<float4 *>(sm + G::phys(4 * j)) =
+                    make_float4(form<KIND>(v.x, w.x, true), form<KIND>(v.y, w.y, true), form<KIND>(v.z, w.z, true), form<KIND>(v.w, w.w, true));
+            }
         }
     } else {
         for (int i = threadIdx.x; i < 4 * G::QUADS; i += NT) sm[G::phys(i)] = source<KIND>(a, xs, x2s, zs, b, P0 + i);
     }
     __syncthreads();
 
-    // thread t's window starts at logical index ROW*t = word PITCH*t; c = p + OFF is the index inside the window of the
-    // sample p positions after output 0's newest one, and output r uses it with tap k = D*r - p
-    const float *w = sm + G::PITCH * threadIdx.x;
-    float acc[R];
+#pragma unroll 1
+    for (int h = 0; h < PASSES; ++h) {
+        // row = threadIdx.x + h*NT: its window starts at logical index ROW*row = word PITCH*row; c = p + OFF is the index
+        // inside the window of the sample p positions after the row's first output's newest one, and output r uses it
+        // with tap k = D*r - p
+        const int row = threadIdx.x + h * NT;
+        const float *w = sm + G::PITCH * row;
+        float acc[RO];
 #pragma unroll
-    for (int r = 0; r < R; ++r) acc[r] = 0.0f;
+        for (int r = 0; r < RO; ++r) acc[r] = 0.0f;
 #pragma unroll
-    for (int q = G::QHI; q >= G::QLO; --q) {
-        const float4 v = *reinterpret_cast<const float4 *>(w + G::phys(4 * q));
-        const float xv[4] = {v.x, v.y, v.z, v.w};
+        for (int q = G::QHI; q >= G::QLO; --q) {
+            const float4 v = *reinterpret_cast<const float4 *>(w + G::phys(4 * q));
+            const float xv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int e = 3; e >= 0; --e) {  // newest sample first
-            const int p_ = 4 * q + e - OFF;
+            for (int e = 3; e >= 0; --e) {  // newest sample first
+                const int p_ = 4 * q + e - OFF;
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const int k = D * r - p_;
-                if (k >= 0 && k < kTaps) acc[r] = mac<EXACT>(acc[r], xv[e], taps.h[k]);
+                for (int r = 0; r < RO; ++r) {
+                    const int k = D * r - p_;
+                    if (k >= 0 && k < kTaps) acc[r] = mac<EXACT>(acc[r], xv[e], taps.h[k]);
+                }
             }
         }
-    }
-    const int o = n0 + R * threadIdx.x;
-    float *ys = a.y + (long long)s * a.ldy + (long long)b * a.ny + o;
-    if (o + R <= a.ny && ((reinterpret_cast<uintptr_t>(ys) & 15) == 0)) {
-        reinterpret_cast<float4 *>(ys)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        reinterpret_cast<float4 *>(ys)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-    } else {
+        const int o = n0 + RO * row;
+        float *ys = a.y + (long long)s * a.ldy + (long long)b * a.ny + o;
+        if (o + RO <= a.ny && ((reinterpret_cast<uintptr_t>(ys) & 15) == 0)) {
 #pragma unroll
-        for (int r = 0; r < R; ++r)
-            if (o + r < a.ny) ys[r] = acc[r];
+            for (int r = 0; r < RO; r += 4) reinterpret_cast<float4 *>(ys)[r / 4] = make_float4(acc[r], acc[r + 1], acc[r + 2], acc[r + 3]);
+        } else {
+#pragma unroll
+            for (int r = 0; r < RO; ++r)
+                if (o + r < a.ny) ys[r] = acc[r];
+        }
     }
 }
 

@@ -135,14 +135,21 @@ __global__ void resample_fix_kernel(const PolyDev a, int total) {
     const float *xs = a.x + (long long)s * a.ldx;
     const float *zs = a.zi + (long long)s * a.nzi;
     float *ys = a.y + (long long)s * a.ldy + (long long)b * a.ny;
+    // history values live at indices (nzi-1-c)/U of the carried state (block 0) or of the previous block's tail
+    const float *hist = b > 0 ? xs + (long long)(b - 1) * a.n + (a.n_ref - a.nzi - 1) : zs;
     for (int o = lane; o < G::NFIX && o < a.ny; o += 32) {
         const int base = D * o, k0 = base % U, q0 = base / U;
+        const float *hp = a.h + k0;
         float acc = ys[o];
-        for (int c = q0 + 1; c < TPP; ++c) {
-            const int j = (a.nzi - 1 - c) / U;
-            const float v = b > 0 ? xs[(long long)(b - 1) * a.n + (a.n_ref - a.nzi - 1 + j)] : zs[j];
-            acc = fmaf(v, a.h[k0 + U * c], acc);
+        int c = q0 + 1;
+        for (; c + 8 <= TPP; c += 8) {  // loads of a batch are independent of the sum: all in flight before the eight dependent FMAs
+            float t[8], v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { t[u] = __ldg(hp + U * (c + u)); v[u] = __ldg(hist + (a.nzi - 1 - (c + u)) / U); }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc = fmaf(v[u], t[u], acc);
         }
+        for (; c < TPP; ++c) acc = fmaf(__ldg(hist + (a.nzi - 1 - c) / U), __ldg(hp + U * c), acc);
         ys[o] = a.gain_up ? __fmul_rn(acc, (float)U) : acc;
     }
 }
