@@ -141,20 +141,37 @@ __global__ void __launch_bounds__(NT) fir151_kernel(const FirDev a, const __grid
     constexpr bool MIX = KIND == SRC_MIX_LATE || KIND == SRC_MIX_HALF;
     const float *xt = xs + (long long)b * a.n + P0;
     const float *x2t = MIX ? x2s + (long long)b * a.n + P0 : xt;
-    if (P0 >= 0 && P0 + 4 * G::QUADS <= a.n && (((uintptr_t)xt | (uintptr_t)x2t) & 15) == 0) {
-        // interior tile: every staged sample lies inside block b -> 128-bit loads and stores, no per-sample case
-        // analysis; the loop is unrolled so that all of a thread's loads are in flight before the first store
+    if ((a.n & 3) == 0 && (((uintptr_t)xt | (uintptr_t)x2t) & 15) == 0) {
+        // P0 and n are multiples of 4, so a quad lies wholly inside block b or wholly outside it.  Inside: 128-bit
+        // traffic, no per-sample case analysis (PLAIN has nothing to form: asynchronous 16-byte copies straight into
+        // the padded tile, LDGSTS, no register staging).  Outside (the 168 history samples of a block's first tile,
+        // padding past the end): sample by sample.  The loop is unrolled so that all loads of a thread are in flight
+        // before its first store.
         constexpr int ITERS = (G::QUADS + NT - 1) / NT;
+        const unsigned sbase = (unsigned)__cvta_generic_to_shared(sm);
 #pragma unroll
         for (int it = 0; it < ITERS; ++it) {
             const int j = threadIdx.x + it * NT;
-            if (j < G::QUADS) {
-                const float4 v = __ldg(reinterpret_cast<const float4 *>(xt) + j);
-                float4 w = v;
-                if (MIX) w = __ldg(reinterpret_cast<const float4 *>(x2t) + j);
-                *reinterpret_cast<float4 *>(sm + G::phys(4 * j)) =
-                    make_float4(form<KIND>(v.x, w.x, true), form<KIND>(v.y, w.y, true), form<KIND>(v.z, w.z, true), form<KIND>(v.w, w.w, true));
+            if (j >= G::QUADS) break;
+            const int p = P0 + 4 * j;
+            float *dst = sm + G::phys(4 * j);
+            if (p >= 0 && p + 4 <= a.n) {
+                if (KIND == SRC_PLAIN) {
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + 4u * (unsigned)G::phys(4 * j)), "l"(xt + 4 * j) : "memory");
+                } else {
+                    const float4 v = __ldg(reinterpret_cast<const float4 *>(xt) + j);
+                    float4 w = v;
+                    if (MIX) w = __ldg(reinterpret_cast<const float4 *>(x2t) + j);
+                    *reinterpret_cast<float4 *>(dst) = make_float4(form<KIND>(v.x, w.x, true), form<KIND>(v.y, w.y, true), form<KIND>(v.z, w.z, true), form<KIND>(v.w, w.w, true));
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) dst[e] = source<KIND>(a, xs, x2s, zs, b, p + e);
             }
+        }
+        if (KIND == SRC_PLAIN) {
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
     } else {
         for (int i = threadIdx.x; i < 4 * G::QUADS; i += NT) sm[G::phys(i)] = source<KIND>(a, xs, x2s, zs, b, P0 + i);

@@ -71,18 +71,28 @@ __global__ void __launch_bounds__(64) resample_tile_kernel(const PolyDev a, cons
     const int s = blockIdx.z, b = blockIdx.y, g0 = blockIdx.x * G::NT;
     const float *xb = a.x + (long long)s * a.ldx + (long long)b * a.n;
     const int P0 = D * g0 - G::LEAD;  // block-relative position of staged sample 0 (a multiple of 4)
-    for (int j = threadIdx.x; j < G::SPAN / 4; j += G::NT) {
-        const int p = P0 + 4 * j;
-        float4 v;
-        if (p >= 0 && p + 4 <= a.n && ((uintptr_t)(xb + p) & 15) == 0) {
-            v = __ldg(reinterpret_cast<const float4 *>(xb + p));
-        } else {  // block edges: positions outside the block contribute nothing to the in-block sum
+    if ((a.n & 3) == 0 && ((uintptr_t)xb & 15) == 0) {
+        // asynchronous 16-byte copies straight into the padded tile (LDGSTS): every quad of a thread is in flight at once
+        // and none of them occupies a register.  P0 and n are multiples of 4, so a quad is wholly inside the block or
+        // wholly outside it; outside = zero fill (src-size 0): those positions contribute nothing to the in-block sum.
+        const unsigned sbase = (unsigned)__cvta_generic_to_shared(sm);
+        for (int j = threadIdx.x; j < G::SPAN / 4; j += G::NT) {
+            const int p = P0 + 4 * j;
+            const bool in = p >= 0 && p + 4 <= a.n;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sbase + 4u * (unsigned)G::phys(4 * j)), "l"(in ? xb + p : xb), "r"(in ? 16 : 0));
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else {
+        for (int j = threadIdx.x; j < G::SPAN / 4; j += G::NT) {
+            const int p = P0 + 4 * j;
+            float4 v;
             v.x = (p >= 0 && p < a.n) ? xb[p] : 0.0f;
             v.y = (p + 1 >= 0 && p + 1 < a.n) ? xb[p + 1] : 0.0f;
             v.z = (p + 2 >= 0 && p + 2 < a.n) ? xb[p + 2] : 0.0f;
             v.w = (p + 3 >= 0 && p + 3 < a.n) ? xb[p + 3] : 0.0f;
+            *reinterpret_cast<float4 *>(sm + G::phys(4 * j)) = v;
         }
-        *reinterpret_cast<float4 *>(sm + G::phys(4 * j)) = v;
     }
     __syncthreads();
 
