@@ -175,7 +175,7 @@ def run_fmrx_arm(args, rank, world, local_rank):
     import torch.distributed as dist
 
     import fmrx
-    from fmrx import synth
+    from fmrx import shard, synth
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -195,7 +195,7 @@ def run_fmrx_arm(args, rank, world, local_rank):
         return float(t.item())
 
     S, B = args.stations, args.blocks
-    stations = range(rank * S, rank * S + S)
+    stations = shard.weak_range(S, rank)  # weak scaling: every rank owns S stations, numbered globally; no collective on the data path
     t0 = time.perf_counter()
     d_iq = synth.synth_batch_torch(stations, B, 0, dev, chunk=64)
     torch.cuda.synchronize()
@@ -353,7 +353,7 @@ def main():
     ap.add_argument("--impl", default="fmrx", choices=["fmrx", "reference"])
     ap.add_argument("--stations", type=int, default=4096, help="stations per GPU")
     ap.add_argument("--blocks", type=int, default=1, help="blocks per station per step")
-    ap.add_argument("--cpu-blocks", type=int, default=16, help="blocks per process of the CPU baseline sample")
+    ap.add_argument("--cpu-blocks", type=int, default=48, help="blocks per process of the CPU baseline sample")
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--device-only", action="store_true", help="tuning aid: device-resident number and stage times only (not a bench line)")
     args = ap.parse_args()
