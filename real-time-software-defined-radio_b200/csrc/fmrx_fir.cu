@@ -49,28 +49,52 @@ struct Geom {
     __host__ __device__ static constexpr int phys(int i) { return i + i / ROW; }
 };
 
-// quad-aligned geometry of the single-channel kernel: a thread computes RO consecutive outputs per pass and makes
-// PASSES passes (pass h = rows t + h*NT), so a tile is RO*PASSES*NT outputs whatever the split.  The exact
-// (FMUL + FADD) kernels use RO = 4 x 2 passes: their unrolled body for 8 outputs is 40 KB of code, more than the
-// instruction cache holds (ncu, profiles/r1k: icc hit rate 78%, stalled_no_instruction 2.6-8.1 per issue against 0.18
-// for the 23 KB FFMA body); one 4-output body run twice is 21 KB.
-template <int D, int NT, int RO, int PASSES>
-struct Geom4 {
-    static constexpr int TO = RO * PASSES * NT;
-    static constexpr int ROW = D * RO;
+// Geometry of the single-channel kernel.  A thread owns TWO rows of RO consecutive outputs each (rows t and t + NT of
+// the tile) and computes them together on the packed fp32x2 pipe form: the tile is staged as PAIRS, entry i =
+// (x[i], x[i + NT*ROW]), so that one 128-bit LDS delivers two consecutive samples of both rows as two ready-made
+// register pairs, and every tap is one FFMA2 (two for the exact form) with the tap as a broadcast scalar operand.
+// Row pitch = 2*ROW floats + a pad that keeps 16-byte alignment and makes pitch/4 odd, so the LDS.128 of a quarter
+// warp cover all 32 banks; staging stores are 128-bit too.  RO = 8 for the fused-multiply-add kernels, 4 for the
+// exact ones: the unrolled body is then 1208 FFMA2 = 19 KB either way and stays inside the instruction cache (the first
+// exact version, 2416 FMUL/FADD = 40 KB, ran with an icc hit rate of 78%: profiles/r1k_kernels.md).
+template <int D, int NT, int RO>
+struct GeomP {
+    static constexpr int TO = 2 * RO * NT;                 // outputs per tile
+    static constexpr int ROW = D * RO;                     // input samples between consecutive rows
+    static constexpr int HALF = ROW * NT;                  // distance between the two rows of one thread
     static_assert(ROW % 4 == 0 && OFF % 4 == 0, "rows and the tile origin must keep 128-bit alignment");
-    static constexpr int PAD = (ROW / 4) % 2 == 0 ? 4 : 8;  // (ROW + PAD) / 4 odd: a quarter-warp's LDS.128 covers all 32 banks
-    static constexpr int PITCH = ROW + PAD;
-    static constexpr int SPAN = D * (TO - 1) + OFF + 1;
-    static constexpr int QUADS = (SPAN + 3) / 4;
-    static constexpr int WORDS = ((4 * QUADS + ROW - 1) / ROW) * PITCH;
-    static constexpr int QHI = (D * (RO - 1) + OFF) / 4, QLO = (OFF - kHist) / 4;  // quads one thread touches per pass
-    __host__ __device__ static constexpr int phys(int i) { return i + PAD * (i / ROW); }
+    static constexpr int PADF = ((2 * ROW) / 4) % 2 == 0 ? 4 : 8;
+    static constexpr int PITCHF = 2 * ROW + PADF;          // floats per row of pairs
+    static constexpr int PQHI = (D * (RO - 1) + OFF) / 2, PQLO = (OFF - kHist) / 2;  // sample pairs (c, c+1), c = 2*pq, one thread touches
+    static constexpr int NP = ((ROW * (NT - 1) + 2 * (PQHI + 1)) + 3) / 4 * 4;       // pair entries staged
+    static constexpr int NPQ = NP / 4;
+    static constexpr int WORDS = ((NP + ROW - 1) / ROW) * PITCHF;
+    __host__ __device__ static constexpr int physf(int i) { return 2 * i + PADF * (i / ROW); }  // float index of entry i
 };
 
 template <bool EXACT>
 __device__ __forceinline__ float mac(float acc, float x, float h) {
     return EXACT ? __fadd_rn(acc, __fmul_rn(x, h)) : fmaf(x, h, acc);
+}
+
+// The same tap on a PAIR of lanes with the packed fp32x2 pipe form (FFMA2, sm_100): one instruction, two lanes, the
+// tap as a scalar operand broadcast to both.  FFMA2 has the lane throughput of FFMA (bench.py peak kinds 0 and 2), so
+// the FP32 pipe time is unchanged, but the pipe is fed with half the issue slots and the other half is free for the
+// loads, conversions and constant fetches that otherwise compete with the taps for them.
+// EXACT keeps the reference's two roundings: fma(x, h, -0) IS the rounded product (adding -0 changes neither value nor
+// the sign of a zero) and fma(p, 1, acc) IS the rounded sum.  The -0 and the 1 arrive as kernel parameters: there is no
+// packed FMUL/FADD in SASS, and with literal constants ptxas folds the pair into a single FFMA2 -- one rounding
+// (checked with cuobjdump on bench kind 3).
+struct Exact2 {
+    float negzero, one;
+};
+template <bool EXACT>
+__device__ __forceinline__ float2 mac2(float2 acc, float2 x, float h, const Exact2 &c) {
+    if (EXACT) {
+        const float2 p = __ffma2_rn(x, make_float2(h, h), make_float2(c.negzero, c.negzero));
+        return __ffma2_rn(p, make_float2(c.one, c.one), acc);
+    }
+    return __ffma2_rn(x, make_float2(h, h), acc);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -128,89 +152,87 @@ __device__ __forceinline__ float source(const FirDev &a, const float *xs, const 
 // ------------------------------------------------------------------------------------------------------------------
 // single-channel kernel
 // ------------------------------------------------------------------------------------------------------------------
+template <int KIND>
+__device__ __forceinline__ float4 stage_quad(const FirDev &a, const float *xs, const float *x2s, const float *zs, const float *xt, const float *x2t,
+                                             int b, int P0, int i, bool vec_ok) {
+    // four consecutive input samples starting at tile index i (block position P0 + i), formed
+    const int p = P0 + i;
+    if (vec_ok && p >= 0 && p + 4 <= a.n) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(xt + i));
+        float4 w = v;
+        if (KIND == SRC_MIX_LATE || KIND == SRC_MIX_HALF) w = __ldg(reinterpret_cast<const float4 *>(x2t + i));
+        return make_float4(form<KIND>(v.x, w.x, true), form<KIND>(v.y, w.y, true), form<KIND>(v.z, w.z, true), form<KIND>(v.w, w.w, true));
+    }
+    // outside the block (the 168 history samples of a block's first tile, padding past the end): sample by sample
+    return make_float4(source<KIND>(a, xs, x2s, zs, b, p), source<KIND>(a, xs, x2s, zs, b, p + 1), source<KIND>(a, xs, x2s, zs, b, p + 2),
+                       source<KIND>(a, xs, x2s, zs, b, p + 3));
+}
+
 template <int D, int KIND, bool EXACT, int NT>
-__global__ void __launch_bounds__(NT) fir151_kernel(const FirDev a, const __grid_constant__ Taps taps) {
-    constexpr int RO = EXACT ? 4 : 8, PASSES = R / RO;
-    using G = Geom4<D, NT, RO, PASSES>;
+__global__ void __launch_bounds__(NT) fir151_kernel(const FirDev a, const __grid_constant__ Taps taps, const Exact2 ex) {
+    constexpr int RO = EXACT ? 4 : 8;
+    using G = GeomP<D, NT, RO>;
     __shared__ __align__(16) float sm[G::WORDS];
     const int s = blockIdx.z, b = blockIdx.y, n0 = blockIdx.x * G::TO;
     const float *xs = a.x + (long long)s * a.ldx;
     const float *x2s = a.x2 ? a.x2 + (long long)s * a.ldx : nullptr;
     const float *zs = a.zi + (long long)s * a.nzi;
-    const int P0 = D * n0 - OFF;
+    const int P0 = D * n0 - OFF;  // block position of tile index 0: a multiple of 4, like n, so a quad is wholly inside the block or wholly outside
     constexpr bool MIX = KIND == SRC_MIX_LATE || KIND == SRC_MIX_HALF;
     const float *xt = xs + (long long)b * a.n + P0;
     const float *x2t = MIX ? x2s + (long long)b * a.n + P0 : xt;
-    if ((a.n & 3) == 0 && (((uintptr_t)xt | (uintptr_t)x2t) & 15) == 0) {
-        // P0 and n are multiples of 4, so a quad lies wholly inside block b or wholly outside it.  Inside: 128-bit
-        // traffic, no per-sample case analysis (PLAIN has nothing to form: asynchronous 16-byte copies straight into
-        // the padded tile, LDGSTS, no register staging).  Outside (the 168 history samples of a block's first tile,
-        // padding past the end): sample by sample.  The loop is unrolled so that all loads of a thread are in flight
-        // before its first store.
-        constexpr int ITERS = (G::QUADS + NT - 1) / NT;
-        const unsigned sbase = (unsigned)__cvta_generic_to_shared(sm);
+    const bool vec_ok = (a.n & 3) == 0 && (((uintptr_t)xt | (uintptr_t)x2t) & 15) == 0;
+    {
+        // entries 4j..4j+3 pair tile samples 4j.. with tile samples HALF+4j..: two 128-bit loads (per input signal), two
+        // 128-bit stores.  Unrolled, so that all loads of a thread are in flight before its first store.
+        constexpr int ITERS = (G::NPQ + NT - 1) / NT;
 #pragma unroll
         for (int it = 0; it < ITERS; ++it) {
             const int j = threadIdx.x + it * NT;
-            if (j >= G::QUADS) break;
-            const int p = P0 + 4 * j;
-            float *dst = sm + G::phys(4 * j);
-            if (p >= 0 && p + 4 <= a.n) {
-                if (KIND == SRC_PLAIN) {
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + 4u * (unsigned)G::phys(4 * j)), "l"(xt + 4 * j) : "memory");
-                } else {
-                    const float4 v = __ldg(reinterpret_cast<const float4 *>(xt) + j);
-                    float4 w = v;
-                    if (MIX) w = __ldg(reinterpret_cast<const float4 *>(x2t) + j);
-                    *reinterpret_cast<float4 *>(dst) = make_float4(form<KIND>(v.x, w.x, true), form<KIND>(v.y, w.y, true), form<KIND>(v.z, w.z, true), form<KIND>(v.w, w.w, true));
-                }
-            } else {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) dst[e] = source<KIND>(a, xs, x2s, zs, b, p + e);
-            }
+            if (j >= G::NPQ) break;
+            const float4 lo = stage_quad<KIND>(a, xs, x2s, zs, xt, x2t, b, P0, 4 * j, vec_ok);
+            const float4 hi = stage_quad<KIND>(a, xs, x2s, zs, xt, x2t, b, P0, 4 * j + G::HALF, vec_ok);
+            float4 *dst = reinterpret_cast<float4 *>(sm + G::physf(4 * j));
+            dst[0] = make_float4(lo.x, hi.x, lo.y, hi.y);
+            dst[1] = make_float4(lo.z, hi.z, lo.w, hi.w);
         }
-        if (KIND == SRC_PLAIN) {
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
-    } else {
-        for (int i = threadIdx.x; i < 4 * G::QUADS; i += NT) sm[G::phys(i)] = source<KIND>(a, xs, x2s, zs, b, P0 + i);
     }
     __syncthreads();
 
-#pragma unroll 1
-    for (int h = 0; h < PASSES; ++h) {
-        // row = threadIdx.x + h*NT: its window starts at logical index ROW*row = word PITCH*row; c = p + OFF is the index
-        // inside the window of the sample p positions after the row's first output's newest one, and output r uses it
-        // with tap k = D*r - p
-        const int row = threadIdx.x + h * NT;
-        const float *w = sm + G::PITCH * row;
-        float acc[RO];
+    // row t's window starts at entry ROW*t = float PITCHF*t; c = p + OFF is the index inside the window of the sample p
+    // positions after the row's first output's newest one, and output r uses it with tap k = D*r - p
+    const float *w = sm + G::PITCHF * threadIdx.x;
+    float2 acc[RO];  // .x: row t, .y: row t + NT
 #pragma unroll
-        for (int r = 0; r < RO; ++r) acc[r] = 0.0f;
+    for (int r = 0; r < RO; ++r) acc[r] = make_float2(0.0f, 0.0f);
 #pragma unroll
-        for (int q = G::QHI; q >= G::QLO; --q) {
-            const float4 v = *reinterpret_cast<const float4 *>(w + G::phys(4 * q));
-            const float xv[4] = {v.x, v.y, v.z, v.w};
+    for (int pq = G::PQHI; pq >= G::PQLO; --pq) {
+        const float4 v = *reinterpret_cast<const float4 *>(w + G::physf(2 * pq));
 #pragma unroll
-            for (int e = 3; e >= 0; --e) {  // newest sample first
-                const int p_ = 4 * q + e - OFF;
+        for (int e = 1; e >= 0; --e) {  // newest sample first
+            const float2 x2 = e ? make_float2(v.z, v.w) : make_float2(v.x, v.y);
+            const int p_ = 2 * pq + e - OFF;
 #pragma unroll
-                for (int r = 0; r < RO; ++r) {
-                    const int k = D * r - p_;
-                    if (k >= 0 && k < kTaps) acc[r] = mac<EXACT>(acc[r], xv[e], taps.h[k]);
-                }
+            for (int r = 0; r < RO; ++r) {
+                const int k = D * r - p_;
+                if (k >= 0 && k < kTaps) acc[r] = mac2<EXACT>(acc[r], x2, taps.h[k], ex);
             }
         }
-        const int o = n0 + RO * row;
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int o = n0 + RO * (threadIdx.x + h * NT);
         float *ys = a.y + (long long)s * a.ldy + (long long)b * a.ny + o;
+        float out[RO];
+#pragma unroll
+        for (int r = 0; r < RO; ++r) out[r] = h ? acc[r].y : acc[r].x;
         if (o + RO <= a.ny && ((reinterpret_cast<uintptr_t>(ys) & 15) == 0)) {
 #pragma unroll
-            for (int r = 0; r < RO; r += 4) reinterpret_cast<float4 *>(ys)[r / 4] = make_float4(acc[r], acc[r + 1], acc[r + 2], acc[r + 3]);
+            for (int r = 0; r < RO; r += 4) reinterpret_cast<float4 *>(ys)[r / 4] = make_float4(out[r], out[r + 1], out[r + 2], out[r + 3]);
         } else {
 #pragma unroll
             for (int r = 0; r < RO; ++r)
-                if (o + r < a.ny) ys[r] = acc[r];
+                if (o + r < a.ny) ys[r] = out[r];
         }
     }
 }
@@ -370,7 +392,7 @@ struct RowTaps {
 };
 
 template <bool EXACT>
-__global__ void __launch_bounds__(64, 8) frontend_stream_kernel(const IqDev a, const __grid_constant__ RowTaps taps, int L, int segs, long long total) {
+__global__ void __launch_bounds__(64, 8) frontend_stream_kernel(const IqDev a, const __grid_constant__ RowTaps taps, int L, int segs, long long total, const Exact2 ex) {
     const long long gid = blockIdx.x * 64LL + threadIdx.x;
     if (gid >= total) return;
     const int g = (int)(gid % segs);
@@ -382,9 +404,9 @@ __global__ void __launch_bounds__(64, 8) frontend_stream_kernel(const IqDev a, c
     const bool aligned = ((uintptr_t)row & 15) == 0;
     const long long ob = (long long)s * a.ldy + (long long)b * a.ny;
 
-    float bi[SLOTS], bq[SLOTS];
+    float2 bb[SLOTS];  // (I, Q) accumulators of the open outputs: one packed lane pair each
 #pragma unroll
-    for (int i = 0; i < SLOTS; ++i) bi[i] = bq[i] = 0.0f;
+    for (int i = 0; i < SLOTS; ++i) bb[i] = make_float2(0.0f, 0.0f);
     float2 ycur = make_float2(0.0f, 0.0f);                  // the output completed just before (index n+1 when n completes)
 
     // group of four rows with top row rt (rt = 3 mod 4): samples 10*rt-38 .. 10*rt+1, bytes 20*rt-76 .. 20*rt+4
@@ -438,17 +460,16 @@ __global__ void __launch_bounds__(64, 8) frontend_stream_kernel(const IqDev a, c
                     const int k = 10 * sl - 1 + j;
                     if (k >= 0 && k < kTaps) {
                         const int i = sl + 1 - rr;
-                        bi[i] = mac<EXACT>(bi[i], smp[j].x, taps.t[j][sl]);
-                        bq[i] = mac<EXACT>(bq[i], smp[j].y, taps.t[j][sl]);
+                        bb[i] = mac2<EXACT>(bb[i], smp[j], taps.t[j][sl], ex);
                     }
                 }
             }
-            if (rr == 0) yh = make_float2(bi[16], bq[16]);  // output rho+15
-            else yl = make_float2(bi[15], bq[15]);          // output rho+14
+            if (rr == 0) yh = bb[16];  // output rho+15
+            else yl = bb[15];          // output rho+14
         }
 #pragma unroll
-        for (int i = SLOTS - 1; i >= 2; --i) { bi[i] = bi[i - 2]; bq[i] = bq[i - 2]; }
-        bi[0] = bq[0] = bi[1] = bq[1] = 0.0f;
+        for (int i = SLOTS - 1; i >= 2; --i) bb[i] = bb[i - 2];
+        bb[0] = bb[1] = make_float2(0.0f, 0.0f);
 
         // outputs rho+15 (yh) and rho+14 (yl) are complete; demod[n] pairs output n with output n-1.  An output is
         // genuine only if its first row lay inside the walk, i.e. its index is below a0+L.
@@ -499,21 +520,31 @@ Taps make_taps(const float *h) {
     return t;
 }
 
-constexpr int CT_RRC = 152;  // 8 * 152 = 1216 outputs per tile: the 3648-sample RDS blocks are exactly three tiles
+// threads per CTA: a tile is 2 rows x RO outputs x NT threads = 1024 outputs (exact: RO 4, NT 128; fma: RO 8, NT 64);
+// for the 3648-sample RDS blocks 912-output tiles (NT 114 / 57) divide the block exactly
+template <bool EXACT> struct TileThreads { static constexpr int STD = EXACT ? 128 : 64, RDS = EXACT ? 114 : 57; };
 
-template <int D, int KIND>
-int launch_fir_dk(const FirJob &j, const FirDev &d, dim3 grid, fmrx_stream_t st) {
+template <int D, int KIND, bool EXACT>
+int launch_fir_dke(const FirJob &j, const FirDev &d, fmrx_stream_t st) {
     const Taps t = make_taps(j.h);
-    if (D == 1 && KIND == SRC_PLAIN && d.ny % (R * CT_RRC) == 0 && d.ny % (R * CT) != 0) {
+    const Exact2 ex{-0.0f, 1.0f};
+    constexpr int RO = EXACT ? 4 : 8;
+    using TT = TileThreads<EXACT>;
+    if (D == 1 && KIND == SRC_PLAIN && d.ny % (2 * RO * TT::RDS) == 0 && d.ny % (2 * RO * TT::STD) != 0) {
         constexpr int DD = D == 1 && KIND == SRC_PLAIN ? D : 1, KK = D == 1 && KIND == SRC_PLAIN ? KIND : SRC_PLAIN;  // instantiated once only
-        grid.x = d.ny / (R * CT_RRC);
-        if (j.exact) fir151_kernel<DD, KK, true, CT_RRC><<<grid, CT_RRC, 0, st>>>(d, t);
-        else fir151_kernel<DD, KK, false, CT_RRC><<<grid, CT_RRC, 0, st>>>(d, t);
+        dim3 grid(d.ny / (2 * RO * TT::RDS), j.n_blocks, j.n_streams);
+        fir151_kernel<DD, KK, EXACT, TT::RDS><<<grid, TT::RDS, 0, st>>>(d, t, ex);
         return (int)cudaGetLastError();
     }
-    if (j.exact) fir151_kernel<D, KIND, true, CT><<<grid, CT, 0, st>>>(d, t);
-    else fir151_kernel<D, KIND, false, CT><<<grid, CT, 0, st>>>(d, t);
+    constexpr int TO = 2 * RO * TT::STD;
+    dim3 grid((d.ny + TO - 1) / TO, j.n_blocks, j.n_streams);
+    fir151_kernel<D, KIND, EXACT, TT::STD><<<grid, TT::STD, 0, st>>>(d, t, ex);
     return (int)cudaGetLastError();
+}
+
+template <int D, int KIND>
+int launch_fir_dk(const FirJob &j, const FirDev &d, dim3, fmrx_stream_t st) {
+    return j.exact ? launch_fir_dke<D, KIND, true>(j, d, st) : launch_fir_dke<D, KIND, false>(j, d, st);
 }
 
 template <int KIND>
@@ -589,7 +620,7 @@ int launch_frontend(const FrontendJob &j, fmrx_stream_t st) {
         }
     const int L = stream_run(d.ny), segs = (d.ny + L - 1) / L;
     const long long total = (long long)segs * j.n_blocks * j.n_streams;
-    frontend_stream_kernel<true><<<(unsigned)((total + 63) / 64), 64, 0, st>>>(d, t, L, segs, total);
+    frontend_stream_kernel<true><<<(unsigned)((total + 63) / 64), 64, 0, st>>>(d, t, L, segs, total, Exact2{-0.0f, 1.0f});
     cudaError_t e = cudaGetLastError();
     if (e) return (int)e;
     iq_state_kernel<true><<<j.n_streams, 160, 0, st>>>(d);
