@@ -141,6 +141,12 @@ int fmrx_batch_reset(fmrx_batch *);                 /* back to block 0 with the 
 /* host -> host.  iq:[S][n_blocks][307200] bytes.  Copies are staged through pinned rings and overlapped with the
  * kernels on separate CUDA streams (the replacement for the reference's producer/consumer threads). */
 int fmrx_batch_process(fmrx_batch *, const uint8_t *iq, int n_blocks, const fmrx_outputs *out);
+/* host -> host, asynchronous: enqueues the H2D copy of the whole step, the three-phase pipeline and the D2H copy of
+ * the results, and returns a ticket; consecutive submits overlap (step k+1's ingest runs under step k's kernels, which
+ * is what replaces the reference's rf_thread -> queue -> consumer threads, src/fm_radio.cpp:86-138).  `iq` and the
+ * output buffers must be page-locked (fmrx_pinned_alloc) and stay untouched until fmrx_batch_wait(ticket) returns. */
+int fmrx_batch_submit(fmrx_batch *, const uint8_t *iq, int n_blocks, const fmrx_outputs *out, long long *ticket);
+int fmrx_batch_wait(fmrx_batch *, long long ticket);
 /* device -> device, asynchronous on the handle's stream; fmrx_batch_sync() waits. */
 int fmrx_batch_process_device(fmrx_batch *, const uint8_t *iq_device, int n_blocks, const fmrx_outputs *out_device);
 int fmrx_batch_sync(fmrx_batch *);

@@ -265,6 +265,7 @@ constexpr int NRDS = FMRX_RDS_PER_BLOCK;
 constexpr double kPi = 3.14159265358979323846;
 constexpr int kMaxChunks = 8;
 constexpr int kSets = 3;       // rotating buffer sets of the device-resident pipeline
+constexpr int kTickets = 8;    // completion events kept by the asynchronous host path
 
 }  // namespace
 
@@ -308,6 +309,12 @@ struct fmrx_batch {
     cudaEvent_t ev_a[kSets]{}, ev_p[kSets]{}, ev_c[kSets]{};
     bool ev_c_valid[kSets] = {};
     bool was_serial = false;
+    // asynchronous host path (fmrx_batch_submit / fmrx_batch_wait): two device staging buffers for the IQ bytes, so that
+    // the H2D of step k+1 runs under the kernels of step k; tickets are events on the copy-out stream
+    uint8_t *d_iq2 = nullptr;
+    cudaEvent_t e_h2d[2]{}, e_iqfree[2]{}, e_d2h = nullptr, ev_ticket[kTickets]{};
+    bool iqfree_valid[2] = {false, false}, d2h_valid = false;
+    long long submits = 0;
     long long calls = 0;
     int last_set = 0;
     size_t set_if = 0, set_au = 0;  // elements per set of an IF-rate / audio-rate signal
@@ -328,6 +335,10 @@ struct fmrx_batch {
         for (auto e : prof_pool) cudaEventDestroy(e);
         for (int i = 0; i < kMaxChunks; ++i) { if (e_in[i]) cudaEventDestroy(e_in[i]); if (e_done[i]) cudaEventDestroy(e_done[i]); if (e_out[i]) cudaEventDestroy(e_out[i]); }
         for (int i = 0; i < kSets; ++i) { if (ev_a[i]) cudaEventDestroy(ev_a[i]); if (ev_p[i]) cudaEventDestroy(ev_p[i]); if (ev_c[i]) cudaEventDestroy(ev_c[i]); }
+        for (auto e : e_h2d) if (e) cudaEventDestroy(e);
+        for (auto e : e_iqfree) if (e) cudaEventDestroy(e);
+        for (auto e : ev_ticket) if (e) cudaEventDestroy(e);
+        if (e_d2h) cudaEventDestroy(e_d2h);
         for (auto st : {s_a, s_p, s_c, s_ser}) if (st) cudaStreamDestroy(st);
         fmrx::partition_destroy(part);
         if (s_in) cudaStreamDestroy(s_in);
@@ -356,6 +367,7 @@ int init_state(fmrx_batch *b) {
     b->block_id = 0;
     b->calls = 0;
     for (bool &v : b->ev_c_valid) v = false;
+    b->iqfree_valid[0] = b->iqfree_valid[1] = b->d2h_valid = false;
     return FMRX_OK;
 }
 
@@ -620,6 +632,9 @@ int fmrx_batch_create(const fmrx_config *cfg, fmrx_batch **out) {
         CU(cudaEventCreateWithFlags(&b->e_in[i], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&b->e_done[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&b->e_out[i], cudaEventDisableTiming));
     }
+    for (int i = 0; i < 2; ++i) { CU(cudaEventCreateWithFlags(&b->e_h2d[i], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&b->e_iqfree[i], cudaEventDisableTiming)); }
+    CU(cudaEventCreateWithFlags(&b->e_d2h, cudaEventDisableTiming));
+    for (auto &e : b->ev_ticket) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     if (int e = init_state(b)) return e;
     guard.p = nullptr;
     *out = b;
@@ -706,6 +721,55 @@ int fmrx_batch_process(fmrx_batch *b, const uint8_t *iq, int n_blocks, const fmr
     CU(cudaStreamSynchronize(b->s_out)); CU(cudaStreamSynchronize(b->s_cmp[0])); CU(cudaStreamSynchronize(b->s_cmp[1]));
     b->block_id += n_blocks;
     b->last_blocks = n_blocks;
+    return FMRX_OK;
+}
+
+int fmrx_batch_submit(fmrx_batch *b, const uint8_t *iq, int n_blocks, const fmrx_outputs *out, long long *ticket) {
+    if (!b || !iq || !ticket) return fail(FMRX_ERR_ARG, "fmrx_batch_submit: null pointer");
+    if (n_blocks <= 0 || n_blocks > b->NB) return fail(FMRX_ERR_ARG, "n_blocks %d outside 1..%d", n_blocks, b->NB);
+    if (b->profiling && !b->profile_pipelined) return fail(FMRX_ERR_STATE, "fmrx_batch_submit is not available while serialised stage profiling is on");
+    CU(cudaSetDevice(b->cfg.device));
+    fmrx_outputs none{};
+    const fmrx_outputs &o = out ? *out : none;
+    if (b->was_serial) { if (int e = fmrx_batch_sync(b)) return e; b->was_serial = false; }
+    if (!b->d_iq2) CU(b->dalloc(b->d_iq2, (size_t)b->S * b->NB * FMRX_BLOCK_BYTES));
+    const int slot = (int)(b->submits & 1);
+    uint8_t *dst = slot ? b->d_iq2 : b->d_iq;
+    const long long row = (long long)n_blocks * FMRX_BLOCK_BYTES;
+    // ingest: this slot's previous contents must have been consumed by the front end two submits ago
+    if (b->iqfree_valid[slot]) CU(cudaStreamWaitEvent(b->s_in, b->e_iqfree[slot], 0));
+    CU(cudaMemcpyAsync(dst, iq, (size_t)b->S * row, cudaMemcpyHostToDevice, b->s_in));
+    CU(cudaEventRecord(b->e_h2d[slot], b->s_in));
+    CU(cudaStreamWaitEvent(b->s_a, b->e_h2d[slot], 0));
+    // the three-phase pipeline of the device-resident path
+    const int set = (int)(b->calls % kSets);
+    if (b->ev_c_valid[set]) CU(cudaStreamWaitEvent(b->s_a, b->ev_c[set], 0));
+    if (b->d2h_valid) CU(cudaStreamWaitEvent(b->s_c, b->e_d2h, 0));  // phase C overwrites the result buffers the previous copy-out reads
+    if (int e = enqueue_chain(b, dst, row, 0, b->S, n_blocks, none, set, b->s_a, b->s_p, b->s_c)) return e;
+    CU(cudaEventRecord(b->e_iqfree[slot], b->s_a));
+    b->iqfree_valid[slot] = true;
+    CU(cudaEventRecord(b->ev_c[set], b->s_c));
+    b->ev_c_valid[set] = true;
+    // egress
+    CU(cudaStreamWaitEvent(b->s_out, b->ev_c[set], 0));
+    if (int e = copy_outputs(b, 0, b->S, n_blocks, o, cudaMemcpyDeviceToHost, b->s_out)) return e;
+    CU(cudaEventRecord(b->e_d2h, b->s_out));
+    b->d2h_valid = true;
+    *ticket = b->submits;
+    CU(cudaEventRecord(b->ev_ticket[b->submits % kTickets], b->s_out));
+    b->submits += 1;
+    b->calls += 1;
+    b->block_id += n_blocks;
+    b->last_blocks = n_blocks;
+    return FMRX_OK;
+}
+
+int fmrx_batch_wait(fmrx_batch *b, long long ticket) {
+    if (!b) return fail(FMRX_ERR_ARG, "null handle");
+    if (ticket < 0 || ticket >= b->submits) return fail(FMRX_ERR_ARG, "ticket %lld was never issued (next is %lld)", ticket, b->submits);
+    CU(cudaSetDevice(b->cfg.device));
+    // the slot holds this ticket's event or, once recycled, that of a later submit on the same in-order stream
+    CU(cudaEventSynchronize(b->ev_ticket[ticket % kTickets]));
     return FMRX_OK;
 }
 

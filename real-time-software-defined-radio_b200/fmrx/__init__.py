@@ -99,6 +99,8 @@ SIGNATURES = {
     "fmrx_batch_get_state": (C.c_int, [C.c_void_p, C.c_void_p]),
     "fmrx_batch_set_state": (C.c_int, [C.c_void_p, C.c_void_p]),
     "fmrx_batch_partition": (C.c_int, [C.c_void_p, i32p, i32p]),
+    "fmrx_batch_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Outputs), C.POINTER(C.c_longlong)]),
+    "fmrx_batch_wait": (C.c_int, [C.c_void_p, C.c_longlong]),
     "fmrx_batch_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "fmrx_batch_stage_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "fmrx_batch_timeline": (C.c_int, [C.c_void_p, C.c_int, i32p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
@@ -402,6 +404,18 @@ class Batch:
         check(lib().fmrx_batch_process(self.h, C.c_void_p(ptr), n_blocks, C.byref(out)))
         self.block_id += n_blocks
         self.last_blocks = n_blocks
+
+    def submit(self, iq, n_blocks, out: "Outputs"):
+        """Asynchronous host path: enqueue one step (pinned buffers), return its ticket; wait(ticket) before reading `out`."""
+        ptr = iq if isinstance(iq, int) else iq.ctypes.data
+        t = C.c_longlong(-1)
+        check(lib().fmrx_batch_submit(self.h, C.c_void_p(ptr), n_blocks, C.byref(out), C.byref(t)))
+        self.block_id += n_blocks
+        self.last_blocks = n_blocks
+        return t.value
+
+    def wait(self, ticket):
+        check(lib().fmrx_batch_wait(self.h, ticket))
 
     @property
     def launches(self):

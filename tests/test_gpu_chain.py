@@ -170,3 +170,50 @@ def test_fma_numerics_within_tolerance_mono():
     audio, cap, *_ = ch.run(raw, taps=("audio_f",))
     assert rel_rms(res["audio_f"][0], np.stack(cap["audio_f"])) < TOL
     assert np.abs(res["audio"][0].ravel().astype(int) - audio.astype(int)).max() <= 1
+
+
+@pytest.mark.parametrize("pll_sms", ["0", "16"])
+def test_async_submit_pipeline_equals_oracle(monkeypatch, pll_sms):
+    """The asynchronous host path (submit / wait: H2D of step k+1 under the kernels of step k, three-phase pipeline with
+    rotating buffer sets, with and without the PLL's own SM partition) must give, step by step, what the oracle gives
+    for the same bytes: 5 steps of one block each, so every buffer set and both ingest slots are reused."""
+    import ctypes as C
+
+    import torch
+
+    monkeypatch.setenv("FMRX_PLL_SMS", pll_sms)
+    S, steps = 6, 5
+    raw = np.stack([synth.synth_station(s, steps, 0) for s in range(S)])  # [S][steps*307200]
+    na = 3072
+    h_iq = [torch.empty((S, 307200), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    h_audio = [torch.zeros((S, 1, 2 * na), dtype=torch.int16).pin_memory() for _ in range(2)]
+    h_bits = [torch.zeros((S, 1, fmrx.MAX_BITS), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    h_nbits = [torch.zeros((S, 1), dtype=torch.int32).pin_memory() for _ in range(2)]
+
+    def ptr(t, typ):
+        return C.cast(C.c_void_p(t.data_ptr()), typ)
+
+    outs = [fmrx.Outputs(ptr(h_audio[i], fmrx.i16p), None, ptr(h_bits[i], fmrx.u8p), ptr(h_nbits[i], fmrx.i32p), None, None) for i in range(2)]
+    got_audio, got_bits = [], []
+
+    def collect(i):
+        got_audio.append(h_audio[i].numpy().copy())
+        got_bits.append([h_bits[i].numpy()[s, 0, :int(h_nbits[i][s, 0])].copy() for s in range(S)])
+
+    with fmrx.Batch(S, mode=0, profile=1, max_blocks=1) as rx:
+        assert (rx.partition()[0] > 0) == (pll_sms != "0")
+        tickets = []
+        for k in range(steps):
+            h_iq[k % 2].numpy()[:] = raw[:, k * 307200:(k + 1) * 307200]
+            tickets.append(rx.submit(h_iq[k % 2].data_ptr(), 1, outs[k % 2]))
+            if k >= 1:  # consume step k-1 while step k is in flight
+                rx.wait(tickets[k - 1])
+                collect((k - 1) % 2)
+        rx.wait(tickets[-1])
+        collect((steps - 1) % 2)
+        with pytest.raises(fmrx.FmrxError):
+            rx.wait(tickets[-1] + 1)
+    for s in range(S):
+        audio, _, bits, _, _ = Chain(0, 1).run(raw[s])
+        assert_bits(np.concatenate([got_audio[k][s].ravel() for k in range(steps)]), audio, f"station {s} audio")
+        assert np.array_equal(np.concatenate([got_bits[k][s] for k in range(steps)]), np.concatenate(bits)), f"station {s} bits"
