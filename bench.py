@@ -263,7 +263,7 @@ def run_fmrx_arm(args, rank, world, local_rank):
     value = units / (ms_dev * 1e-3) / 1e6
 
     pll_sms, filter_sms = rx.partition()
-    if args.device_only:
+    if args.device_only or args.skip_e2e:
         if rank == 0:
             print(json.dumps({"device_only": True, "value": round(value, 1), "unit": "Msps", "ms_per_step": round(ms_dev / args.steps, 4), "pll_sms": pll_sms,
                               "filter_sms": filter_sms, "stages_ms": {k: round(v[0] / args.steps, 4) for k, v in stage.items() if v[1]}}), flush=True)
@@ -378,6 +378,9 @@ def main():
     ap.add_argument("--blocks", type=int, default=1, help="blocks per station per step")
     ap.add_argument("--cpu-blocks", type=int, default=48, help="blocks per process of the CPU baseline sample")
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true", help="for the ncu launch list: stop after the device-resident and per-stage passes (ncu's "
+                    "measurement library fails with LaunchFailed on the first kernel that waits on an event recorded in another context's stream, "
+                    "which is how the asynchronous host path chains its H2D copy to the partitioned filter stream)")
     ap.add_argument("--device-only", action="store_true", help="tuning aid: device-resident number and stage times only (not a bench line)")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)

@@ -12,9 +12,9 @@ python bench.py > $OUT/${TAG}_bench.log 2> $OUT/${TAG}_bench.err
 echo "bench rc=$?"
 tail -c 600 $OUT/${TAG}_bench.log
 # launch list of the bench command (cold-cache, serialised: compare shares)
-python bench.py --steps 2 --warmup 1 --no-check > $OUT/${TAG}_plain.log 2>&1 &&
+python bench.py --steps 2 --warmup 1 --no-check --skip-e2e > $OUT/${TAG}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:fmrx --csv \
-    --log-file $OUT/${TAG}_launches.csv python bench.py --steps 2 --warmup 1 --no-check > $OUT/${TAG}_ncu1.log 2>&1
+    --log-file $OUT/${TAG}_launches.csv python bench.py --steps 2 --warmup 1 --no-check --skip-e2e > $OUT/${TAG}_ncu1.log 2>&1
 echo "launch list rc=$?"
 # full capture of one chain step
 python tools/prof_chain.py 4096 1 > $OUT/${TAG}_plain2.log 2>&1 &&

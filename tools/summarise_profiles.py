@@ -59,7 +59,7 @@ def launches(tag):
     src = os.path.join(G, f"{tag}_launches.csv")
     if not os.path.exists(src):
         return
-    rows = [r for r in csv.reader(open(src)) if len(r) > 10 and r[0].isdigit()]
+    rows = [r for r in csv.reader(open(src)) if len(r) > 10 and r[0].isdigit() and r[-1].replace(".", "", 1).isdigit()]
     agg = OrderedDict()
     for r in rows:
         k = short(r[4])
