@@ -402,7 +402,6 @@ int enqueue_chain(fmrx_batch *b, const uint8_t *iq, long long ld_iq, int s0, int
     FrontendJob f{};
     f.raw = iq + (long long)s0 * ld_iq; f.demod = IF(b->demod); f.zii = b->zi_i + (long long)s0 * kHist; f.ziq = b->zi_q + (long long)s0 * kHist; f.h = b->h_rf;
     f.ld_raw = ld_iq; f.ld_out = ldif; f.n = NIQ; f.n_blocks = nblk; f.n_streams = ns;
-    if (b->part && stA == b->s_a) { int small = 0; fmrx::partition_sizes(b->part, &small, &f.sms); }
     { STAGE(FMRX_STAGE_FRONTEND); LAUNCH(launch_frontend(f, st)); }
 
     auto fir = [&](const float *x, const float *x2, float *y, float *zi, int nzi, const float *h, long long ldx, long long ldy, int n, int decim, int kind, int exact, int blocks) {

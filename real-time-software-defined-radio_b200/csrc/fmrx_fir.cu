@@ -593,35 +593,13 @@ static int launch_iq_d(const IqDev &d, const float *h, int exact, int n_streams,
     return (int)cudaGetLastError();
 }
 
-// Run length of the streaming front end.  Every thread does the same amount of work (L + 16 rows), so the grid runs in
-// whole waves of (SMs x resident CTAs x 64) threads and a partly filled last wave costs as much as a full one: with
-// L = 240, 4096 stations are 3.46 waves on 148 SMs and the device idles through half of the fourth.  Pick the L (a
-// multiple of 4) that minimises waves x (L + 16): 208 in that case, exactly 4.00 waves.
-static int stream_run(int ny, long long station_blocks, int sms) {
-    static int per_sm = 0, dev_sms = 0;
-    if (!per_sm) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frontend_stream_kernel<true>, 64, 0) != cudaSuccess || per_sm <= 0) per_sm = 8;
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || dev_sms <= 0) dev_sms = 148;
-        cudaGetLastError();
-    }
-    const long long slots = (long long)(sms > 0 ? sms : dev_sms) * per_sm * 64;
-    int best_L = 240;
-    long long best_cost = -1;
-    for (int W = 1; W <= 256; ++W) {
-        const long long segs_max = W * slots / station_blocks;
-        if (segs_max < 1) continue;
-        int L = (int)((ny + segs_max - 1) / segs_max);
-        L = (L + 3) / 4 * 4;
-        if (L < 64) L = 64;
-        const long long segs = (ny + L - 1) / L;
-        const long long waves = (station_blocks * segs + slots - 1) / slots;
-        const long long cost = waves * (L + 16);
-        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_L = L; }
-        if (L == 64) break;
-    }
-    return best_L;
+// run length of the streaming front end: a multiple of 4; the largest one <= 240 that divides ny when there is one.
+// (Sizing L for whole waves of resident CTAs was tried and buys nothing: the kernel is FP32-pipe bound, so a partly
+// filled last wave simply runs its CTAs faster.)
+static int stream_run(int ny) {
+    for (int L = 240; L >= 64; L -= 4)
+        if (ny % L == 0) return L;
+    return 240;
 }
 
 int launch_fir_iq(const FirIqJob &j, fmrx_stream_t st) {
@@ -642,7 +620,7 @@ int launch_frontend(const FrontendJob &j, fmrx_stream_t st) {
             const int k = 10 * sl - 1 + jj;
             t.t[jj][sl] = (k >= 0 && k < kTaps) ? j.h[k] : 0.0f;
         }
-    const int L = stream_run(d.ny, (long long)j.n_blocks * j.n_streams, j.sms), segs = (d.ny + L - 1) / L;
+    const int L = stream_run(d.ny), segs = (d.ny + L - 1) / L;
     const long long total = (long long)segs * j.n_blocks * j.n_streams;
     frontend_stream_kernel<true><<<(unsigned)((total + 63) / 64), 64, 0, st>>>(d, t, L, segs, total, Exact2{-0.0f, 1.0f});
     cudaError_t e = cudaGetLastError();

@@ -54,7 +54,6 @@ struct FrontendJob {  // rf_thread fused: u8 IQ -> FIR(151) /10 on I and Q -> di
     const float *h;      // HOST taps
     long long ld_raw, ld_out;
     int n, n_blocks, n_streams;  // n complex samples per block; decim is fixed at 10
-    int sms;                     // SMs the launch stream owns (green-context partition), 0 = the whole device: sizes the run length
 };
 int launch_frontend(const FrontendJob &j, fmrx_stream_t st);
 

@@ -76,6 +76,10 @@ __global__ void __launch_bounds__(32) pll_kernel(PllSide A, PllSide B, long long
                 const float4 v = v0;
                 v0 = v1;
                 if (g + 2 < groups) v1 = __ldg(x4 + g + 2);
+                // ... and its 128-byte line is pulled into L2 sixteen groups before that: with 8192 lanes each on a row of
+                // its own, every line is a DRAM page (and mostly a TLB) miss, and the register prefetch alone left 15% of
+                // the kernel's samples waiting on it (ncu source page, profiles/r1w)
+                if ((g & 7) == 0 && g + 16 < groups) asm volatile("prefetch.global.L2 [%0];" ::"l"(x4 + g + 16));
                 // four branch-free steps = one basic block; if any of them left the fast path's domain (first group
                 // after loading the state, zero / non-finite input, the +-pi seam: ~1e-5 of the groups) the four
                 // carried floats are restored and the group is redone with libm
