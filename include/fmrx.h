@@ -195,6 +195,42 @@ int fmrx_batch_set_state(fmrx_batch *, const void *blob);
 int fmrx_pinned_alloc(void **ptr, size_t bytes);
 int fmrx_pinned_free(void *ptr);
 
+/* ---- RDS data-link and application layer ----------------------------------------------------
+ * The reference stops at printing syndrome matches (frame_thread, src/fm_radio.cpp:625-718).  This layer takes the
+ * differentially decoded bits the chain emits (fmrx_outputs.rds_bits) and does what IEC 62106 / the course spec names
+ * as the purpose of the RDS path: block synchronisation on the offset words A, B, C, C', D at 26-bit spacing (acquired on
+ * two error-free blocks 26 bits apart in cyclic order, lost after 12 consecutive blocks that were not error-free),
+ * checkword verification with burst-error correction (bursts <= 5 bits, shortened cyclic code (26,16), g(x) = 0x5B9;
+ * attempted only while fewer than 3 consecutive blocks failed the clean check), group assembly, and decoding of PI, PTY, TP, the programme-service name (groups 0A/0B) and RadioText (2A/2B).
+ * Host code (1187.5 bit/s per station is not GPU work); one opaque handle serves n_streams stations. */
+typedef struct fmrx_rds_app fmrx_rds_app;
+typedef struct {
+    uint16_t blk[4];    /* information words of blocks A, B, C (or C'), D */
+    uint8_t type;       /* group type 0..15 */
+    uint8_t version_b;  /* 0 = version A, 1 = version B (block 3 carried offset C') */
+    uint8_t corrected;  /* number of blocks of this group that needed error correction */
+    uint8_t reserved;
+    uint32_t bit_index; /* index, in the stream of fed bits, of the first bit of block A */
+} fmrx_rds_group;
+typedef struct {
+    int32_t synced;           /* 1 while block synchronisation is held */
+    int32_t pi;               /* programme identification, -1 until a block A was accepted */
+    int32_t pty, tp;          /* programme type 0..31, traffic-programme flag; -1 until known */
+    char ps[9];               /* programme-service name, 8 chars + NUL; '_' where no segment arrived yet */
+    char rt[65];              /* RadioText, up to 64 chars + NUL, cut at the 0x0D terminator; '_' where unknown */
+    uint8_t ps_complete, rt_ab_flag;
+    uint32_t groups, blocks_ok, blocks_corrected, blocks_bad, sync_losses;
+    uint64_t bits_fed;
+} fmrx_rds_station;
+int fmrx_rds_app_create(int n_streams, fmrx_rds_app **out);
+void fmrx_rds_app_destroy(fmrx_rds_app *);
+int fmrx_rds_app_reset(fmrx_rds_app *);
+/* bits:[S][n_blocks][FMRX_MAX_BITS] and n_bits:[S][n_blocks] exactly as a process call returns them (host memory);
+ * groups:[S][cap] receives the groups completed by this call (may be NULL), n_groups:[S] their count (may be NULL;
+ * groups beyond `cap` are still decoded into the station record, only not returned) */
+int fmrx_rds_app_feed(fmrx_rds_app *, const uint8_t *bits, const int32_t *n_bits, int n_blocks, fmrx_rds_group *groups, int cap, int32_t *n_groups);
+int fmrx_rds_app_station(const fmrx_rds_app *, int stream, fmrx_rds_station *out);
+
 /* ---- measurement helpers (used by bench.py; not part of the receive path) ---------------------------------- */
 /* runs an FP32 issue-rate microbenchmark on `device` and returns the best-of-`reps` rate in T lane-ops/s:
  * kind 0 = FFMA, 1 = FMUL+FADD pairs, 2 = packed FFMA2, 3 = packed FMUL2+FADD2 */

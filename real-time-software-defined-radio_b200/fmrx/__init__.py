@@ -42,6 +42,16 @@ i16p = C.POINTER(C.c_int16)
 i32p = C.POINTER(C.c_int32)
 
 
+class RdsGroup(C.Structure):
+    _fields_ = [("blk", C.c_uint16 * 4), ("type", C.c_uint8), ("version_b", C.c_uint8), ("corrected", C.c_uint8), ("reserved", C.c_uint8), ("bit_index", C.c_uint32)]
+
+
+class RdsStation(C.Structure):
+    _fields_ = [("synced", C.c_int32), ("pi", C.c_int32), ("pty", C.c_int32), ("tp", C.c_int32), ("ps", C.c_char * 9), ("rt", C.c_char * 65),
+                ("ps_complete", C.c_uint8), ("rt_ab_flag", C.c_uint8), ("groups", C.c_uint32), ("blocks_ok", C.c_uint32), ("blocks_corrected", C.c_uint32),
+                ("blocks_bad", C.c_uint32), ("sync_losses", C.c_uint32), ("bits_fed", C.c_uint64)]
+
+
 class FmrxError(RuntimeError):
     pass
 
@@ -104,6 +114,11 @@ SIGNATURES = {
     "fmrx_batch_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "fmrx_batch_stage_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "fmrx_batch_timeline": (C.c_int, [C.c_void_p, C.c_int, i32p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "fmrx_rds_app_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "fmrx_rds_app_destroy": (None, [C.c_void_p]),
+    "fmrx_rds_app_reset": (C.c_int, [C.c_void_p]),
+    "fmrx_rds_app_feed": (C.c_int, [C.c_void_p, u8p, i32p, C.c_int, C.POINTER(RdsGroup), C.c_int, i32p]),
+    "fmrx_rds_app_station": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(RdsStation)]),
     "fmrx_pinned_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "fmrx_pinned_free": (C.c_int, [C.c_void_p]),
     "fmrx_measure_fp32_peak": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
@@ -283,6 +298,57 @@ def measure_fp32_peak(kind, device=0, reps=5):
 # ---------------------------------------------------------------------------------------------------------------------
 # the batched chain
 # ---------------------------------------------------------------------------------------------------------------------
+class RdsApp:
+    """RDS data-link / application layer over the bits a Batch returns (host code, fmrx_rds_app_*)."""
+
+    def __init__(self, n_streams=1):
+        self.S, self.h = n_streams, C.c_void_p()
+        check(lib().fmrx_rds_app_create(n_streams, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib().fmrx_rds_app_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        check(lib().fmrx_rds_app_reset(self.h))
+
+    def feed(self, bits, n_bits, cap=64):
+        """bits [S][B][MAX_BITS] u8, n_bits [S][B] i32 (as in Batch.process results) -> list (per stream) of group dicts"""
+        bits = np.ascontiguousarray(bits, np.uint8).reshape(self.S, -1, MAX_BITS)
+        n_bits = np.ascontiguousarray(n_bits, np.int32).reshape(self.S, -1)
+        g = (RdsGroup * (self.S * cap))()
+        ng = np.zeros(self.S, np.int32)
+        check(lib().fmrx_rds_app_feed(self.h, bits.ctypes.data_as(u8p), n_bits.ctypes.data_as(i32p), bits.shape[1], g, cap, ng.ctypes.data_as(i32p)))
+        return [[dict(blk=list(g[s * cap + i].blk), type=g[s * cap + i].type, version_b=g[s * cap + i].version_b, corrected=g[s * cap + i].corrected,
+                      bit_index=g[s * cap + i].bit_index) for i in range(min(int(ng[s]), cap))] for s in range(self.S)]
+
+    def feed_stream(self, stream_bits, cap=4096):
+        """convenience for one station: a flat bit array, cut into MAX_BITS-sized pieces"""
+        assert self.S == 1
+        b = np.asarray(stream_bits, np.uint8).ravel()
+        nblk = max(1, -(-b.size // MAX_BITS))
+        pad = np.zeros(nblk * MAX_BITS, np.uint8)
+        pad[:b.size] = b
+        nb = np.full(nblk, MAX_BITS, np.int32)
+        if b.size % MAX_BITS or b.size == 0:
+            nb[-1] = b.size - (nblk - 1) * MAX_BITS
+        return self.feed(pad.reshape(1, nblk, MAX_BITS), nb.reshape(1, nblk), cap)[0]
+
+    def station(self, stream=0):
+        st = RdsStation()
+        check(lib().fmrx_rds_app_station(self.h, stream, C.byref(st)))
+        return dict(synced=bool(st.synced), pi=st.pi, pty=st.pty, tp=st.tp, ps=st.ps.decode("latin-1"), rt=st.rt.decode("latin-1"), ps_complete=bool(st.ps_complete),
+                    groups=st.groups, blocks_ok=st.blocks_ok, blocks_corrected=st.blocks_corrected, blocks_bad=st.blocks_bad, sync_losses=st.sync_losses,
+                    bits_fed=st.bits_fed)
+
+
 class Batch:
     """n_streams independent stations processed in lock step, max_blocks blocks per call."""
 

@@ -51,6 +51,45 @@ def rds_bits(n_bits: int, seed: int) -> np.ndarray:
     return out[:n_bits]
 
 
+def rds_block_bits(info16: int, offset: int) -> list:
+    word = ((info16 & 0xFFFF) << 10) | rds_checkword(info16 & 0xFFFF, offset)
+    return [(word >> (25 - i)) & 1 for i in range(26)]
+
+
+RDS_OFFSET_CPRIME = 0x350
+
+
+def rds_group_bits(pi: int, ps: str = "FMRX-GPU", rt: str = "", pty: int = 10, tp: int = 0, n_bits: int = 0, version_b: bool = False,
+                   rt_ab: int = 0) -> np.ndarray:
+    """Bit stream (MSB first, before differential encoding) of a programme that cycles through its four 0A (or 0B) groups
+    carrying the 8-character PS name and, if `rt` is given, its 2A (or 2B) RadioText groups, repeated to `n_bits`
+    (one pass if 0).  IEC 62106 group layout: block B = type(4) version(1) TP(1) PTY(5) + 5 group-specific bits."""
+    ps = (ps + " " * 8)[:8]
+    groups = []
+    for seg in range(4):
+        b = (0 << 12) | (int(version_b) << 11) | (tp << 10) | (pty << 5) | (1 << 2) | seg  # TA 0, M/S 0, DI bit 1
+        c = pi if version_b else 0xE0CD  # 0A block C: alternative frequencies (filler code pair); 0B: PI again
+        groups.append((pi, b, c, (ord(ps[2 * seg]) << 8) | ord(ps[2 * seg + 1])))
+    if rt:
+        per = 2 if version_b else 4
+        text = rt if len(rt) >= (32 if version_b else 64) else rt + "\r"
+        text = text + " " * (-len(text) % per)
+        for seg in range(len(text) // per):
+            b = (2 << 12) | (int(version_b) << 11) | (tp << 10) | (pty << 5) | (rt_ab << 4) | seg
+            ch = [ord(x) for x in text[per * seg:per * seg + per]]
+            if version_b:
+                groups.append((pi, b, pi, (ch[0] << 8) | ch[1]))
+            else:
+                groups.append((pi, b, (ch[0] << 8) | ch[1], (ch[2] << 8) | ch[3]))
+    one = []
+    for a, b, c, d in groups:
+        one += rds_block_bits(a, RDS_OFFSETS[0]) + rds_block_bits(b, RDS_OFFSETS[1]) + rds_block_bits(c, RDS_OFFSET_CPRIME if version_b else RDS_OFFSETS[2]) + rds_block_bits(d, RDS_OFFSETS[3])
+    one = np.array(one, dtype=np.uint8)
+    if n_bits <= 0:
+        return one
+    return np.tile(one, n_bits // len(one) + 1)[:n_bits]
+
+
 def rds_chips(bits: np.ndarray) -> np.ndarray:
     """Differential encoding d[i] = d[i-1]^b[i], then biphase: 1 -> (+1,-1), 0 -> (-1,+1)."""
     d = np.bitwise_xor.accumulate(bits.astype(np.uint8))
@@ -105,8 +144,9 @@ def station_params(s: int) -> dict:
 
 
 def synth_iq(n_blocks: int, mode: int = 0, seed: int = 1, f_l: float = 1000.0, f_r: float = 3000.0, rds: bool = True,
-             rds_level: float = 0.05, pilot_level: float = 0.08, audio_level: float = 0.45) -> np.ndarray:
-    """Returns n_blocks*307200 bytes of interleaved u8 I,Q."""
+             rds_level: float = 0.05, pilot_level: float = 0.08, audio_level: float = 0.45, rds_payload=None) -> np.ndarray:
+    """Returns n_blocks*307200 bytes of interleaved u8 I,Q.  `rds_payload`: a callable n_bits -> bit array (e.g. a
+    programme from rds_group_bits) replacing the random groups of `seed`."""
     fs = rf_rate(mode)
     n = n_blocks * BLOCK_IQ
     t = np.arange(n, dtype=np.float64) / fs
@@ -116,7 +156,7 @@ def synth_iq(n_blocks: int, mode: int = 0, seed: int = 1, f_l: float = 1000.0, f
     m = audio_level * (left + right) + audio_level * (left - right) * np.cos(2 * th) + pilot_level * np.cos(th)
     if rds:
         n_chips = int(np.ceil(t[-1] * CHIP_RATE)) + 2 * _PULSE_SPAN + 2
-        bits = rds_bits((n_chips + 1) // 2, seed)
+        bits = rds_payload((n_chips + 1) // 2) if rds_payload is not None else rds_bits((n_chips + 1) // 2, seed)
         m = m + rds_level * rds_baseband(rds_chips(bits), t - RDS_T0) * np.cos(3 * th)
     phi = 2 * np.pi * 75e3 * np.cumsum(m) / fs
     out = np.empty(2 * n, dtype=np.uint8)
