@@ -288,7 +288,7 @@ struct fmrx_batch {
     int32_t *dec_st;
     uint8_t *d_iq = nullptr;
     float *demod = nullptr, *mono = nullptr, *pilot = nullptr, *nco = nullptr, *sbpf = nullptr, *mixed = nullptr, *stereo = nullptr;
-    float *rbpf = nullptr, *rsq = nullptr, *rnco = nullptr, *rlpf = nullptr, *rres = nullptr, *rrrc = nullptr;
+    float *rbpf = nullptr, *rsq = nullptr, *rnco = nullptr, *rmixed = nullptr, *rlpf = nullptr, *rres = nullptr, *rrrc = nullptr;
     int16_t *audio = nullptr;
     float *audio_f = nullptr;
     uint8_t *bits = nullptr;
@@ -450,11 +450,16 @@ int enqueue_chain(fmrx_batch *b, const uint8_t *iq, long long ld_iq, int s0, int
         const PllParams pr{114000.0f, 240000.0f, 0.5f, b->rds_phase, 0.001f};
         const bool a_on = b->audio_on && stereo_live;
         STAGE(FMRX_STAGE_PLL);
+        // each loop also writes its NCO output times the signal it will be mixed with (stereo band / RDS band), so the
+        // filters of phase C read one signal instead of two
         if (a_on && b->rds_on && st_blocks == nblk) {
-            LAUNCH(launch_pll_blocks(IF2(b->pilot), IF2(b->nco), pa, b->pll_st + (long long)s0 * 6, IF2(b->rsq), IF2(b->rnco), pr, b->rds_pll_st + (long long)s0 * 6, ldif, ns, NIF, nblk, st));
+            LAUNCH(launch_pll_blocks(IF2(b->pilot), IF2(b->nco), pa, b->pll_st + (long long)s0 * 6, IF2(b->rsq), IF2(b->rnco), pr, b->rds_pll_st + (long long)s0 * 6, ldif, ns, NIF, nblk, st,
+                                     IF2(b->sbpf), IF2(b->mixed), IF2(b->rbpf), IF2(b->rmixed)));
         } else {
-            if (a_on) LAUNCH(launch_pll_blocks(IF2(b->pilot), IF2(b->nco), pa, b->pll_st + (long long)s0 * 6, nullptr, nullptr, pa, nullptr, ldif, ns, NIF, st_blocks, st));
-            if (b->rds_on) LAUNCH(launch_pll_blocks(IF2(b->rsq), IF2(b->rnco), pr, b->rds_pll_st + (long long)s0 * 6, nullptr, nullptr, pr, nullptr, ldif, ns, NIF, nblk, st));
+            if (a_on) LAUNCH(launch_pll_blocks(IF2(b->pilot), IF2(b->nco), pa, b->pll_st + (long long)s0 * 6, nullptr, nullptr, pa, nullptr, ldif, ns, NIF, st_blocks, st,
+                                               IF2(b->sbpf), IF2(b->mixed)));
+            if (b->rds_on) LAUNCH(launch_pll_blocks(IF2(b->rsq), IF2(b->rnco), pr, b->rds_pll_st + (long long)s0 * 6, nullptr, nullptr, pr, nullptr, ldif, ns, NIF, nblk, st,
+                                                    IF2(b->rbpf), IF2(b->rmixed)));
         }
     }
     if (piped) { CU(cudaEventRecord(b->ev_p[set], stP)); CU(cudaStreamWaitEvent(stC, b->ev_p[set], 0)); }
@@ -466,14 +471,13 @@ int enqueue_chain(fmrx_batch *b, const uint8_t *iq, long long ld_iq, int s0, int
             STAGE(FMRX_STAGE_STEREO_LPF);
             if (st_blocks < nblk) CU(cudaMemset2DAsync(AU(b->stereo), lda * 4, 0, (size_t)nblk * b->n_audio * 4, ns, st));
             if (b->cfg.mode == 1) {
-                LAUNCH(launch_multiply(IF2(b->sbpf), IF2(b->nco), IF(b->mixed), ldif, st_blocks * NIF, ns, st));
                 ResampleJob r{};  // convolveWithDecimMode1(stereo_filt, mixed, stereo_coeff, stereo_initial, 5, 24), :245 (Q14)
-                r.x = IF(b->mixed); r.y = AU(b->stereo); r.zi = b->zi_stereo + (long long)s0 * b->nzi_a; r.h = b->d_h_stereo; r.ldx = ldif; r.ldy = lda;
+                r.x = IF2(b->mixed); r.y = AU(b->stereo); r.zi = b->zi_stereo + (long long)s0 * b->nzi_a; r.h = b->d_h_stereo; r.ldx = ldif; r.ldy = lda;
                 r.n = NIF; r.n_ref = NIF; r.ny = b->n_audio; r.n_blocks = st_blocks; r.n_streams = ns; r.ntaps = b->audio_taps; r.nzi = b->nzi_a;
                 r.decim = 5; r.up = b->up; r.gain_up = 0; r.exact = ex;
                 LAUNCH(launch_resample(r, st));
             } else {
-                LAUNCH(fir(IF2(b->sbpf), IF2(b->nco), AU(b->stereo), b->zi_stereo + (long long)s0 * b->nzi_a, b->nzi_a, b->h_stereo.data(), ldif, lda, NIF, 5, SRC_MIX_LATE, ex, st_blocks));
+                LAUNCH(fir(IF2(b->mixed), nullptr, AU(b->stereo), b->zi_stereo + (long long)s0 * b->nzi_a, b->nzi_a, b->h_stereo.data(), ldif, lda, NIF, 5, SRC_PLAIN, ex, st_blocks));
             }
             stereo = AU(b->stereo);
         }
@@ -485,7 +489,7 @@ int enqueue_chain(fmrx_batch *b, const uint8_t *iq, long long ld_iq, int s0, int
     }
     // ---- rds_thread after the PLL (:404-411) and frame_thread
     if (b->rds_on) {
-        { STAGE(FMRX_STAGE_RDS_MIX_LPF); LAUNCH(fir(IF2(b->rnco), IF2(b->rbpf), IF(b->rlpf), b->zi_lpf + (long long)s0 * kHist, kHist, b->h_lpf3k, ldif, ldif, NIF, 1, SRC_MIX_HALF, 0, nblk)); }
+        { STAGE(FMRX_STAGE_RDS_MIX_LPF); LAUNCH(fir(IF2(b->rmixed), nullptr, IF(b->rlpf), b->zi_lpf + (long long)s0 * kHist, kHist, b->h_lpf3k, ldif, ldif, NIF, 1, SRC_PROD_HALF, 0, nblk)); }
         ResampleJob r{};
         r.x = IF(b->rlpf); r.y = RD(b->rres); r.zi = b->zi_anti + (long long)s0 * (kTaps * 19 - 1); r.h = b->d_h_anti; r.h_host = b->h_anti.data(); r.ldx = ldif; r.ldy = ldr;
         r.n = NIF; r.n_ref = NIF + 1; r.ny = NRDS; r.n_blocks = nblk; r.n_streams = ns; r.ntaps = kTaps * 19; r.nzi = kTaps * 19 - 1;
@@ -589,11 +593,11 @@ int fmrx_batch_create(const fmrx_config *cfg, fmrx_batch **out) {
     if (b->audio_on) {
         CU(b->dalloc(b->mono, kSets * S * NB * b->n_audio)); CU(b->dalloc(b->pilot, kSets * S * NB * NIF)); CU(b->dalloc(b->nco, kSets * S * NB * NIF));
         CU(b->dalloc(b->sbpf, kSets * S * NB * NIF)); CU(b->dalloc(b->stereo, S * NB * b->n_audio));
-        if (cfg->mode == 1) CU(b->dalloc(b->mixed, S * NB * NIF));
+        CU(b->dalloc(b->mixed, kSets * S * NB * NIF));  // stereo-band x NCO, written by the PLL kernel
         CU(b->dalloc(b->audio, S * NB * b->n_audio * 2)); CU(b->dalloc(b->audio_f, S * NB * b->n_audio * 2));
     }
     if (b->rds_on) {
-        CU(b->dalloc(b->rbpf, kSets * S * NB * NIF)); CU(b->dalloc(b->rsq, kSets * S * NB * NIF)); CU(b->dalloc(b->rnco, kSets * S * NB * NIF)); CU(b->dalloc(b->rlpf, S * NB * NIF));
+        CU(b->dalloc(b->rbpf, kSets * S * NB * NIF)); CU(b->dalloc(b->rsq, kSets * S * NB * NIF)); CU(b->dalloc(b->rnco, kSets * S * NB * NIF)); CU(b->dalloc(b->rmixed, kSets * S * NB * NIF)); CU(b->dalloc(b->rlpf, S * NB * NIF));
         CU(b->dalloc(b->rres, S * NB * NRDS)); CU(b->dalloc(b->rrrc, S * NB * NRDS));
         CU(b->dalloc(b->bits, S * NB * FMRX_MAX_BITS)); CU(b->dalloc(b->nbits, S * NB)); CU(b->dalloc(b->nev, S * NB)); CU(b->dalloc(b->ev, S * NB * FMRX_MAX_EVENTS));
         CU(cudaMemset(b->bits, 0, S * NB * FMRX_MAX_BITS));

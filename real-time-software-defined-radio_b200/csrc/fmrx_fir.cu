@@ -113,6 +113,7 @@ __device__ __forceinline__ float form(float a, float b, bool in_block) {
     if (KIND == SRC_PLAIN) return a;
     if (KIND == SRC_SQUARE) return __fmul_rn(a, a);
     if (KIND == SRC_MIX_LATE) return __fmul_rn(a, b);
+    if (KIND == SRC_PROD_HALF) return in_block ? a : __fmul_rn(a, 0.5f);  // the sum is doubled at the end
     return in_block ? __fmul_rn(__fmul_rn(a, b), 2.0f) : __fmul_rn(a, b);  // SRC_MIX_HALF
 }
 
@@ -125,9 +126,10 @@ __device__ __forceinline__ float source(const FirDev &a, const float *xs, const 
     if (in_block) {
         q = (long long)b * a.n + p;
     } else if (b > 0) {
-        q = (long long)b * a.n + p - (KIND == SRC_MIX_HALF ? 0 : 1);  // one-late history, except the mixer (Q8)
+        q = (long long)b * a.n + p - ((KIND == SRC_MIX_HALF || KIND == SRC_PROD_HALF) ? 0 : 1);  // one-late history, except the mixer (Q8)
     } else {
-        return zs[kHist + p];  // carried state already holds the formed value
+        const float z = zs[kHist + p];  // carried state already holds the formed value (for the mixer: the product without its x2)
+        return KIND == SRC_PROD_HALF ? __fmul_rn(z, 0.5f) : z;
     }
     float v = xs[q];
     float w = (KIND == SRC_MIX_LATE || KIND == SRC_MIX_HALF) ? x2s[q] : 0.0f;
@@ -225,7 +227,10 @@ __global__ void __launch_bounds__(NT) fir151_kernel(const FirDev a, const __grid
         float *ys = a.y + (long long)s * a.ldy + (long long)b * a.ny + o;
         float out[RO];
 #pragma unroll
-        for (int r = 0; r < RO; ++r) out[r] = h ? acc[r].y : acc[r].x;
+        for (int r = 0; r < RO; ++r) {
+            out[r] = h ? acc[r].y : acc[r].x;
+            if (KIND == SRC_PROD_HALF) out[r] = __fmul_rn(out[r], 2.0f);
+        }
         if (o + RO <= a.ny && ((reinterpret_cast<uintptr_t>(ys) & 15) == 0)) {
 #pragma unroll
             for (int r = 0; r < RO; r += 4) reinterpret_cast<float4 *>(ys)[r / 4] = make_float4(out[r], out[r + 1], out[r + 2], out[r + 3]);
@@ -243,12 +248,12 @@ __global__ void fir_state_kernel(const float *x, const float *x2, float *zi, lon
     const int s = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nzi) return;
-    const int p = n - nzi + i - (KIND == SRC_MIX_HALF ? 0 : 1);
+    const int p = n - nzi + i - ((KIND == SRC_MIX_HALF || KIND == SRC_PROD_HALF) ? 0 : 1);
     if (p < 0) return;  // block shorter than the state: entry keeps its old value (never live for a 151-tap filter)
     const long long q = (long long)s * ldx + (long long)(n_blocks - 1) * n + p;
     const float v = x[q];
     const float w = (KIND == SRC_MIX_LATE || KIND == SRC_MIX_HALF) ? x2[q] : 0.0f;
-    zi[(long long)s * nzi + i] = form<KIND>(v, w, false);
+    zi[(long long)s * nzi + i] = KIND == SRC_PROD_HALF ? v : form<KIND>(v, w, false);  // the state keeps the plain product
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -575,6 +580,7 @@ int launch_fir(const FirJob &j, fmrx_stream_t st) {
         case SRC_SQUARE: return launch_fir_k<SRC_SQUARE>(j, d, grid, st);
         case SRC_MIX_LATE: return launch_fir_k<SRC_MIX_LATE>(j, d, grid, st);
         case SRC_MIX_HALF: return launch_fir_k<SRC_MIX_HALF>(j, d, grid, st);
+        case SRC_PROD_HALF: return launch_fir_k<SRC_PROD_HALF>(j, d, grid, st);
         default: return (int)cudaErrorInvalidValue;
     }
 }

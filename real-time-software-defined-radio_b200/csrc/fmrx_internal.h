@@ -23,7 +23,10 @@ enum SrcKind {
     SRC_PLAIN = 0,    // x[p]; history one sample late (Q1)
     SRC_SQUARE = 1,   // x[p]^2; zi holds squares (pllCombine, src/helper.cpp:139,162-164)
     SRC_MIX_LATE = 2, // a[p]*b[p]; history one sample late (stereo mixer + LPF, src/fm_radio.cpp:269-274)
-    SRC_MIX_HALF = 3  // 2*a[p]*b[p] in the block, a*b (not late, no x2) in the history (Q8, src/filter.cpp:387,399)
+    SRC_MIX_HALF = 3, // 2*a[p]*b[p] in the block, a*b (not late, no x2) in the history (Q8, src/filter.cpp:387,399)
+    SRC_PROD_HALF = 4 // the same filter fed with the ready-made product p = a*b (the PLL kernel writes it next to its NCO
+                      // output): staged as p in the block and p/2 in the history, the sum doubled at the end -- scaling by two
+                      // is exact at every step, so this is the MIX_HALF sum with one input signal instead of two
 };
 
 struct FirJob {
@@ -80,8 +83,12 @@ struct PllParams {
 };
 // x,nco: [S][ld] with n_blocks*n samples; state [S][6].  One launch runs up to two independent PLL populations
 // (stereo pilot + RDS carrier); pass xb == nullptr for a single one.
+// mula/mulb (optional, same layout): a second signal whose product with the NCO OUTPUT is written to proda/prodb in the same
+// pass (the stereo mixer src/fm_radio.cpp:269-272 and the RDS mixer src/filter.cpp:387 without its x2), so that the
+// filters behind the PLLs read one signal instead of two.
 int launch_pll_blocks(const float *xa, float *ncoa, PllParams pa, float *sta, const float *xb, float *ncob, PllParams pb, float *stb,
-                      long long ld, int n_streams, int n, int n_blocks, fmrx_stream_t st);
+                      long long ld, int n_streams, int n, int n_blocks, fmrx_stream_t st, const float *mula = nullptr, float *proda = nullptr,
+                      const float *mulb = nullptr, float *prodb = nullptr);
 
 // mixed = a*b elementwise (mode-1 stereo path materialises it for the resampler, src/fm_radio.cpp:240-245)
 int launch_multiply(const float *a, const float *b, float *y, long long ld, int n_total, int n_streams, fmrx_stream_t st);

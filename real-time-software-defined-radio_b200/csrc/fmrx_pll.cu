@@ -38,6 +38,8 @@ struct PllSide {
     const float *x;
     float *nco;
     float *state;
+    const float *mul;  // optional second signal ...
+    float *prod;       // ... and where nco[k] * mul[k] goes
     float Ki, Kp, fratio, scale, adj;
 };
 
@@ -48,6 +50,8 @@ __global__ void __launch_bounds__(32) pll_kernel(PllSide A, PllSide B, long long
     if (lane >= n_streams || P.x == nullptr) return;
     const float *x = P.x + (long long)lane * ld;
     float *nco = P.nco + (long long)lane * ld;
+    const float *mul = P.mul ? P.mul + (long long)lane * ld : nullptr;
+    float *prod = P.prod ? P.prod + (long long)lane * ld : nullptr;
     float *st = P.state + (long long)lane * 6;
     PllCarry c{st[0], st[1], st[2], st[3]};
     PllFast f;
@@ -65,21 +69,33 @@ __global__ void __launch_bounds__(32) pll_kernel(PllSide A, PllSide B, long long
     for (int b = 0; b < n_blocks; ++b) {
         const float *xb = x + (long long)b * n;
         float *ob = nco + (long long)b * n;
+        const float *mb = mul ? mul + (long long)b * n : nullptr;
+        float *pb = prod ? prod + (long long)b * n : nullptr;
         int k = 0;
-        if ((((uintptr_t)xb | (uintptr_t)ob) & 15) == 0 && n >= 8) {
+        if ((((uintptr_t)xb | (uintptr_t)ob | (uintptr_t)mb | (uintptr_t)pb) & 15) == 0 && n >= 8) {
             // the input is read two groups (8 samples, ~2.5k cycles of loop time) ahead of its use: a lane streams its
             // own row, so every load is a cache line of its own and would otherwise sit on the dependency chain
             const float4 *x4 = reinterpret_cast<const float4 *>(xb);
             const int groups = n / 4;
+            const float4 *m4 = reinterpret_cast<const float4 *>(mb);
             float4 v0 = __ldg(x4), v1 = __ldg(x4 + 1);
+            float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
+            if (pb) { w0 = __ldg(m4); w1 = __ldg(m4 + 1); }
             for (int g = 0; g < groups; ++g, k += 4) {
-                const float4 v = v0;
+                const float4 v = v0, w = w0;
                 v0 = v1;
-                if (g + 2 < groups) v1 = __ldg(x4 + g + 2);
+                w0 = w1;
+                if (g + 2 < groups) {
+                    v1 = __ldg(x4 + g + 2);
+                    if (pb) w1 = __ldg(m4 + g + 2);
+                }
                 // ... and its 128-byte line is pulled into L2 sixteen groups before that: with 8192 lanes each on a row of
                 // its own, every line is a DRAM page (and mostly a TLB) miss, and the register prefetch alone left 15% of
                 // the kernel's samples waiting on it (ncu source page, profiles/r1w)
-                if ((g & 7) == 0 && g + 16 < groups) asm volatile("prefetch.global.L2 [%0];" ::"l"(x4 + g + 16));
+                if ((g & 7) == 0 && g + 16 < groups) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(x4 + g + 16));
+                    if (pb) asm volatile("prefetch.global.L2 [%0];" ::"l"(m4 + g + 16));
+                }
                 // four branch-free steps = one basic block; if any of them left the fast path's domain (first group
                 // after loading the state, zero / non-finite input, the +-pi seam: ~1e-5 of the groups) the four
                 // carried floats are restored and the group is redone with libm
@@ -101,10 +117,12 @@ __global__ void __launch_bounds__(32) pll_kernel(PllSide A, PllSide B, long long
                     last = slow(v.w, count(off, k + 3));
                 }
                 *reinterpret_cast<float4 *>(ob + k) = o;
+                if (pb) *reinterpret_cast<float4 *>(pb + k) = make_float4(__fmul_rn(w.x, o.x), __fmul_rn(w.y, o.y), __fmul_rn(w.z, o.z), __fmul_rn(w.w, o.w));
             }
         }
         for (; k < n; ++k) {
             ob[k] = last;  // output sample k is the NCO value of step k-1 (src/helper.cpp:29,44,56)
+            if (pb) pb[k] = __fmul_rn(mb[k], last);
             last = slow(xb[k], count(off, k));
         }
         off = __fadd_rn(off, (float)n);  // src/helper.cpp:53
@@ -140,9 +158,10 @@ __global__ void multiply_kernel(const float *a, const float *b, float *y, long l
     y[q] = __fmul_rn(a[q], b[q]);
 }
 
-PllSide make_side(const float *x, float *nco, float *state, const PllParams &p) {
+PllSide make_side(const float *x, float *nco, float *state, const PllParams &p, const float *mul, float *prod) {
     PllSide s;
     s.x = x; s.nco = nco; s.state = state;
+    s.mul = (mul && prod) ? mul : nullptr; s.prod = (mul && prod) ? prod : nullptr;
     const float Cp = 2.666f, Ci = 3.555f;  // src/helper.cpp:15-16
     s.Ki = (p.bw * p.bw) * Ci;
     s.Kp = p.bw * Cp;
@@ -155,9 +174,9 @@ PllSide make_side(const float *x, float *nco, float *state, const PllParams &p) 
 }  // namespace
 
 int launch_pll_blocks(const float *xa, float *ncoa, PllParams pa, float *sta, const float *xb, float *ncob, PllParams pb, float *stb,
-                      long long ld, int n_streams, int n, int n_blocks, fmrx_stream_t st) {
-    PllSide A = make_side(xa, ncoa, sta, pa);
-    PllSide B = xb ? make_side(xb, ncob, stb, pb) : PllSide{};
+                      long long ld, int n_streams, int n, int n_blocks, fmrx_stream_t st, const float *mula, float *proda, const float *mulb, float *prodb) {
+    PllSide A = make_side(xa, ncoa, sta, pa, mula, proda);
+    PllSide B = xb ? make_side(xb, ncob, stb, pb, mulb, prodb) : PllSide{};
     const int lanes = xb ? 2 * n_streams : n_streams;
     pll_kernel<<<(lanes + 31) / 32, 32, 0, st>>>(A, B, ld, n_streams, n, n_blocks);
     launch_counter() += 1;
