@@ -8,6 +8,8 @@
 //
 // The driver entry points are resolved through cudaGetDriverEntryPoint, so libfmrx.so keeps no link-time dependency on
 // libcuda (it must load on a host without a driver: the C-ABI export test runs there).
+#include <cstdlib>
+
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -62,7 +64,14 @@ SmPartition *partition_create(int device, int want_small, int prio_small, fmrx_s
     unsigned int groups = 1;
     if (devGet(&dev, device) != CUDA_SUCCESS || getRes(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return nullptr;
     if (want_small <= 0 || (unsigned)want_small + 8 > all.sm.smCount) return nullptr;
-    if (split(&part, &groups, &all, &rest, 0, (unsigned)want_small) != CUDA_SUCCESS || groups != 1 || rest.sm.smCount == 0) return nullptr;
+    // without the flag the split granularity is 8 SMs on this architecture; IGNORE_SM_COSCHEDULING (clusters are not used
+    // here) brings it down to 2, which lets the two sides be balanced more finely
+    unsigned flags = CU_DEV_SM_RESOURCE_SPLIT_IGNORE_SM_COSCHEDULING;
+    if (const char *e = getenv("FMRX_PLL_SPLIT_FLAGS")) flags = (unsigned)atoi(e);
+    if (split(&part, &groups, &all, &rest, flags, (unsigned)want_small) != CUDA_SUCCESS || groups != 1 || rest.sm.smCount == 0) {
+        groups = 1;
+        if (split(&part, &groups, &all, &rest, 0, (unsigned)want_small) != CUDA_SUCCESS || groups != 1 || rest.sm.smCount == 0) return nullptr;
+    }
     CUdevResourceDesc d_small, d_big;
     if (genDesc(&d_small, &part, 1) != CUDA_SUCCESS || genDesc(&d_big, &rest, 1) != CUDA_SUCCESS) return nullptr;
     SmPartition *p = new SmPartition();
