@@ -231,6 +231,25 @@ int fmrx_rds_app_reset(fmrx_rds_app *);
 int fmrx_rds_app_feed(fmrx_rds_app *, const uint8_t *bits, const int32_t *n_bits, int n_blocks, fmrx_rds_group *groups, int cap, int32_t *n_groups);
 int fmrx_rds_app_station(const fmrx_rds_app *, int stream, fmrx_rds_station *out);
 
+/* ---- model-compatible operators ------------------------------------------------------------
+ * The arithmetic of the reference's PYTHON models (the model directory), float64, so that fmMonoBlock.py / fmRDSblock.py can be
+ * diffed tightly against the GPU; the C++ program is numerically a different receiver.  Batched over
+ * n_streams independent streams ([stream][sample]); host buffers. */
+/* scipy.signal.firwin(ntaps, cutoff, window='hann') as the models call it: one cutoff (fraction of Nyquist) with
+ * pass_zero=1 = low-pass, two with pass_zero=0 = band-pass (model/fmMonoBlock.py:43-45,115,150,159) */
+int fmrx_model_firwin(int ntaps, const double *cutoff, int n_cutoff, int pass_zero, double *h);
+/* scipy.signal.lfilter(b, 1.0, x, zi=...) then the models' [::decim] slicing, on the input zero-stuffed by `up`
+ * (model/fmRDSblock.py:188-199); y:[S][n*up/decim].  hist:[S][ntaps-1] = the last ntaps-1 input samples (zeros before
+ * the first block), updated in place.  Products and sums are rounded one by one, oldest tap first (a transposed direct
+ * form II); scipy's own FIR shortcut sums in numpy.convolve's order, so agreement is 1e-13 relative, not bit for bit. */
+int fmrx_model_lfilter(double *y, const double *x, int n_streams, int n, const double *b, int ntaps, double *hist, int decim, int up);
+/* fmSupportLib.fmDemodArctan (model/fmSupportLib.py:12-44): atan2 + numpy.unwrap against the carried phase; prev_phase:[S] in/out */
+int fmrx_model_demod(double *demod, const double *I, const double *Q, int n_streams, int n, double *prev_phase);
+/* fmPll.fmPll (model/fmPll.py:4-56): nco, nco_q:[S][n+1] (untrimmed like the model's; nco_q[0] is 0 where the model leaves
+ * it uninitialised); state:[S][6] in the MODEL's order: integrator, phaseEst, feedbackI, feedbackQ, ncoOut[0], trigOffset */
+int fmrx_model_pll(double *nco, double *nco_q, const double *x, int n_streams, int n, double freq, double Fs, double nco_scale, double phase_adjust,
+                   double norm_bandwidth, double *state);
+
 /* ---- measurement helpers (used by bench.py; not part of the receive path) ---------------------------------- */
 /* runs an FP32 issue-rate microbenchmark on `device` and returns the best-of-`reps` rate in T lane-ops/s:
  * kind 0 = FFMA, 1 = FMUL+FADD pairs, 2 = packed FFMA2, 3 = packed FMUL2+FADD2 */

@@ -40,6 +40,7 @@ fp = C.POINTER(C.c_float)
 u8p = C.POINTER(C.c_uint8)
 i16p = C.POINTER(C.c_int16)
 i32p = C.POINTER(C.c_int32)
+dp = C.POINTER(C.c_double)
 
 
 class RdsGroup(C.Structure):
@@ -114,6 +115,10 @@ SIGNATURES = {
     "fmrx_batch_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "fmrx_batch_stage_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "fmrx_batch_timeline": (C.c_int, [C.c_void_p, C.c_int, i32p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "fmrx_model_firwin": (C.c_int, [C.c_int, dp, C.c_int, C.c_int, dp]),
+    "fmrx_model_lfilter": (C.c_int, [dp, dp, C.c_int, C.c_int, dp, C.c_int, dp, C.c_int, C.c_int]),
+    "fmrx_model_demod": (C.c_int, [dp, dp, dp, C.c_int, C.c_int, dp]),
+    "fmrx_model_pll": (C.c_int, [dp, dp, dp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, dp]),
     "fmrx_rds_app_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "fmrx_rds_app_destroy": (None, [C.c_void_p]),
     "fmrx_rds_app_reset": (C.c_int, [C.c_void_p]),
@@ -298,6 +303,54 @@ def measure_fp32_peak(kind, device=0, reps=5):
 # ---------------------------------------------------------------------------------------------------------------------
 # the batched chain
 # ---------------------------------------------------------------------------------------------------------------------
+# ---- model-compatible operators (float64, the arithmetic of the reference's Python models)
+def _d(a):
+    return np.ascontiguousarray(a, np.float64)
+
+
+def model_firwin(ntaps, cutoff, pass_zero=True):
+    """scipy.signal.firwin(ntaps, cutoff, window='hann', pass_zero=...) with cutoff a scalar (low-pass) or [lo, hi] (band-pass)"""
+    c = _d(np.atleast_1d(cutoff))
+    h = np.empty(ntaps, np.float64)
+    check(lib().fmrx_model_firwin(ntaps, c.ctypes.data_as(dp), c.size, 1 if pass_zero is True or pass_zero == "lowpass" else 0, h.ctypes.data_as(dp)))
+    return h
+
+
+def model_lfilter(x, b, hist, decim=1, up=1):
+    """lfilter(b, 1, x, zi) then [::decim] (on the input zero-stuffed by `up`); x:[S][n] or [n]; hist:[S][len(b)-1] updated in place"""
+    x2 = _d(x)
+    x2 = x2.reshape(1, -1) if x2.ndim == 1 else x2
+    b = _d(b)
+    S, n = x2.shape
+    assert hist.dtype == np.float64 and hist.flags.c_contiguous and hist.size == S * (b.size - 1)
+    y = np.empty((S, n * up // decim), np.float64)
+    check(lib().fmrx_model_lfilter(y.ctypes.data_as(dp), x2.ctypes.data_as(dp), S, n, b.ctypes.data_as(dp), b.size, hist.ctypes.data_as(dp), decim, up))
+    return y[0] if np.ndim(x) == 1 else y
+
+
+def model_demod(i, q, prev_phase):
+    """fmSupportLib.fmDemodArctan; prev_phase: float64 array [S] updated in place"""
+    i2, q2 = _d(i), _d(q)
+    i2 = i2.reshape(1, -1) if i2.ndim == 1 else i2
+    q2 = q2.reshape(i2.shape)
+    assert prev_phase.dtype == np.float64 and prev_phase.size == i2.shape[0]
+    out = np.empty_like(i2)
+    check(lib().fmrx_model_demod(out.ctypes.data_as(dp), i2.ctypes.data_as(dp), q2.ctypes.data_as(dp), i2.shape[0], i2.shape[1], prev_phase.ctypes.data_as(dp)))
+    return out[0] if np.ndim(i) == 1 else out
+
+
+def model_pll(x, freq, Fs, state, nco_scale=1.0, phase_adjust=0.0, norm_bandwidth=0.01):
+    """fmPll.fmPll; state: float64 [S][6] in the model's order, updated in place; returns (ncoOut, ncoOutQ) of length n+1"""
+    x2 = _d(x)
+    x2 = x2.reshape(1, -1) if x2.ndim == 1 else x2
+    S, n = x2.shape
+    assert state.dtype == np.float64 and state.size == 6 * S
+    a, b = np.empty((S, n + 1), np.float64), np.empty((S, n + 1), np.float64)
+    check(lib().fmrx_model_pll(a.ctypes.data_as(dp), b.ctypes.data_as(dp), x2.ctypes.data_as(dp), S, n, freq, Fs, nco_scale, phase_adjust, norm_bandwidth,
+                               state.ctypes.data_as(dp)))
+    return (a[0], b[0]) if np.ndim(x) == 1 else (a, b)
+
+
 class RdsApp:
     """RDS data-link / application layer over the bits a Batch returns (host code, fmrx_rds_app_*)."""
 
