@@ -142,6 +142,31 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def bind_to_gpu_numa_node(index):
+    """Pins this rank's threads to the CPUs of the NUMA node its GPU hangs off, so that the pinned host buffers it
+    allocates (first touch) and the H2D copies out of them stay on that node's memory controller.  Returns the node or None."""
+    try:
+        import torch
+
+        bus = torch.cuda.get_device_properties(index).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(index), "pci_domain_id", 0)
+        dev_id = torch.cuda.get_device_properties(index).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev_id:02x}.0/numa_node"
+        node = int(open(path).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def run_reference_arm(args, rank):
     if rank != 0:
         return
@@ -179,6 +204,7 @@ def run_fmrx_arm(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None  # pinned buffers are first-touched on the GPU's own node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -356,10 +382,10 @@ def run_fmrx_arm(args, rank, world, local_rank):
                    "numerics": "audio path reference-exact (mul+add), RDS path fma",
                    "sm_partition": {"pll_sms": pll_sms, "filter_sms": filter_sms} if pll_sms else "none (phases share the device)", "realtime_streams": int(value / 2.4), "e2e_realtime_streams": int(e2e_value / 2.4),
                    "l2": "input per step %.2f GB >> 126 MB L2, no flush needed" % (S * B * BLOCK_BYTES / 1e9), "input_reuse": "same synthesised block replayed each step, state carried",
-                   "synth_seconds": round(t_synth, 2), "parity_spot_check": parity,
+                   "synth_seconds": round(t_synth, 2), "parity_spot_check": parity, "rank0_numa_node": numa,
                    "e2e_timer": "host clock around K fmrx_batch_submit calls with fmrx_batch_wait on the previous step (two steps in flight), barrier + synchronize on both sides, max over ranks",
                    "e2e_sync_call_msps": round(e2e_sync_value, 1)},
-        "e2e": {"value": round(e2e_value, 1), "unit": "Msps", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "e2e": {"value": round(e2e_value, 1), "unit": "Msps", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world},  # whole job, like `value`
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
