@@ -613,7 +613,13 @@ int fmrx_batch_create(const fmrx_config *cfg, fmrx_batch **out) {
         if (const char *e = getenv("FMRX_PIPE_PRIO")) { if (e[0] == '0') greatest = least; }  // experiment switch: equal priorities
         const int mid = greatest < least ? greatest + 1 : least;
         // FMRX_PLL_SMS: SMs set aside for the PLL stream (0 = no partition); default 32 once the batch fills the device
-        int pll_sms = b->S >= 1024 && b->audio_on && b->rds_on ? 32 : 0;
+        // two PLL warps per scheduler: 32 SMs for the 8192 loops of 4096 stations with stereo + RDS, 16 when only the pilot loop runs
+        int pll_sms = 0;
+        if (b->S >= 1024 && b->audio_on) {
+            const int loops = b->S * (b->rds_on ? 2 : 1), warps = (loops + 31) / 32;
+            pll_sms = ((warps + 7) / 8 + 7) / 8 * 8;  // warps / (4 schedulers x 2), rounded up to the split granularity
+            if (pll_sms > 64) pll_sms = 64;
+        }
         if (const char *e = getenv("FMRX_PLL_SMS")) pll_sms = atoi(e);
         if (pll_sms > 0) {
             const int prio_big[2] = {least, mid};
