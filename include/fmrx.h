@@ -147,7 +147,9 @@ int fmrx_batch_process(fmrx_batch *, const uint8_t *iq, int n_blocks, const fmrx
  * output buffers must be page-locked (fmrx_pinned_alloc) and stay untouched until fmrx_batch_wait(ticket) returns. */
 int fmrx_batch_submit(fmrx_batch *, const uint8_t *iq, int n_blocks, const fmrx_outputs *out, long long *ticket);
 int fmrx_batch_wait(fmrx_batch *, long long ticket);
-/* device -> device, asynchronous on the handle's stream; fmrx_batch_sync() waits. */
+/* device -> device, asynchronous on the handle's own (non-blocking) streams; fmrx_batch_sync() waits.  The handle's
+ * streams do not synchronise with any stream of the caller: iq_device must be complete before the call (synchronise the
+ * stream that produced it) and the outputs must not be read before fmrx_batch_sync() or a wait on fmrx_batch_cuda_stream(). */
 int fmrx_batch_process_device(fmrx_batch *, const uint8_t *iq_device, int n_blocks, const fmrx_outputs *out_device);
 int fmrx_batch_sync(fmrx_batch *);
 void *fmrx_batch_cuda_stream(fmrx_batch *);         /* cudaStream_t on which a call's outputs are completed */

@@ -217,3 +217,69 @@ def test_async_submit_pipeline_equals_oracle(monkeypatch, pll_sms):
         audio, _, bits, _, _ = Chain(0, 1).run(raw[s])
         assert_bits(np.concatenate([got_audio[k][s].ravel() for k in range(steps)]), audio, f"station {s} audio")
         assert np.array_equal(np.concatenate([got_bits[k][s] for k in range(steps)]), np.concatenate(bits)), f"station {s} bits"
+
+
+def test_full_batch_4096_three_entry_points_agree():
+    """BASELINE config 5 at its full size: 4096 stations x 1 block x 3 steps, mono + stereo + RDS, state carried.  The
+    second half of the batch replays the first half's bytes, so rows s and s + 2048 must be bit-identical whatever tile,
+    chunk, buffer set or SM partition they land on; the synchronous host path, the asynchronous host path and the
+    device-resident pipeline must return the same bytes; a few stations are checked against the oracle."""
+    import ctypes as C
+
+    import torch
+
+    S, H, steps, na = 4096, 2048, 3, 3072
+    dev = torch.device("cuda", 0)
+    half = synth.synth_batch_torch(range(H), steps, 0, dev, chunk=64)          # [H][steps*307200]
+    d_iq = torch.cat([half, half], 0).contiguous()
+    h_all = d_iq.cpu()
+
+    def ptr(t, typ):
+        return C.cast(C.c_void_p(t.data_ptr()), typ)
+
+    results = {}
+    # --- device-resident pipeline
+    d_audio = torch.empty((S, 1, 2 * na), dtype=torch.int16, device=dev)
+    d_bits = torch.zeros((S, 1, fmrx.MAX_BITS), dtype=torch.uint8, device=dev)
+    d_nbits = torch.zeros((S, 1), dtype=torch.int32, device=dev)
+    dout = fmrx.Outputs(ptr(d_audio, fmrx.i16p), None, ptr(d_bits, fmrx.u8p), ptr(d_nbits, fmrx.i32p), None, None)
+    with fmrx.Batch(S, mode=0, profile=1, max_blocks=1) as rx:
+        assert rx.partition()[0] > 0, "the full batch should run with the PLL partition"
+        acc = []
+        for k in range(steps):
+            blk = d_iq[:, k * 307200:(k + 1) * 307200].contiguous()
+            torch.cuda.synchronize()  # torch's copy runs on torch's stream; the library's streams do not wait for it
+            rx.process_device(blk.data_ptr(), 1, dout)
+            rx.sync()
+            acc.append((d_audio.cpu().numpy().copy(), d_bits.cpu().numpy().copy(), d_nbits.cpu().numpy().copy()))
+        results["device"] = acc
+    # --- asynchronous and synchronous host paths
+    for name in ("submit", "process"):
+        h_iq = torch.empty((S, 307200), dtype=torch.uint8).pin_memory()
+        h_audio = torch.zeros((S, 1, 2 * na), dtype=torch.int16).pin_memory()
+        h_bits = torch.zeros((S, 1, fmrx.MAX_BITS), dtype=torch.uint8).pin_memory()
+        h_nbits = torch.zeros((S, 1), dtype=torch.int32).pin_memory()
+        hout = fmrx.Outputs(ptr(h_audio, fmrx.i16p), None, ptr(h_bits, fmrx.u8p), ptr(h_nbits, fmrx.i32p), None, None)
+        with fmrx.Batch(S, mode=0, profile=1, max_blocks=1) as rx:
+            acc = []
+            for k in range(steps):
+                h_iq.copy_(h_all[:, k * 307200:(k + 1) * 307200])
+                if name == "submit":
+                    rx.wait(rx.submit(h_iq.data_ptr(), 1, hout))
+                else:
+                    rx.process_into(h_iq.data_ptr(), 1, hout)
+                acc.append((h_audio.numpy().copy(), h_bits.numpy().copy(), h_nbits.numpy().copy()))
+            results[name] = acc
+    for k in range(steps):
+        a, b, n = results["device"][k]
+        assert (a[:H] == a[H:]).all() and (b[:H] == b[H:]).all() and (n[:H] == n[H:]).all(), f"step {k}: replicated stations diverged"
+        for other in ("submit", "process"):
+            a2, b2, n2 = results[other][k]
+            assert (a == a2).all() and (n == n2).all(), f"step {k}: {other} differs from the device-resident path"
+            assert all((b[s, 0, :n[s, 0]] == b2[s, 0, :n[s, 0]]).all() for s in range(0, S, 97)), f"step {k}: {other} bits"
+    for s in (0, 1, 63, 2047, 4095):
+        audio, _, bits, _, _ = Chain(0, 1).run(h_all[s].numpy())
+        got = np.concatenate([results["device"][k][0][s].ravel() for k in range(steps)])
+        assert_bits(got, audio, f"station {s} audio vs oracle")
+        gb = np.concatenate([results["device"][k][1][s, 0, :results["device"][k][2][s, 0]] for k in range(steps)])
+        assert np.array_equal(gb, np.concatenate(bits)), f"station {s} bits vs oracle"
