@@ -283,3 +283,43 @@ def test_full_batch_4096_three_entry_points_agree():
         assert_bits(got, audio, f"station {s} audio vs oracle")
         gb = np.concatenate([results["device"][k][1][s, 0, :results["device"][k][2][s, 0]] for k in range(steps)])
         assert np.array_equal(gb, np.concatenate(bits)), f"station {s} bits vs oracle"
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_noise_input_audio_stays_bit_exact(mode):
+    """White-noise bytes instead of a broadcast: the discriminator's zero-denominator branch, an unlocked PLL wandering
+    through the +-pi seam and the libm redo path of the fast PLL step all get exercised; the audio path must still be
+    bit-identical to the oracle (the RDS path is fused-multiply-add and only has to agree on decisions with margins,
+    which noise does not have, so it is not compared here)."""
+    S, B = 6, 3
+    rng = np.random.default_rng(100 + mode)
+    raw = rng.integers(0, 256, (S, B * 307200), dtype=np.uint8)
+    raw[1, :307200] = 128                      # a silent first block (exact zeros, then noise)
+    raw[2, 100000:100000 + 4000] = 0           # a burst of full-scale negative samples
+    with fmrx.Batch(S, mode=mode, profile=1, max_blocks=B) as rx:
+        res = rx.process(raw, want_float=True)
+    for s in range(S):
+        audio, cap, _, _, _ = Chain(mode, 1).run(raw[s], taps=("audio_f",))
+        assert_bits(res["audio_f"][s], np.stack(cap["audio_f"]), f"mode {mode} stream {s} float audio")
+        assert_bits(res["audio"][s].ravel(), audio, f"mode {mode} stream {s} int16")
+
+
+def test_long_run_fifty_blocks():
+    """3.2 s of signal (parity runs <= ~50 blocks because the reference's fp32 oscillator argument degrades): two
+    stations, one block per call, audio bit-exact and RDS bits / sync events / stderr text equal to the oracle throughout."""
+    S, B = 2, 50
+    raw = np.stack([synth.synth_station(s, B, 0) for s in (5, 70)])
+    audio, bits, events, text = [[] for _ in range(S)], [[] for _ in range(S)], [[] for _ in range(S)], ["", ""]
+    with fmrx.Batch(S, mode=0, profile=1, max_blocks=1) as rx:
+        for b in range(B):
+            res = rx.process(raw[:, b * 307200:(b + 1) * 307200])
+            for s in range(S):
+                audio[s].append(res["audio"][s, 0])
+                bits[s].append(res["rds_bits"][s, 0, :res["rds_n_bits"][s, 0]])
+                events[s] += [tuple(int(v) for v in e) for e in res["rds_events"][s, 0, :res["rds_n_events"][s, 0]]]
+                text[s] += rx.rds_text(res, s)
+    for s in range(S):
+        a, _, bt, ev, tx = Chain(0, 1).run(raw[s])
+        assert_bits(np.concatenate(audio[s]), a, f"station {s} audio over 50 blocks")
+        assert np.array_equal(np.concatenate(bits[s]), np.concatenate(bt)), f"station {s} bits"
+        assert events[s] == ev and text[s] == tx, f"station {s} sync events"
