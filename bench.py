@@ -40,12 +40,15 @@ STAGE_MACS = {
     "frontend": (NIF * NT * 2, True), "mono": (NAUD * NT, True), "pilot_bpf": (NIF * NT, True), "stereo_bpf": (NIF * NT, True),
     "rds_bpf": (NIF * NT, False), "rds_sq_bpf": (NIF * NT, False), "stereo_lpf": (NAUD * NT, True), "rds_mix_lpf": (NIF * NT, False),
     "rds_resample": (NRDS * NT, False), "rds_rrc": (NRDS * NT, False),
+    # the symbol-rate RDS back end (csrc/fmrx_rdsfast.cu) does the WORK it does, not the reference's 3.4 M MACs: head 1008 + 240 + 34
+    # outputs x 151, 142 interior symbols x 933, state 150 x 301 + 8 x 151
+    "rds_symbols": ((1008 + 240 + 34) * NT + 142 * 933 + 150 * 301 + 8 * NT, False),
 }
 # algorithmic HBM bytes per station-block for the kernel split actually used (u8 in, fp32 intermediates, int16 out)
 STAGE_BYTES = {
     "frontend": BLOCK_BYTES + 4 * NIF, "mono": 4 * NIF + 4 * NAUD, "pilot_bpf": 8 * NIF, "stereo_bpf": 8 * NIF, "rds_bpf": 8 * NIF,
     "rds_sq_bpf": 8 * NIF, "pll": 16 * NIF, "stereo_lpf": 8 * NIF + 4 * NAUD, "combine": 8 * NAUD + 12 * NAUD * 2 // 2, "rds_mix_lpf": 12 * NIF,
-    "rds_resample": 4 * NIF + 4 * NRDS, "rds_rrc": 8 * NRDS, "rds_decode": 4 * NRDS,
+    "rds_resample": 4 * NIF + 4 * NRDS, "rds_rrc": 8 * NRDS, "rds_decode": 4 * NRDS, "rds_symbols": 4 * NIF + 4 * 152,
 }
 
 

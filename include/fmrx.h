@@ -107,7 +107,11 @@ int fmrx_rds_format_block(int block_id, int initial_offset, const fmrx_rds_event
 
 /* ---- the batched receive chain ------------------------------------------------------------------------------ */
 enum { FMRX_PROFILE_BINARY = 0, FMRX_PROFILE_INTENT = 1 };   /* SURVEY App. A */
-enum { FMRX_PATH_AUDIO = 1, FMRX_PATH_RDS = 2 };
+/* FMRX_PATH_RDS_STAGES (with FMRX_PATH_RDS): run the RDS back end stage by stage at full rate, as the reference does --
+ * mixer + 3 kHz LPF, 19/80 resampler, RRC -- so that every intermediate signal exists (FMRX_TAP_RDS_LPF / _RES / _RRC).
+ * Without it (the default) those three filters run as one composite polyphase filter evaluated only at the 152 samples
+ * per block the decoder reads (csrc/fmrx_rdsfast.cu); the RRC tap then holds just those samples. */
+enum { FMRX_PATH_AUDIO = 1, FMRX_PATH_RDS = 2, FMRX_PATH_RDS_STAGES = 4 };
 enum { FMRX_NUMERICS_REFERENCE = 0, FMRX_NUMERICS_FMA = 1 }; /* audio-path FIR rounding, see `exact` above */
 
 typedef struct {
@@ -180,7 +184,7 @@ int fmrx_batch_tap(fmrx_batch *, int which, float *dst);
 enum {
     FMRX_STAGE_FRONTEND = 0, FMRX_STAGE_MONO, FMRX_STAGE_PILOT_BPF, FMRX_STAGE_STEREO_BPF, FMRX_STAGE_RDS_BPF,
     FMRX_STAGE_RDS_SQ_BPF, FMRX_STAGE_PLL, FMRX_STAGE_STEREO_LPF, FMRX_STAGE_COMBINE, FMRX_STAGE_RDS_MIX_LPF,
-    FMRX_STAGE_RDS_RESAMPLE, FMRX_STAGE_RDS_RRC, FMRX_STAGE_RDS_DECODE, FMRX_STAGE_COUNT
+    FMRX_STAGE_RDS_RESAMPLE, FMRX_STAGE_RDS_RRC, FMRX_STAGE_RDS_DECODE, FMRX_STAGE_RDS_SYMBOLS, FMRX_STAGE_COUNT
 };
 int fmrx_batch_profile(fmrx_batch *, int enable); /* 0 off, 1 serialised per-stage timing, 2 timeline: keep the pipeline */
 /* start / end of every bracket recorded since profiling was enabled, in ms after the first bracket's start; returns the

@@ -273,6 +273,9 @@ struct fmrx_batch {
     fmrx_config cfg{};
     int S = 0, NB = 0, n_audio = 0, nzi_a = 0, audio_taps = 0, up = 1, decim_a = 5, mult = 1;
     bool audio_on = false, rds_on = false, exact = true;
+    bool rds_fast = false;  // RDS back end at symbol rate (fmrx_rdsfast.cu) instead of stage by stage
+    float *d_W = nullptr, *d_G = nullptr, *d_h2p = nullptr;
+    int32_t *d_off = nullptr;
     long long block_id = 0;  // blocks consumed per stream so far
     int last_blocks = 0;
     long long launches = 0;
@@ -489,13 +492,23 @@ int enqueue_chain(fmrx_batch *b, const uint8_t *iq, long long ld_iq, int s0, int
     }
     // ---- rds_thread after the PLL (:404-411) and frame_thread
     if (b->rds_on) {
-        { STAGE(FMRX_STAGE_RDS_MIX_LPF); LAUNCH(fir(IF2(b->rmixed), nullptr, IF(b->rlpf), b->zi_lpf + (long long)s0 * kHist, kHist, b->h_lpf3k, ldif, ldif, NIF, 1, SRC_PROD_HALF, 0, nblk)); }
-        ResampleJob r{};
-        r.x = IF(b->rlpf); r.y = RD(b->rres); r.zi = b->zi_anti + (long long)s0 * (kTaps * 19 - 1); r.h = b->d_h_anti; r.h_host = b->h_anti.data(); r.ldx = ldif; r.ldy = ldr;
-        r.n = NIF; r.n_ref = NIF + 1; r.ny = NRDS; r.n_blocks = nblk; r.n_streams = ns; r.ntaps = kTaps * 19; r.nzi = kTaps * 19 - 1;
-        r.decim = 80; r.up = 19; r.gain_up = 1; r.exact = 0;
-        { STAGE(FMRX_STAGE_RDS_RESAMPLE); LAUNCH(launch_resample(r, st)); }
-        { STAGE(FMRX_STAGE_RDS_RRC); LAUNCH(fir(RD(b->rres), nullptr, RD(b->rrrc), b->zi_rrc + (long long)s0 * kHist, kHist, b->h_rrc, ldr, ldr, NRDS, 1, SRC_PLAIN, 0, nblk)); }
+        if (b->rds_fast) {
+            RdsFastJob q{};
+            q.p = IF2(b->rmixed); q.rrc = RD(b->rrrc); q.zi_lpf = b->zi_lpf + (long long)s0 * kHist; q.zi_anti = b->zi_anti + (long long)s0 * (kTaps * 19 - 1);
+            q.zi_rrc = b->zi_rrc + (long long)s0 * kHist; q.h1 = b->h_lpf3k; q.hr = b->h_rrc; q.h2p = b->d_h2p; q.W = b->d_W; q.G = b->d_G;
+            q.off_state = b->dec_st + (long long)s0 * FMRX_RDS_STATE_WORDS + 1; q.off_state_stride = FMRX_RDS_STATE_WORDS; q.off_scratch = b->d_off + s0;
+            q.ld = ldif; q.ldr = ldr; q.n_streams = ns; q.n_blocks = nblk; q.first_block_is_zero = b->block_id == 0; q.nzi_anti = kTaps * 19 - 1;
+            STAGE(FMRX_STAGE_RDS_SYMBOLS);
+            LAUNCH(launch_rds_fast(q, st));
+        } else {
+            { STAGE(FMRX_STAGE_RDS_MIX_LPF); LAUNCH(fir(IF2(b->rmixed), nullptr, IF(b->rlpf), b->zi_lpf + (long long)s0 * kHist, kHist, b->h_lpf3k, ldif, ldif, NIF, 1, SRC_PROD_HALF, 0, nblk)); }
+            ResampleJob r{};
+            r.x = IF(b->rlpf); r.y = RD(b->rres); r.zi = b->zi_anti + (long long)s0 * (kTaps * 19 - 1); r.h = b->d_h_anti; r.h_host = b->h_anti.data(); r.ldx = ldif; r.ldy = ldr;
+            r.n = NIF; r.n_ref = NIF + 1; r.ny = NRDS; r.n_blocks = nblk; r.n_streams = ns; r.ntaps = kTaps * 19; r.nzi = kTaps * 19 - 1;
+            r.decim = 80; r.up = 19; r.gain_up = 1; r.exact = 0;
+            { STAGE(FMRX_STAGE_RDS_RESAMPLE); LAUNCH(launch_resample(r, st)); }
+            { STAGE(FMRX_STAGE_RDS_RRC); LAUNCH(fir(RD(b->rres), nullptr, RD(b->rrrc), b->zi_rrc + (long long)s0 * kHist, kHist, b->h_rrc, ldr, ldr, NRDS, 1, SRC_PLAIN, 0, nblk)); }
+        }
         STAGE(FMRX_STAGE_RDS_DECODE);
         LAUNCH(launch_rds_decode(RD(b->rrrc), ldr, ns, nblk, NRDS, b->bits + (long long)s0 * nblk * FMRX_MAX_BITS, b->nbits + (long long)s0 * nblk,
                                  b->ev + (long long)s0 * nblk * FMRX_MAX_EVENTS, b->nev + (long long)s0 * nblk, b->dec_st + (long long)s0 * FMRX_RDS_STATE_WORDS, st));
@@ -544,6 +557,7 @@ int fmrx_batch_create(const fmrx_config *cfg, fmrx_batch **out) {
     const int paths = cfg->paths ? cfg->paths : (FMRX_PATH_AUDIO | FMRX_PATH_RDS);
     b->audio_on = (paths & FMRX_PATH_AUDIO) != 0;
     b->rds_on = (paths & FMRX_PATH_RDS) != 0 && cfg->mode == 0;  // src/fm_radio.cpp:324,446
+    b->rds_fast = b->rds_on && !(paths & FMRX_PATH_RDS_STAGES);
     b->exact = cfg->numerics == FMRX_NUMERICS_REFERENCE;
     // ---- constants of the thread bodies
     const float rf_Fs = cfg->mode == 1 ? 2500000.0f : 2400000.0f;  // :36-37
@@ -600,6 +614,12 @@ int fmrx_batch_create(const fmrx_config *cfg, fmrx_batch **out) {
         CU(b->dalloc(b->rbpf, kSets * S * NB * NIF)); CU(b->dalloc(b->rsq, kSets * S * NB * NIF)); CU(b->dalloc(b->rnco, kSets * S * NB * NIF)); CU(b->dalloc(b->rmixed, kSets * S * NB * NIF)); CU(b->dalloc(b->rlpf, S * NB * NIF));
         CU(b->dalloc(b->rres, S * NB * NRDS)); CU(b->dalloc(b->rrrc, S * NB * NRDS));
         CU(b->dalloc(b->bits, S * NB * FMRX_MAX_BITS)); CU(b->dalloc(b->nbits, S * NB)); CU(b->dalloc(b->nev, S * NB)); CU(b->dalloc(b->ev, S * NB * FMRX_MAX_EVENTS));
+        if (b->rds_fast) {
+            CU((cudaError_t)fmrx::rds_fast_tables(b->h_lpf3k, b->h_anti.data(), b->h_rrc, &b->d_W, &b->d_G, &b->d_h2p));
+            b->allocs.push_back(b->d_W); b->allocs.push_back(b->d_G); b->allocs.push_back(b->d_h2p);
+            CU(b->dalloc(b->d_off, S));
+            CU(cudaMemset(b->rrrc, 0, S * NB * NRDS * sizeof(float)));  // only the decoder's positions are ever written
+        }
         CU(cudaMemset(b->bits, 0, S * NB * FMRX_MAX_BITS));
         CU(cudaMemset(b->ev, 0, S * NB * FMRX_MAX_EVENTS * sizeof(fmrx_rds_event)));
     }

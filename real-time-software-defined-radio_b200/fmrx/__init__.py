@@ -28,12 +28,12 @@ MAX_EVENTS = 96
 MAX_BITS = 80
 RDS_STATE_WORDS = 160
 PROFILE_BINARY, PROFILE_INTENT = 0, 1
-PATH_AUDIO, PATH_RDS = 1, 2
+PATH_AUDIO, PATH_RDS, PATH_RDS_STAGES = 1, 2, 4
 NUMERICS_REFERENCE, NUMERICS_FMA = 0, 1
 TAPS = dict(demod=0, mono=1, pilot=2, nco=3, stereo_bpf=4, stereo=5, rds_bpf=6, rds_sq=7, rds_nco=8, rds_lpf=9, rds_res=10, rds_rrc=11)
 
 STAGES = ("frontend", "mono", "pilot_bpf", "stereo_bpf", "rds_bpf", "rds_sq_bpf", "pll", "stereo_lpf", "combine", "rds_mix_lpf",
-          "rds_resample", "rds_rrc", "rds_decode")
+          "rds_resample", "rds_rrc", "rds_decode", "rds_symbols")
 
 F = np.float32
 fp = C.POINTER(C.c_float)

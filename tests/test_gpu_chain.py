@@ -24,12 +24,18 @@ NAMES = {0: "binary", 1: "intent"}
 
 @pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("profile", [0, 1])
-def test_chain_golden(golden, mode, profile):
+@pytest.mark.parametrize("rds_stages", [True, False])
+def test_chain_golden(golden, mode, profile, rds_stages):
+    """rds_stages: the RDS back end stage by stage (every tap exists and is compared) or at symbol rate (the default: only
+    the samples the decoder reads exist; they are compared at those positions, and bits / events / text as always)."""
+    if mode == 1 and not rds_stages:
+        pytest.skip("mode 1 has no RDS path")
     g = golden[f"chain_mode{mode}"]
     nblk, name = int(g["nblk"]), NAMES[profile]
     raw = synth.synth_iq(nblk, mode, seed=int(g["seed"]))
     assert sha(raw) == str(g["input_sha256"])
-    with fmrx.Batch(1, mode=mode, profile=profile, max_blocks=1) as rx:
+    paths = fmrx.PATH_AUDIO | fmrx.PATH_RDS | (fmrx.PATH_RDS_STAGES if rds_stages else 0)
+    with fmrx.Batch(1, mode=mode, profile=profile, max_blocks=1, paths=paths) as rx:
         audio, text = [], ""
         for b in range(nblk):
             res = rx.process(raw[b * 307200:(b + 1) * 307200], want_float=True)
@@ -42,7 +48,15 @@ def test_chain_golden(golden, mode, profile):
                 key = f"{name}_{t}_{b}"
                 if key in g.files:
                     assert_bits(rx.tap(t)[0, 0][::LONG_STRIDE], g[key], key)
-            if mode == 0:
+            if mode == 0 and not rds_stages:
+                off = int(rx.rds_offsets()[0])
+                pos = off + 24 * np.arange(152)
+                got, ref = rx.tap("rds_rrc")[0, 0][pos], g[f"{name}_rds_rrc_{b}"][pos]
+                err = float(np.sqrt(np.mean((got - ref) ** 2)) / np.sqrt(np.mean(ref ** 2)))
+                print(f"mode {mode} {name} block {b} symbols (symbol-rate path): rel-rms {err:.3g}")
+                assert err < TOL_AFTER_RDS_PLL, f"symbols block {b}"
+                text += rx.rds_text(res)
+            if mode == 0 and rds_stages:
                 for t, tol in (("rds_bpf", TOL), ("rds_sq", TOL), ("rds_lpf", TOL_AFTER_RDS_PLL), ("rds_res", TOL_AFTER_RDS_PLL)):
                     key = f"{name}_{t}_{b}"
                     if key in g.files:
@@ -323,3 +337,40 @@ def test_long_run_fifty_blocks():
         assert_bits(np.concatenate(audio[s]), a, f"station {s} audio over 50 blocks")
         assert np.array_equal(np.concatenate(bits[s]), np.concatenate(bt)), f"station {s} bits"
         assert events[s] == ev and text[s] == tx, f"station {s} sync events"
+
+
+@pytest.mark.parametrize("nblk", [1, 3])
+def test_rds_symbol_rate_path_equals_staged(nblk):
+    """The symbol-rate RDS back end (one composite polyphase filter at the 152 samples per block the decoder reads, block
+    edges restated exactly: csrc/fmrx_rdsfast.cu) against the staged one (mixer LPF -> resampler -> RRC at full rate):
+    same bits, same sync events, symbol values equal to fp32 rounding, over several calls of `nblk` blocks (nblk > 1
+    exercises the in-call block edges, the first call the phase derivation from block 0) and after a checkpoint."""
+    S, calls = 7, 4
+    raw = np.stack([synth.synth_station(s, calls * nblk, 0) for s in range(S)])
+    outs = {}
+    for name, extra in (("staged", fmrx.PATH_RDS_STAGES), ("fast", 0)):
+        with fmrx.Batch(S, mode=0, profile=1, max_blocks=nblk, paths=fmrx.PATH_AUDIO | fmrx.PATH_RDS | extra) as rx:
+            acc = []
+            for c in range(calls):
+                if c == 2:  # checkpoint / resume in the middle: the carried state of either path must be self-consistent
+                    blob = rx.get_state()
+                    rx.reset()
+                    rx.set_state(blob)
+                res = rx.process(raw[:, c * nblk * 307200:(c + 1) * nblk * 307200])
+                off = rx.rds_offsets()
+                rrc = rx.tap("rds_rrc")
+                sym = np.stack([rrc[s][:, off[s] + 24 * np.arange(152)] for s in range(S)])
+                acc.append((res["rds_bits"].copy(), res["rds_n_bits"].copy(), res["rds_events"].copy(), res["rds_n_events"].copy(), sym, off.copy(), res["audio"].copy()))
+            outs[name] = acc
+    for c in range(calls):
+        bs, ns, es, nes, syms, offs, aus = outs["staged"][c]
+        bf, nf, ef, nef, symf, offf, auf = outs["fast"][c]
+        assert np.array_equal(offs, offf) and np.array_equal(ns, nf) and np.array_equal(nes, nef) and np.array_equal(aus, auf)
+        for s in range(S):
+            for b in range(nblk):
+                assert np.array_equal(bs[s, b, :ns[s, b]], bf[s, b, :nf[s, b]]), f"call {c} station {s} block {b}: bits"
+                assert np.array_equal(es[s, b, :nes[s, b]], ef[s, b, :nef[s, b]]), f"call {c} station {s} block {b}: events"
+        err = float(np.sqrt(np.mean((symf - syms) ** 2)) / np.sqrt(np.mean(syms ** 2)))
+        worst = float(np.max(np.abs(symf - syms)) / np.sqrt(np.mean(syms ** 2)))
+        print(f"nblk {nblk} call {c}: symbols rel-rms {err:.3g}, worst {worst:.3g}")
+        assert err < 2e-6 and worst < 2e-5
