@@ -18,8 +18,8 @@
 // p with the composite taps.
 //
 //   rds_head_kernel    one CTA per (station, block): X window -> rlpf[0..1008) -> rres[0..240) -> rrc at the head symbols
-//   rds_symbol_kernel  one CTA per (station, block), one warp per filter phase: the 142 interior symbols
-//   rds_tail_kernel    one CTA per station: new carried state from the last block
+//   rds_symbol_kernel  one CTA per (station, block), one warp per filter phase: the 142 interior symbols; for the last
+//                      block of a call also the new carried state, from the same staged samples
 // The decoder kernel is unchanged: the symbols are written at their positions 24k + off of the (otherwise untouched) RRC
 // buffer.  FMRX_PATH_RDS_STAGES selects the staged kernels instead (every stage materialised, debug taps available).
 #include <cuda_runtime.h>
@@ -38,7 +38,7 @@ constexpr int HEAD_SYMS = 10;                 // symbols 0..9 (rrc index < 240) 
 constexpr int NRH = HEAD_SYMS * SPS;          // 240 resampler outputs restated by the head kernel
 constexpr int NLH = 1008;                     // mixer-LPF outputs they need: floor(80*239/19) = 1006
 constexpr int WLEN = 960;                     // composite taps per phase, zero padded (support 933)
-constexpr int GLEN = 304;                     // mixer-LPF x resampler composite per phase (support 301)
+constexpr int GLEN = 320;                     // mixer-LPF x resampler composite per phase (support 301), zero padded to 10 x 32
 constexpr int ZA_LO = 143, ZA_N = 8;          // entries of the resampler state its history map can reach: (2867 - c)/19, c <= 150
 
 __host__ __device__ constexpr int qof(int o) { return (D * o) / U; }
@@ -67,8 +67,7 @@ __device__ __forceinline__ float rres_interior_warp(const float *pb, const float
     const float *x = pb + qof(o) - lane;
     float acc = 0.0f;
 #pragma unroll
-    for (int it = 0; it < (GLEN + 31) / 32; ++it)
-        if (32 * it + lane < GLEN) acc = fmaf(__ldg(g + 32 * it), __ldg(x - 32 * it), acc);  // G is zero beyond its 301 taps
+    for (int it = 0; it < GLEN / 32; ++it) acc = fmaf(__ldg(g + 32 * it), __ldg(x - 32 * it), acc);  // G is zero beyond its 301 taps
 #pragma unroll
     for (int sh = 16; sh > 0; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
     return acc;
@@ -143,17 +142,21 @@ __global__ void __launch_bounds__(256) rds_head_kernel(const FastDev a, const __
         const int q0 = qof(t);
         const float4 *hp = reinterpret_cast<const float4 *>(a.h2p + phof(t) * 152);  // phase-major copy: hp[c] = h2[ph + 19c]
         float acc = 0.0f;
+        if (q0 >= TPP - 1) {  // every tap in-block (all but the first 36 outputs): no case analysis in the loop
+            const float *r = rl + q0;
 #pragma unroll 2
-        for (int c4 = 0; c4 < 152 / 4; ++c4) {
-            const float4 h = __ldg(hp + c4);
-            const float hv[4] = {h.x, h.y, h.z, h.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int c = 4 * c4 + e;
-                if (c < TPP) {
-                    const float v = c <= q0 ? rl[q0 - c] : a8[(a.nzi_anti - 1 - c) / U - ZA_LO];
-                    acc = fmaf(v, hv[e], acc);
-                }
+            for (int c4 = 0; c4 < 152 / 4; ++c4) {
+                const float4 h = __ldg(hp + c4);
+                acc = fmaf(r[-4 * c4], h.x, acc);
+                acc = fmaf(r[-4 * c4 - 1], h.y, acc);
+                acc = fmaf(r[-4 * c4 - 2], h.z, acc);
+                if (c4 < 37) acc = fmaf(r[-4 * c4 - 3], h.w, acc);  // tap 151 does not exist
+            }
+        } else {
+            const float *hs = reinterpret_cast<const float *>(hp);
+            for (int c = 0; c < TPP; ++c) {
+                const float v = c <= q0 ? rl[q0 - c] : a8[(a.nzi_anti - 1 - c) / U - ZA_LO];
+                acc = fmaf(v, __ldg(hs + c), acc);
             }
         }
         rh[kHist + t] = __fmul_rn(acc, (float)U);
@@ -187,7 +190,7 @@ __global__ void __launch_bounds__(256) rds_head_kernel(const FastDev a, const __
 // interior symbols: the block's p is staged once in shared memory (asynchronous 16-byte copies); warp w handles filter
 // phases w, w+8, w+16, a phase's taps staying in registers (30 per lane) for its 7-8 symbols; each symbol is 30 conflict-free
 // LDS + FFMA per lane and a warp reduction
-__global__ void __launch_bounds__(256) rds_symbol_kernel(const FastDev a) {
+__global__ void __launch_bounds__(256) rds_symbol_kernel(const FastDev a, const __grid_constant__ Taps151 h1) {
     extern __shared__ __align__(16) float ps[];  // NIF floats
     const int b = blockIdx.x, s = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float *pb = a.p + (long long)s * a.ld + (long long)b * NIF;
@@ -220,24 +223,34 @@ __global__ void __launch_bounds__(256) rds_symbol_kernel(const FastDev a) {
             if (lane == 0) out[i] = acc;
         }
     }
-}
-
-// new carried state from the last block of the call
-__global__ void __launch_bounds__(256) rds_tail_kernel(const FastDev a, const __grid_constant__ Taps151 h1) {
-    const int s = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const float *pb = a.p + (long long)s * a.ld + (long long)(a.n_blocks - 1) * NIF;
-    if (t < kHist) a.zi_lpf[(long long)s * kHist + t] = pb[NIF - kHist + t];                      // src/filter.cpp:398-400 at its call site (Q8)
-    for (int i = warp; i < kHist; i += 8) {                                                        // last 150 resampler outputs, one late (Q1)
-        const float v = rres_interior_warp(pb, a.G, NRDS - kHist - 1 + i, lane);
-        if (lane == 0) a.zi_rrc[(long long)s * kHist + i] = v;
-    }
+    if (b != a.n_blocks - 1) return;
+    // ---- the last block of the call also leaves the carried state, from the same staged samples
+    if (threadIdx.x < kHist) a.zi_lpf[(long long)s * kHist + threadIdx.x] = ps[NIF - kHist + threadIdx.x];  // src/filter.cpp:398-400 at its call site (Q8)
     {   // the eight reachable entries of the resampler state: rlpf[12492 + 143 + e], one warp each
-        const float *x = pb + (NIF + 1 - a.nzi_anti - 1) + ZA_LO + warp;
+        const float *x = ps + (NIF + 1 - a.nzi_anti - 1) + ZA_LO + warp;
         float acc = 0.0f;
         for (int k = lane; k < kTaps; k += 32) acc = fmaf(__fmul_rn(x[-k], 2.0f), h1.h[k], acc);
 #pragma unroll
         for (int sh = 16; sh > 0; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
         if (lane == 0) a.zi_anti[(long long)s * a.nzi_anti + ZA_LO + warp] = acc;
+    }
+    // the last 150 resampler outputs, one late (Q1): rres[3497 + i] = sum_d G[ph][d] p[q - d]; a warp takes a phase, keeps its
+    // composite taps in registers and walks the 7-8 outputs of that phase (ph(o) = 4o mod 19, so o = 5 ph mod 19)
+    for (int ph = warp; ph < U; ph += 8) {
+        float g[GLEN / 32];
+#pragma unroll
+        for (int it = 0; it < GLEN / 32; ++it) g[it] = __ldg(a.G + ph * GLEN + 32 * it + lane);
+        constexpr int O0 = NRDS - kHist - 1;
+        int o = O0 + (((5 * ph) % U - O0 % U) % U + U) % U;
+        for (; o < O0 + kHist; o += U) {
+            const float *x = ps + qof(o) - lane;
+            float acc = 0.0f;
+#pragma unroll
+            for (int it = 0; it < GLEN / 32; ++it) acc = fmaf(g[it], x[-32 * it], acc);
+#pragma unroll
+            for (int sh = 16; sh > 0; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
+            if (lane == 0) a.zi_rrc[(long long)s * kHist + (o - O0)] = acc;
+        }
     }
 }
 
@@ -309,9 +322,8 @@ int launch_rds_fast(const RdsFastJob &j, fmrx_stream_t st) {
         if (cudaError_t e0 = cudaFuncSetAttribute(rds_symbol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NIF * (int)sizeof(float))) return (int)e0;
         attr_set = true;
     }
-    rds_symbol_kernel<<<dim3(j.n_blocks, j.n_streams), 256, NIF * sizeof(float), st>>>(d);
-    rds_tail_kernel<<<j.n_streams, 256, 0, st>>>(d, h1);
-    launch_counter() += 3;
+    rds_symbol_kernel<<<dim3(j.n_blocks, j.n_streams), 256, NIF * sizeof(float), st>>>(d, h1);
+    launch_counter() += 2;
     return (int)cudaGetLastError();
 }
 
