@@ -46,7 +46,7 @@ size_t read_fully(uint8_t *dst, size_t n) {
 
 int main(int argc, char *argv[]) {
     int mode = 0, profile = FMRX_PROFILE_BINARY, blocks = 1, device = 0;
-    bool quiet = false;
+    bool quiet = false, rds_info = false;
     int pos = 1;
     std::cerr << ((argc >= 2 && argv[1][0] != '-') ? 2 : 1) << std::endl;  // the reference prints argc first (:738); options are not counted
     if (argc >= 2 && argv[1][0] != '-') {
@@ -64,6 +64,7 @@ int main(int argc, char *argv[]) {
         else if (a == "--blocks") blocks = std::max(1, atoi(next()));
         else if (a == "--device") device = atoi(next());
         else if (a == "--quiet") quiet = true;
+        else if (a == "--rds-info") rds_info = true;  // extension: decode the RDS groups (PI, PS, RadioText) and report them at the end
         else { std::cerr << "Usage " << argv[0] << std::endl; return 1; }  // :762
     }
     std::cerr << "Operating in mode " << mode << std::endl;            // :741,:756
@@ -85,6 +86,10 @@ int main(int argc, char *argv[]) {
     fmrx_pinned_alloc((void **)&audio, (size_t)blocks * 2 * na * sizeof(int16_t));
     std::vector<fmrx_rds_event> ev((size_t)blocks * FMRX_MAX_EVENTS);
     std::vector<int32_t> nev(blocks);
+    std::vector<uint8_t> bits((size_t)blocks * FMRX_MAX_BITS);
+    std::vector<int32_t> nbits(blocks);
+    fmrx_rds_app *app = nullptr;
+    if (rds_info && mode == 0 && fmrx_rds_app_create(1, &app) != FMRX_OK) { std::cerr << "fm_radio: " << fmrx_last_error() << std::endl; return 2; }
 
     Ring ring;
     std::thread reader([&] {
@@ -129,12 +134,14 @@ int main(int argc, char *argv[]) {
         fmrx_outputs out{};
         out.audio = audio;
         if (mode == 0) { out.rds_events = ev.data(); out.rds_n_events = nev.data(); }
+        if (app) { out.rds_bits = bits.data(); out.rds_n_bits = nbits.data(); }
         if (fmrx_batch_process(rx, slots[i], nb, &out) != FMRX_OK) {
             std::cerr << "fm_radio: " << fmrx_last_error() << std::endl;
             rc = 2;
             break;
         }
         fwrite(audio, sizeof(int16_t), (size_t)nb * 2 * na, stdout);  // :302
+        if (app) fmrx_rds_app_feed(app, bits.data(), nbits.data(), nb, nullptr, 0, nullptr);
         if (mode == 0 && !quiet) {
             if (block_id == 0) fmrx_batch_rds_offsets(rx, offset.data());
             char text[8192];
@@ -156,6 +163,16 @@ int main(int argc, char *argv[]) {
     for (auto &s : slots) fmrx_pinned_free(s);
     fmrx_pinned_free(audio);
     fmrx_batch_destroy(rx);
+    if (app) {
+        fmrx_rds_station st;
+        if (fmrx_rds_app_station(app, 0, &st) == FMRX_OK) {
+            char line[256];
+            snprintf(line, sizeof(line), "RDS: PI %04X PTY %d TP %d PS \"%s\" RT \"%s\" groups %u blocks ok/corrected/bad %u/%u/%u", st.pi < 0 ? 0 : st.pi, st.pty, st.tp, st.ps,
+                     st.rt, st.groups, st.blocks_ok, st.blocks_corrected, st.blocks_bad);
+            std::cerr << line << std::endl;
+        }
+        fmrx_rds_app_destroy(app);
+    }
     if (rc == 0) std::cerr << "Run: gnuplot -e 'set terminal png size 1024,768' example.gnuplot > ../data/example.png" << std::endl;  // :795
     return rc;
 }

@@ -45,3 +45,12 @@ def test_cli_intent_profile(golden):
     audio, err, rc = run_cli(["--profile", "intent", "--quiet"], raw)
     assert rc == 0 and "Syndrome" not in err
     assert_bits(audio, g["intent_audio"], "intent profile stdout")
+
+
+def test_cli_rds_info_reports_the_programme():
+    """extension beyond the reference CLI: --rds-info runs the RDS application layer on the decoded bits"""
+    raw = synth.synth_iq(40, 0, seed=1, rds_payload=lambda n: synth.rds_group_bits(0xBEEF, "CLI TEST", "radiotext through the executable", pty=3, n_bits=n))
+    _, err, rc = run_cli(["--profile", "intent", "--quiet", "--rds-info", "--blocks", "4"], raw)
+    assert rc == 0, err
+    line = [l for l in err.splitlines() if l.startswith("RDS: ")]
+    assert len(line) == 1 and 'PI BEEF PTY 3 TP 0 PS "CLI TEST" RT "radiotext through the executable"' in line[0], err
