@@ -23,6 +23,9 @@
 // roundings, and FFMA2 has the same lane throughput as FFMA anyway (measured, bench.py peak kinds 0 and 2).
 #include <cuda_runtime.h>
 
+#include <cstdint>
+#include <cstdlib>
+
 #include "fmrx_internal.h"
 
 namespace fmrx {
@@ -495,6 +498,145 @@ __global__ void __launch_bounds__(64, 8) frontend_stream_kernel(const IqDev a, c
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Second form of the streaming front end (the default; the kernel above is kept for unaligned / ragged inputs and as
+// FMRX_FRONTEND=1).  ncu on the first form (profiles/r2j_kernels.md): 0.6 non-FFMA2 instructions per FFMA2 -- ptxas
+// fetched all 151 taps at the top of every two-row iteration (78 uniform + 60 vector registers), spilled ~28 live
+// values around the tap loop to make room, kept the input group in local memory, and carried a second copy of the loop
+// (the per-sample path for history / edge rows) whose call sites pin more registers.  This form removes all three:
+//   * taps live in shared memory and are fetched per ROW with explicit 128-bit loads (40 LDS.128 per 302 FFMA2,
+//     broadcast, conflict-free), 16 registers at a time.  The reference's summation order forces rows outer / samples
+//     inner, so a tap cannot be reused across rows without holding all 151; reloading is the cheap side of that trade.
+//   * one iteration walks a whole 80-byte group (four rows): no half-group selects, the five 128-bit loads of the next
+//     group refill the registers of the current one as soon as a row has consumed them (>= 300 FFMA2 ahead of use).
+//   * no history path: the hot kernel treats everything before the block as silence and does not emit outputs 0..15 of
+//     a block (the only ones whose support reaches the history); frontend_edge_kernel computes those 16 from scratch
+//     (in-block samples and history, reference order) -- 0.1 % of the MACs.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int SLOTS4 = 19;
+constexpr int EDGE_OUT = 16;  // outputs per block left to the edge kernel: n < 15 touch the history, 15 keeps quads whole
+
+__device__ __forceinline__ float4 lds_f4(unsigned addr) {
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+template <bool EXACT>
+__global__ void __launch_bounds__(64, 8) frontend_stream4_kernel(const IqDev a, const __grid_constant__ RowTaps taps, int L, int segs, long long total, const Exact2 ex) {
+    __shared__ __align__(16) float staps[4 * 160];          // one copy per row of the group: identical loads from one address would be merged
+    for (int i = threadIdx.x; i < 4 * 160; i += 64) staps[i] = taps.t[(i % 160) / 16][i % 16];
+    __syncthreads();
+    const long long gid = blockIdx.x * 64LL + threadIdx.x;
+    if (gid >= total) return;
+    const int g = (int)(gid % segs);
+    const long long sb = gid / segs;
+    const int b = (int)(sb % a.n_blocks), s = (int)(sb / a.n_blocks);
+    const int a0 = g * L;                                   // first output of the run (multiple of 4)
+    const int lo_out = a0 == 0 ? EDGE_OUT : a0;             // first output this thread emits
+    const uint4 *row = reinterpret_cast<const uint4 *>(a.raw + (long long)s * a.ldx + 2LL * b * a.n);
+    const long long ob = (long long)s * a.ldy + (long long)b * a.ny;
+    const unsigned tap_base = (unsigned)__cvta_generic_to_shared(staps);
+
+    float2 bb[SLOTS4];
+#pragma unroll
+    for (int i = 0; i < SLOTS4; ++i) bb[i] = make_float2(0.0f, 0.0f);
+    float2 ycur = make_float2(0.0f, 0.0f);                  // y[rho + 16]: the lowest output of the previous iteration
+
+    // group with top row rho (= 3 mod 4): samples 10*rho-38 .. 10*rho+1 = bytes 20*rho-76 .. 20*rho+3, five uint4;
+    // quad i is word 4i..4i+3, word w = samples (lo + 2w, lo + 2w + 1) as I,Q,I,Q bytes
+    uint4 cur[5];
+    const uint4 silence = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);  // u8 128 = exactly 0.0
+    auto fetch = [&](int rt, int i) -> uint4 {
+        const int q = (5 * rt - 19) / 4 + i;                // (20*rt - 76) / 16, exact: rt = 3 mod 4
+        return q >= 0 ? __ldg(row + q) : silence;           // below the block: only the first run gets there, and nothing it emits depends on it
+    };
+    int rho = a0 + L - 1;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) cur[i] = fetch(rho, i);
+    const int iters = (L + 16) / 4;
+    for (int it = 0; it < iters; ++it, rho -= 4) {
+        const bool more = it + 1 < iters;
+        float2 yo[4];                                       // yo[rr] = y[rho + 15 - rr]
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+            unsigned tb = tap_base + 640 * rr;
+            asm volatile("" : "+r"(tb));                    // the taps are re-read per row: do not let them be kept (151 registers) or hoisted
+            const unsigned *cw = reinterpret_cast<const unsigned *>(cur);
+#pragma unroll
+            for (int j = 0; j < 10; ++j) {
+                const int pos = 39 - 10 * rr - j;           // sample index inside the group
+                const unsigned u = cw[pos >> 1];
+                const float2 rawf = (pos & 1) ? make_float2(__uint_as_float(__byte_perm(u, 0x4B000000u, 0x7442)), __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7443)))
+                                              : make_float2(__uint_as_float(__byte_perm(u, 0x4B000000u, 0x7440)), __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7441)));
+                const float2 smp = __ffma2_rn(rawf, make_float2(0.0078125f, 0.0078125f), make_float2(-65537.0f, -65537.0f));  // (v - 128) / 128, exact
+                float t[16];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 v = lds_f4(tb + (64 * j + 16 * q));
+                    t[4 * q] = v.x; t[4 * q + 1] = v.y; t[4 * q + 2] = v.z; t[4 * q + 3] = v.w;
+                }
+#pragma unroll
+                for (int sl = 0; sl < 16; ++sl) {
+                    const int k = 10 * sl - 1 + j;
+                    if (k >= 0 && k < kTaps) bb[sl + 3 - rr] = mac2<EXACT>(bb[sl + 3 - rr], smp, t[sl], ex);
+                }
+            }
+            yo[rr] = bb[18 - rr];
+            // this row's quads are consumed: refill them with the next group
+            if (more) {
+                if (rr == 0) cur[4] = fetch(rho - 4, 4);
+                if (rr == 1) cur[3] = fetch(rho - 4, 3);
+                if (rr == 2) cur[2] = fetch(rho - 4, 2);
+                if (rr == 3) { cur[1] = fetch(rho - 4, 1); cur[0] = fetch(rho - 4, 0); }
+            }
+        }
+#pragma unroll
+        for (int i = SLOTS4 - 1; i >= 4; --i) bb[i] = bb[i - 4];
+        bb[0] = bb[1] = bb[2] = bb[3] = make_float2(0.0f, 0.0f);
+
+        // outputs rho+12 .. rho+15 are complete; the aligned quad rho+13 .. rho+16 (ycur = y[rho+16]) can be emitted:
+        // demod[n] pairs y[n] with y[n-1].  Genuine only inside [lo_out, a0 + L).
+        const int q0 = rho + 13;                            // multiple of 4
+        if (q0 >= lo_out && q0 + 4 <= a0 + L) {
+            const float d3 = discriminate(ycur.x, ycur.y, yo[0].x, yo[0].y);
+            const float d2 = discriminate(yo[0].x, yo[0].y, yo[1].x, yo[1].y);
+            const float d1 = discriminate(yo[1].x, yo[1].y, yo[2].x, yo[2].y);
+            const float d0 = discriminate(yo[2].x, yo[2].y, yo[3].x, yo[3].y);
+            *reinterpret_cast<float4 *>(a.demod + ob + q0) = make_float4(d0, d1, d2, d3);
+            if (a.yi) {
+                *reinterpret_cast<float4 *>(a.yi + ob + q0) = make_float4(yo[2].x, yo[1].x, yo[0].x, ycur.x);
+                *reinterpret_cast<float4 *>(a.yq + ob + q0) = make_float4(yo[2].y, yo[1].y, yo[0].y, ycur.y);
+            }
+        }
+        ycur = yo[3];
+    }
+}
+
+// outputs 0 .. EDGE_OUT-1 of every (stream, block), from scratch in the reference's order (taps ascending: in-block
+// samples first, then the history), and their discriminator values; 16 lanes per (stream, block).
+template <bool EXACT>
+__global__ void __launch_bounds__(128) frontend_edge_kernel(const IqDev a, const __grid_constant__ Taps taps, int n_sb) {
+    const int sbi = blockIdx.x * 8 + threadIdx.x / EDGE_OUT, n = threadIdx.x % EDGE_OUT;
+    const bool live = sbi < n_sb;
+    const int b = live ? sbi % a.n_blocks : 0, s = live ? sbi / a.n_blocks : 0;
+    float yi = 0.0f, yq = 0.0f;
+    if (live) {
+#pragma unroll 1
+        for (int k = 0; k < kTaps; ++k) {
+            const float2 v = source_iq<true>(a, s, b, 10 * n - k);
+            yi = mac<EXACT>(yi, v.x, taps.h[k]);
+            yq = mac<EXACT>(yq, v.y, taps.h[k]);
+        }
+    }
+    float pi_ = __shfl_up_sync(0xffffffffu, yi, 1, EDGE_OUT), pq_ = __shfl_up_sync(0xffffffffu, yq, 1, EDGE_OUT);
+    if (n == 0) pi_ = pq_ = 0.0f;                           // block start: the previous sample is zero (Q3)
+    if (!live || n >= a.ny) return;
+    const long long o = (long long)s * a.ldy + (long long)b * a.ny + n;
+    a.demod[o] = discriminate(yi, yq, pi_, pq_);
+    if (a.yi) { a.yi[o] = yi; a.yq[o] = yq; }
+}
+
 template <bool RAW>
 __global__ void iq_state_kernel(const IqDev a) {
     const int s = blockIdx.x, i = threadIdx.x;
@@ -628,7 +770,21 @@ int launch_frontend(const FrontendJob &j, fmrx_stream_t st) {
         }
     const int L = stream_run(d.ny), segs = (d.ny + L - 1) / L;
     const long long total = (long long)segs * j.n_blocks * j.n_streams;
-    frontend_stream_kernel<true><<<(unsigned)((total + 63) / 64), 64, 0, st>>>(d, t, L, segs, total, Exact2{-0.0f, 1.0f});
+    // the group-walk form needs whole runs, whole quads and 16-byte aligned rows; anything else takes the first form
+    static const int forced = [] { const char *v = getenv("FMRX_FRONTEND"); return v ? atoi(v) : 0; }();
+    auto al16 = [](const void *p) { return p == nullptr || ((uintptr_t)p & 15) == 0; };
+    const bool walk4 = forced != 1 && d.n == 10 * d.ny && d.ny % L == 0 && L % 4 == 0 && d.ny >= 32 && al16(d.raw) && d.ldx % 16 == 0 && (2LL * d.n) % 16 == 0 &&
+                       al16(d.demod) && al16(d.yi) && al16(d.yq) && d.ldy % 4 == 0 && d.ny % 4 == 0;
+    if (walk4) {
+        frontend_stream4_kernel<true><<<(unsigned)((total + 63) / 64), 64, 0, st>>>(d, t, L, segs, total, Exact2{-0.0f, 1.0f});
+        cudaError_t e4 = cudaGetLastError();
+        if (e4) return (int)e4;
+        const int n_sb = j.n_blocks * j.n_streams;
+        frontend_edge_kernel<true><<<(n_sb + 7) / 8, 128, 0, st>>>(d, make_taps(j.h), n_sb);
+        launch_counter() += 1;
+    } else {
+        frontend_stream_kernel<true><<<(unsigned)((total + 63) / 64), 64, 0, st>>>(d, t, L, segs, total, Exact2{-0.0f, 1.0f});
+    }
     cudaError_t e = cudaGetLastError();
     if (e) return (int)e;
     iq_state_kernel<true><<<j.n_streams, 160, 0, st>>>(d);

@@ -102,6 +102,29 @@ def test_frontend_fused_vs_oracle(port):
         assert_bits(zi[s], a, "zi_i"); assert_bits(zq[s], b, "zi_q")
 
 
+@pytest.mark.parametrize("n", [30720, 15360 * 10, 30730, 2400])
+def test_frontend_state_carry_and_ragged_sizes(port, n):
+    """Two calls with the state carried between them (non-zero history at the start of the second call), at sizes that
+    take the group-walk kernel + edge kernel (whole runs of whole quads: 30720, the chain's 153600, and 2400 = a single run per block) and a size that takes
+    the first form of the kernel (30730: ny = 3073 has no run length and is not a multiple of 4)."""
+    rng = np.random.default_rng(n)
+    h = fmrx.design_lpf(2.4e6, 1e5, 151)
+    S = 2
+    zi, zq = np.zeros((S, 150), F), np.zeros((S, 150), F)
+    ref = [(np.zeros(150, F), np.zeros(150, F)) for _ in range(S)]
+    for call, nb in enumerate((1, 2)):
+        raw = rng.integers(0, 256, (S, nb, 2 * n), dtype=np.uint8)
+        d, yi, yq = fmrx.frontend(raw, h, zi, zq, want_iq=True)
+        for s in range(S):
+            a, b = ref[s]
+            for k in range(nb):
+                iq = port.unpack(raw[s, k])
+                ri, rq = port.fir_decim_iq(iq[0::2].copy(), iq[1::2].copy(), h, a, b, 10)
+                assert_bits(yi[s, k], ri, f"I call {call} stream {s} block {k}"); assert_bits(yq[s, k], rq, "Q")
+                assert_bits(d[s, k], port.demod(ri, rq), f"demod call {call} stream {s} block {k}")
+            assert_bits(zi[s], a, "zi_i"); assert_bits(zq[s], b, "zi_q")
+
+
 def test_resamplers_golden(golden):
     g = golden["functions"]
     cases = [("res_24_125", "lpf_mono1", 125, 24, False, 0, "res_x"), ("res_19_80", "lpf_anti", 80, 19, True, 0, "res_x"),
