@@ -344,6 +344,19 @@ def run_fmrx_arm(args, rank, world, local_rank):
     e2e_sync_value = units / s_sync / 1e6
     if rank == 0 and not args.no_check:
         assert (hsets[0]["audio"].numpy() != 0).any(), "end-to-end path produced no audio"
+    # what bounds the end-to-end figure: the host->device link.  The same pinned buffer copied alone, timed on the device.
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d_iq.copy_(h_iq[0], non_blocking=True)
+    torch.cuda.synchronize()
+    c0.record()
+    for _ in range(5):
+        d_iq.copy_(h_iq[0], non_blocking=True)
+    c1.record()
+    torch.cuda.synchronize()
+    link_gbs = 5 * h2d / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    link = {"h2d_copy_alone_gbs": round(link_gbs, 1), "h2d_achieved_gbs": round(S * B * BLOCK_BYTES * args.steps / s_e2e / 1e9, 1),
+            "frac_of_link": round(S * B * BLOCK_BYTES * args.steps / s_e2e / 1e9 / link_gbs, 3),
+            "note": "per GPU; the end-to-end path moves 2 bytes per complex sample over PCIe, so the link rate / 2 is its ceiling"}
 
     # ---- the other mode (the metric is per mode): mode 1 = 2.5 Msps, x24 / 125 polyphase audio resamplers, mono + stereo, no RDS
     # (src/fm_radio.cpp:174-180,324); device-resident, same batch size, reported beside the headline in config.mode1
@@ -415,7 +428,7 @@ def run_fmrx_arm(args, rank, world, local_rank):
                    "l2": "input per step %.2f GB >> 126 MB L2, no flush needed" % (S * B * BLOCK_BYTES / 1e9), "input_reuse": "same synthesised block replayed each step, state carried",
                    "synth_seconds": round(t_synth, 2), "parity_spot_check": parity, "rank0_numa_node": numa,
                    "e2e_timer": "host clock around K fmrx_batch_submit calls with fmrx_batch_wait on the previous step (two steps in flight), barrier + synchronize on both sides, max over ranks",
-                   "e2e_sync_call_msps": round(e2e_sync_value, 1), "mode1": mode1},
+                   "e2e_sync_call_msps": round(e2e_sync_value, 1), "e2e_link": link, "mode1": mode1},
         "e2e": {"value": round(e2e_value, 1), "unit": "Msps", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world},  # whole job, like `value`
         "gpu_launches": int(launches),
         "clocks": clocks,

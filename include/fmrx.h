@@ -115,7 +115,9 @@ enum { FMRX_PATH_AUDIO = 1, FMRX_PATH_RDS = 2, FMRX_PATH_RDS_STAGES = 4 };
 enum { FMRX_NUMERICS_REFERENCE = 0, FMRX_NUMERICS_FMA = 1 }; /* audio-path FIR rounding, see `exact` above */
 
 typedef struct {
-    int32_t mode;       /* 0: 2.4 Msps, /10, /5, +RDS ; 1: 2.5 Msps, /10, x24 /125, no RDS (src/fm_radio.cpp:36-37,174-180) */
+    int32_t mode;       /* 0: 2.4 Msps, /10, /5, +RDS ; 1: 2.5 Msps, /10, x24 /125, no RDS (src/fm_radio.cpp:36-37,174-180);
+                         * 2 (extension, not in the reference's main()): mode 0's front end and RDS path with the audio
+                         * resampled x147 /800 to 44.1 kHz by the reference's polyphase resampler (BASELINE config 2) */
     int32_t profile;    /* FMRX_PROFILE_* */
     int32_t n_streams;  /* independent stations */
     int32_t max_blocks; /* largest n_blocks a process call will be given */
@@ -140,7 +142,7 @@ typedef struct {
 
 int fmrx_batch_create(const fmrx_config *cfg, fmrx_batch **out);
 void fmrx_batch_destroy(fmrx_batch *);
-int fmrx_batch_audio_per_block(const fmrx_batch *); /* 3072 (mode 0) / 2949 (mode 1) */
+int fmrx_batch_audio_per_block(const fmrx_batch *); /* 3072 (mode 0) / 2949 (mode 1) / 2822 (mode 2) */
 int fmrx_batch_reset(fmrx_batch *);                 /* back to block 0 with the reference's initial state */
 /* host -> host.  iq:[S][n_blocks][307200] bytes.  Copies are staged through pinned rings and overlapped with the
  * kernels on separate CUDA streams (the replacement for the reference's producer/consumer threads). */

@@ -461,12 +461,21 @@ orc_chain *orc_chain_create(int mode, int profile) {
     float audio_Fs = 240000.0f;
     c->audio_taps = NT; c->audio_up = 1; c->audio_decim = 5; c->mult = 1;
     if (mode == 1) { audio_Fs = 6000000.0f; c->audio_decim = 125; c->audio_up = 24; c->audio_taps = NT * 24; c->mult = 24; }
+    /* mode 2 is NOT in the reference (its main() accepts only "1", src/fm_radio.cpp:736-764): the 44.1 kHz output BASELINE.json's
+     * config 2 names, composed from the reference's own mode-1 thread body (:174-180, :228, :245) with (U, D) = (147, 800) on
+     * the 240 kHz IF of mode 0 -- 151 * 147 = 22197 taps (odd: no NaN tap, Q5), floor(15360 * 147 / 800) = 2822 samples per
+     * block.  Every function it calls is pinned against the reference; the composition has no reference output to pin. */
+    if (mode == 2) { audio_Fs = 240000.0f * 147.0f; c->audio_decim = 800; c->audio_up = 147; c->audio_taps = NT * 147; c->mult = 147; }
     c->nzi_a = c->audio_taps - 1; /* all four states sized from audio_taps (:189-193) */
+    if (c->nzi_a > NIF - 1) c->nzi_a = NIF - 1; /* mode 2 only: the update rule zi[i] = x[N - Z - 1 + i] needs Z <= N - 1 */
     c->n_audio = (int)(((long)NIF * c->audio_up) / c->audio_decim);
     c->h_mono = fz((size_t)c->audio_taps); c->h_stereo = fz((size_t)c->audio_taps);
     orc_design_lpf(audio_Fs, 16000.0f, (unsigned short)c->audio_taps, c->h_mono);   /* :200 */
-    orc_design_bpf(18.5e3f, 19.5e3f, audio_Fs, NT, c->h_pilot);                      /* :201 */
-    orc_design_bpf(22e3f, 54e3f, audio_Fs, NT, c->h_sbpf);                           /* :202 */
+    /* :201-202 design the two band-pass filters at audio_Fs, which in mode 1 is the UPSAMPLED rate (6 MHz) although they run
+     * on the 250 kHz IF -- replicated for mode 1; mode 2 designs them at the rate they run at, like mode 0 */
+    float bpf_Fs = mode == 2 ? 240000.0f : audio_Fs;
+    orc_design_bpf(18.5e3f, 19.5e3f, bpf_Fs, NT, c->h_pilot);                        /* :201 */
+    orc_design_bpf(22e3f, 54e3f, bpf_Fs, NT, c->h_sbpf);                             /* :202 */
     orc_design_lpf(audio_Fs, 16000.0f, (unsigned short)c->audio_taps, c->h_stereo); /* :203 */
     c->zi_mono = fz((size_t)c->nzi_a); c->zi_pilot = fz((size_t)c->nzi_a); c->zi_sbpf = fz((size_t)c->nzi_a); c->zi_stereo = fz((size_t)c->nzi_a);
     static const float pll0[6] = {0.0f, 0.0f, 1.0f, 0.0f, 0.0f, 1.0f}; /* :165-171, :343-349 */
@@ -522,7 +531,7 @@ int orc_chain_block(orc_chain *c, const uint8_t *raw, int16_t *audio) {
     /* ---- mono_stero_thread: :226-307 ---- */
     if (c->paths & 1) {
         int na = c->n_audio;
-        if (c->mode == 1) orc_resample(c->mono, 0, c->demod, NIF, c->h_mono, c->audio_taps, c->zi_mono, c->nzi_a, c->audio_decim, c->audio_up, 0); /* :228 */
+        if (c->mode != 0) orc_resample(c->mono, 0, c->demod, NIF, c->h_mono, c->audio_taps, c->zi_mono, c->nzi_a, c->audio_decim, c->audio_up, 0); /* :228 */
         else orc_fir_decim(c->mono, c->demod, NIF, c->h_mono, NT, c->zi_mono, c->nzi_a, 5);                                                   /* :258 */
         /* Q7: `mixed.clear()` (:307) kills the stereo path from block 1 on in the shipped binary */
         int stereo_live = (c->profile == ORC_PROFILE_INTENT) || c->block_id == 0;
@@ -532,6 +541,7 @@ int orc_chain_block(orc_chain *c, const uint8_t *raw, int16_t *audio) {
             orc_fir_decim(c->sbpf, c->demod, NIF, c->h_sbpf, NT, c->zi_sbpf, c->nzi_a, 1);                    /* :236/:265 */
             for (int i = 0; i < NIF; i++) c->mixed[i] = c->sbpf[i] * c->nco[i];                                /* :240-243/:269-272 */
             if (c->mode == 1) orc_resample(c->stereo, na, c->mixed, NIF, c->h_stereo, c->audio_taps, c->zi_stereo, c->nzi_a, 5, c->audio_up, 0); /* :245 (Q14) */
+            else if (c->mode == 2) orc_resample(c->stereo, 0, c->mixed, NIF, c->h_stereo, c->audio_taps, c->zi_stereo, c->nzi_a, c->audio_decim, c->audio_up, 0); /* the call :245 meant to make */
             else orc_fir_decim(c->stereo, c->mixed, NIF, c->h_stereo, NT, c->zi_stereo, c->nzi_a, 5);                                          /* :274 */
         } else {
             for (int i = 0; i < na; i++) c->stereo[i] = 0.0f;
@@ -543,9 +553,9 @@ int orc_chain_block(orc_chain *c, const uint8_t *raw, int16_t *audio) {
         }
     }
 
-    /* ---- rds_thread (:395-411) + frame_thread, mode 0 only (:324, :446) ---- */
+    /* ---- rds_thread (:395-411) + frame_thread: not in mode 1 (:324, :446); mode 2 has mode 0's 240 kHz IF, so it runs ---- */
     c->nbits = 0; c->nev = 0;
-    if (c->mode == 0 && (c->paths & 2)) {
+    if (c->mode != 1 && (c->paths & 2)) {
         orc_fir_decim(c->rbpf, c->demod, NIF, c->h_rbpf, NT, c->zi_rbpf, NT - 1, 1);
         orc_pll_combine(c->rsq, c->rnco, c->rbpf, NIF, c->h_sq, NT, c->zi_sq, 114000.0f, 240000.0f, 0.5f, c->rds_phase, 0.001f, c->rds_pll_st);
         orc_fir_mixer(c->rlpf, c->rnco, c->rbpf, NIF, c->h_lpf3k, NT, c->zi_lpf);

@@ -78,7 +78,7 @@ enum {
 typedef struct orc_chain orc_chain;
 orc_chain *orc_chain_create(int mode, int profile);
 void orc_chain_destroy(orc_chain *);
-int orc_chain_audio_per_block(const orc_chain *); /* 3072 (mode 0) or 2949 (mode 1) */
+int orc_chain_audio_per_block(const orc_chain *); /* 3072 (mode 0), 2949 (mode 1), 2822 (mode 2: 44.1 kHz, not in the reference) */
 /* one 307200-byte block -> 2*audio_per_block int16 (L,R interleaved).  Returns #int16 written. */
 int orc_chain_block(orc_chain *, const uint8_t *iq, int16_t *audio);
 const float *orc_chain_tap(const orc_chain *, int which, int *n);

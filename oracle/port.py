@@ -223,7 +223,7 @@ class Chain:
             audio.append(self.block(raw[b * 307200:(b + 1) * 307200]))
             for t in taps:
                 cap[t].append(self.tap(t))
-            if self.mode == 0:
+            if self.mode != 1:
                 bb, ev = self.rds()
                 bits.append(bb)
                 events.extend(ev)

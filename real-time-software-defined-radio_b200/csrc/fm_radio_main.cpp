@@ -4,7 +4,9 @@
 //   stdout headerless little-endian int16, interleaved L,R, 48 kHz, one write per block (:286-302)
 //   stderr the reference's diagnostics: argc, mode line, rf_Fs, and in mode 0 the frame_thread lines (:516,:619-701)
 // Extensions (after the mode argument, all optional): --profile binary|intent (default binary = byte-compatible with
-// the shipped executable), --blocks N (blocks per GPU call, default 1), --device D, --quiet.
+// the shipped executable), --blocks N (blocks per GPU call, default 1), --device D, --quiet,
+// --audio-rate 44100 (mode 0 only: audio through the x147 /800 polyphase resampler, 2822 samples per block; the 44.1 kHz
+// mode of the project the reference never implemented), --rds-info (PI / PS / RadioText from the decoded bits, at exit).
 // EOF handling is normalised (Q9): only whole blocks are processed.
 //
 // The reference's four threads and three bounded queues are replaced by: a reader thread filling a ring of pinned host
@@ -45,7 +47,7 @@ size_t read_fully(uint8_t *dst, size_t n) {
 }  // namespace
 
 int main(int argc, char *argv[]) {
-    int mode = 0, profile = FMRX_PROFILE_BINARY, blocks = 1, device = 0;
+    int mode = 0, lib_mode = -1, profile = FMRX_PROFILE_BINARY, blocks = 1, device = 0;
     bool quiet = false, rds_info = false;
     int pos = 1;
     std::cerr << ((argc >= 2 && argv[1][0] != '-') ? 2 : 1) << std::endl;  // the reference prints argc first (:738); options are not counted
@@ -64,6 +66,11 @@ int main(int argc, char *argv[]) {
         else if (a == "--blocks") blocks = std::max(1, atoi(next()));
         else if (a == "--device") device = atoi(next());
         else if (a == "--quiet") quiet = true;
+        else if (a == "--audio-rate") {  // extension: 44100 selects the x147 /800 audio resampler (library mode 2); only with the 2.4 Msps front end
+            const int rate = atoi(next());
+            if ((rate != 48000 && rate != 44100) || (rate == 44100 && mode != 0)) { std::cerr << "Usage " << argv[0] << std::endl; return 1; }
+            if (rate == 44100) lib_mode = 2;
+        }
         else if (a == "--rds-info") rds_info = true;  // extension: decode the RDS groups (PI, PS, RadioText) and report them at the end
         else { std::cerr << "Usage " << argv[0] << std::endl; return 1; }  // :762
     }
@@ -71,7 +78,7 @@ int main(int argc, char *argv[]) {
     std::cerr << "rf_Fs = " << (mode == 1 ? 2500000 : 2400000) << std::endl;  // :61
 
     fmrx_config cfg{};
-    cfg.mode = mode; cfg.profile = profile; cfg.n_streams = 1; cfg.max_blocks = blocks; cfg.device = device;
+    cfg.mode = lib_mode >= 0 ? lib_mode : mode; cfg.profile = profile; cfg.n_streams = 1; cfg.max_blocks = blocks; cfg.device = device;
     fmrx_batch *rx = nullptr;
     if (fmrx_batch_create(&cfg, &rx) != FMRX_OK) {
         std::cerr << "fm_radio: " << fmrx_last_error() << std::endl;

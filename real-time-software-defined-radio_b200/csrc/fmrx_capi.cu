@@ -419,7 +419,7 @@ int enqueue_chain(fmrx_batch *b, const uint8_t *iq, long long ld_iq, int s0, int
     // ---- mono_stero_thread, filters (:226-236 / :255-265)
     if (b->audio_on) {
         STAGE(FMRX_STAGE_MONO);
-        if (b->cfg.mode == 1) {
+        if (b->cfg.mode != 0) {
             ResampleJob r{};
             r.x = IF(b->demod); r.y = AU2(b->mono); r.zi = b->zi_mono + (long long)s0 * b->nzi_a; r.h = b->d_h_mono; r.ldx = ldif; r.ldy = lda;
             r.n = NIF; r.n_ref = NIF; r.ny = b->n_audio; r.n_blocks = nblk; r.n_streams = ns; r.ntaps = b->audio_taps; r.nzi = b->nzi_a;
@@ -473,11 +473,11 @@ int enqueue_chain(fmrx_batch *b, const uint8_t *iq, long long ld_iq, int s0, int
         if (stereo_live) {
             STAGE(FMRX_STAGE_STEREO_LPF);
             if (st_blocks < nblk) CU(cudaMemset2DAsync(AU(b->stereo), lda * 4, 0, (size_t)nblk * b->n_audio * 4, ns, st));
-            if (b->cfg.mode == 1) {
-                ResampleJob r{};  // convolveWithDecimMode1(stereo_filt, mixed, stereo_coeff, stereo_initial, 5, 24), :245 (Q14)
+            if (b->cfg.mode != 0) {
+                ResampleJob r{};  // convolveWithDecimMode1(stereo_filt, mixed, stereo_coeff, stereo_initial, 5, 24), :245 (Q14); mode 2: the decimation it meant
                 r.x = IF2(b->mixed); r.y = AU(b->stereo); r.zi = b->zi_stereo + (long long)s0 * b->nzi_a; r.h = b->d_h_stereo; r.ldx = ldif; r.ldy = lda;
                 r.n = NIF; r.n_ref = NIF; r.ny = b->n_audio; r.n_blocks = st_blocks; r.n_streams = ns; r.ntaps = b->audio_taps; r.nzi = b->nzi_a;
-                r.decim = 5; r.up = b->up; r.gain_up = 0; r.exact = ex;
+                r.decim = b->cfg.mode == 1 ? 5 : b->decim_a; r.up = b->up; r.gain_up = 0; r.exact = ex;
                 LAUNCH(launch_resample(r, st));
             } else {
                 LAUNCH(fir(IF2(b->mixed), nullptr, AU(b->stereo), b->zi_stereo + (long long)s0 * b->nzi_a, b->nzi_a, b->h_stereo.data(), ldif, lda, NIF, 5, SRC_PLAIN, ex, st_blocks));
@@ -543,8 +543,8 @@ extern "C" {
 int fmrx_batch_create(const fmrx_config *cfg, fmrx_batch **out) {
     if (!cfg || !out) return fail(FMRX_ERR_ARG, "fmrx_batch_create: null pointer");
     *out = nullptr;
-    if ((cfg->mode != 0 && cfg->mode != 1) || cfg->n_streams <= 0 || cfg->max_blocks <= 0 || cfg->n_streams > 65535 || cfg->max_blocks > 65535)
-        return fail(FMRX_ERR_ARG, "fmrx_batch_create: mode must be 0 or 1, 1 <= n_streams,max_blocks <= 65535");
+    if (cfg->mode < 0 || cfg->mode > 2 || cfg->n_streams <= 0 || cfg->max_blocks <= 0 || cfg->n_streams > 65535 || cfg->max_blocks > 65535)
+        return fail(FMRX_ERR_ARG, "fmrx_batch_create: mode must be 0, 1 or 2, 1 <= n_streams,max_blocks <= 65535");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(FMRX_ERR_CUDA, "no CUDA device: libfmrx has no CPU fallback"); }
     if (cfg->device < 0 || cfg->device >= ndev) return fail(FMRX_ERR_ARG, "device %d out of range (%d devices)", cfg->device, ndev);
@@ -556,7 +556,7 @@ int fmrx_batch_create(const fmrx_config *cfg, fmrx_batch **out) {
     b->S = cfg->n_streams; b->NB = cfg->max_blocks;
     const int paths = cfg->paths ? cfg->paths : (FMRX_PATH_AUDIO | FMRX_PATH_RDS);
     b->audio_on = (paths & FMRX_PATH_AUDIO) != 0;
-    b->rds_on = (paths & FMRX_PATH_RDS) != 0 && cfg->mode == 0;  // src/fm_radio.cpp:324,446
+    b->rds_on = (paths & FMRX_PATH_RDS) != 0 && cfg->mode != 1;  // src/fm_radio.cpp:324,446 (mode 2 has mode 0's 240 kHz IF)
     b->rds_fast = b->rds_on && !(paths & FMRX_PATH_RDS_STAGES);
     b->exact = cfg->numerics == FMRX_NUMERICS_REFERENCE;
     // ---- constants of the thread bodies
@@ -564,13 +564,17 @@ int fmrx_batch_create(const fmrx_config *cfg, fmrx_batch **out) {
     float audio_Fs = 240000.0f;                                    // :153
     b->audio_taps = kTaps; b->up = 1; b->decim_a = 5; b->mult = 1;
     if (cfg->mode == 1) { audio_Fs = 6000000.0f; b->decim_a = 125; b->up = 24; b->audio_taps = kTaps * 24; b->mult = 24; }  // :174-180,229
+    // mode 2 (not in the reference): the mode-1 thread body with (U, D) = (147, 800) on mode 0's 240 kHz IF -> 44.1 kHz, 2822 per block
+    if (cfg->mode == 2) { audio_Fs = 240000.0f * 147.0f; b->decim_a = 800; b->up = 147; b->audio_taps = kTaps * 147; b->mult = 147; }
     b->nzi_a = b->audio_taps - 1;                                  // :189-193
+    if (b->nzi_a > NIF - 1) b->nzi_a = NIF - 1;                    // mode 2 only: the reference's update rule zi[i] = x[N - Z - 1 + i] needs Z <= N - 1
     b->n_audio = (int)(((long long)NIF * b->up) / b->decim_a);
     b->h_mono.resize(b->audio_taps); b->h_stereo.resize(b->audio_taps); b->h_anti.resize(kTaps * 19);
     fmrx_design_lpf(rf_Fs, 100000.0f, kTaps, b->h_rf);                                  // :40-42,75
     fmrx_design_lpf(audio_Fs, 16000.0f, (unsigned short)b->audio_taps, b->h_mono.data());   // :200
-    fmrx_design_bpf(18.5e3f, 19.5e3f, audio_Fs, kTaps, b->h_pilot);                     // :201
-    fmrx_design_bpf(22e3f, 54e3f, audio_Fs, kTaps, b->h_sbpf);                          // :202
+    const float bpf_Fs = cfg->mode == 2 ? 240000.0f : audio_Fs;  // :201-202 use audio_Fs, in mode 1 the upsampled 6 MHz (replicated); mode 2: the IF rate, like mode 0
+    fmrx_design_bpf(18.5e3f, 19.5e3f, bpf_Fs, kTaps, b->h_pilot);                       // :201
+    fmrx_design_bpf(22e3f, 54e3f, bpf_Fs, kTaps, b->h_sbpf);                            // :202
     fmrx_design_lpf(audio_Fs, 16000.0f, (unsigned short)b->audio_taps, b->h_stereo.data()); // :203
     fmrx_design_bpf(54000.0f, 60000.0f, 240000.0f, kTaps, b->h_rbpf);                   // :366
     fmrx_design_bpf(113500.0f, 114500.0f, 240000.0f, kTaps, b->h_sq);                   // :367

@@ -411,7 +411,7 @@ class Batch:
         check(lib().fmrx_batch_create(C.byref(self.cfg), C.byref(self.h)))
         self.S, self.mode, self.max_blocks = n_streams, mode, max_blocks
         self.n_audio = lib().fmrx_batch_audio_per_block(self.h)
-        self.rds = mode == 0 and (paths == 0 or paths & PATH_RDS)
+        self.rds = mode != 1 and (paths == 0 or paths & PATH_RDS)
         self.audio_on = paths == 0 or bool(paths & PATH_AUDIO)
         self.block_id = 0
 
