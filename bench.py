@@ -411,12 +411,21 @@ def run_fmrx_arm(args, rank, world, local_rank):
         gbs = STAGE_BYTES[name] * S * B * args.steps / (ms * 1e-3) / 1e9
         ent.update({"hbm_gbs": round(gbs, 1), "frac_hbm": round(gbs / hbm_peak, 4)})
         per[name] = ent
+    # the PLL stage has no throughput roofline: 8192 loops = 256 warps on 592 schedulers, each one dependency chain per
+    # sample.  Its bound is the latency of one step of that chain, measured here on one warp running alone from registers.
+    if "pll" in per:
+        sm_mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965
+        chain = fmrx.measure_pll_chain(local_rank)
+        cyc = per["pll"]["ms_per_step"] * 1e-3 * sm_mhz * 1e6 / (15360 * B)
+        per["pll"].update({"bound": "latency of the per-sample dependency chain (one loop per lane, 1 warp per scheduler when run alone)",
+                           "cycles_per_step": round(cyc, 1), "chain_latency_cycles": round(chain, 1), "frac_latency": round(chain / cyc, 3),
+                           "sm_mhz_used": sm_mhz})
     top = max((n for n in per if n in STAGE_MACS), key=lambda n: per[n]["ms_per_step"])
     roofline = {
         "bound": "fp32", "kernel": top, "achieved": per[top]["tflops"], "peak": per[top]["fp32_peak_tflops"], "unit": "TFLOP/s", "frac": per[top]["frac_fp32"],
         # dram__bytes_read.sum + dram__bytes_write.sum of one front-end launch (4096 stations x 1 block) from the committed
-        # `ncu --set full` capture profiles/r2d_kernels.md: 1.387 GB + 0.248 GB, against 1.510 GB algorithmic
-        "traffic": 1.635e9 * (S * B / 4096.0) if top == "frontend" else None, "traffic_unit": "bytes per launch (ncu, profiles/r2d_kernels.md)",
+        # `ncu --set full` capture profiles/r3g_kernels.md: 1.390 GB + 0.241 GB, against 1.510 GB algorithmic
+        "traffic": 1.632e9 * (S * B / 4096.0) if top == "frontend" else None, "traffic_unit": "bytes per launch (ncu, profiles/r3g_kernels.md)",
         "algorithmic_bytes": STAGE_BYTES[top] * S * B,
         "peak_source": "measured in this run by fmrx_measure_fp32_peak: %.2f T FFMA/s (x2 flop), %.2f T FMUL+FADD lane-ops/s; a stage that keeps the "
                        "reference's two roundings per tap is bounded by the latter" % (peak_ffma, peak_muladd),

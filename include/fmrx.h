@@ -262,6 +262,9 @@ int fmrx_model_pll(double *nco, double *nco_q, const double *x, int n_streams, i
 /* runs an FP32 issue-rate microbenchmark on `device` and returns the best-of-`reps` rate in T lane-ops/s:
  * kind 0 = FFMA, 1 = FMUL+FADD pairs, 2 = packed FFMA2, 3 = packed FMUL2+FADD2 */
 int fmrx_measure_fp32_peak(int device, int kind, int reps, double *tera_ops_per_s);
+/* latency roofline of the PLL kernel: SM cycles per step of ONE loop's dependency chain (phase detector -> loop filter ->
+ * oscillator, src/helper.cpp:32-45 as csrc/fmrx_pllmath.h computes it) run alone on one warp from registers */
+int fmrx_measure_pll_chain(int device, double *cycles_per_step);
 
 #ifdef __cplusplus
 }

@@ -9,9 +9,39 @@
 #include <cuda_runtime.h>
 
 #include "fmrx_internal.h"
+#include "fmrx_pllmath.h"
 
 namespace fmrx {
 namespace {
+
+// The PLL kernel's roofline is not a throughput: one loop is one dependency chain (detector -> loop filter -> oscillator
+// -> next sample), 8192 loops are 256 warps on 592 schedulers, and what bounds the kernel is the LATENCY of one step of
+// that chain.  This measures it in isolation: one warp, the step of csrc/fmrx_pllmath.h fed from registers (no memory
+// traffic, no other warp on the scheduler), cycles per step from clock64.
+__global__ void pll_chain_kernel(float *out, long long *cycles, int steps, float freq_ratio, float scale) {
+    using namespace pllmath;
+    PllCarry c{0.0f, 0.0f, 1.0f, 0.0f};
+    PllFast f;
+    pll_disarm(f);
+    const PllCoef p{1e-6f * 3.555f, 1e-3f * 2.666f, scale, 0.1f, (2 * 3.14159265358979323846) * (double)freq_ratio};
+    float acc = 0.0f, x = 0.05f + 1e-4f * threadIdx.x;
+    { const PllLibmOut o = pll_step_libm(c, p, x, 1.0f); c = o.c; pll_rearm(f, o.trig); }
+    int bad = 0;
+    const long long t0 = clock64();
+    for (int k = 1; k < steps; k += 4) {
+        bool ok0, ok1, ok2, ok3;
+        const float x0 = -x * 0.999f + 1e-5f, x1 = -x0 * 0.999f + 1e-5f, x2 = -x1 * 0.999f + 1e-5f, x3 = -x2 * 0.999f + 1e-5f;
+        x = x3;
+        acc += pll_step_fast(c, f, p, x0, __fadd_rn((float)k, 1.0f), ok0);
+        acc += pll_step_fast(c, f, p, x1, __fadd_rn((float)k, 2.0f), ok1);
+        acc += pll_step_fast(c, f, p, x2, __fadd_rn((float)k, 3.0f), ok2);
+        acc += pll_step_fast(c, f, p, x3, __fadd_rn((float)k, 4.0f), ok3);
+        bad += !(ok0 && ok1 && ok2 && ok3);
+    }
+    const long long t1 = clock64();
+    out[threadIdx.x] = acc + c.phase + bad;
+    if (threadIdx.x == 0) *cycles = t1 - t0;
+}
 
 constexpr int ILP = 16;
 constexpr int ITERS = 4096;
@@ -73,6 +103,23 @@ int run(int reps, double *tera) {
 }
 
 }  // namespace
+
+int measure_pll_chain(double *cycles_per_step) {
+    const int steps = 60000;
+    float *out = nullptr;
+    long long *cyc = nullptr, h = 0;
+    cudaError_t e = cudaMalloc(&out, 32 * sizeof(float));
+    if (e) return (int)e;
+    e = cudaMalloc(&cyc, sizeof(long long));
+    if (e) { cudaFree(out); return (int)e; }
+    for (int r = 0; r < 2; ++r) pll_chain_kernel<<<1, 32>>>(out, cyc, steps, 19e3f / 240e3f, 2.0f);  // second run: instruction cache warm
+    launch_counter() += 2;
+    e = cudaMemcpy(&h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(out); cudaFree(cyc);
+    if (e) return (int)e;
+    *cycles_per_step = (double)h / (double)(steps - 1);
+    return (int)cudaGetLastError();
+}
 
 int measure_fp32_peak(int, int kind, int reps, double *tera) {
     if (reps < 1) reps = 1;

@@ -252,6 +252,13 @@ int fmrx_rds_format_block(int block_id, int initial_offset, const fmrx_rds_event
     return w;
 }
 
+int fmrx_measure_pll_chain(int device, double *cycles_per_step) {
+    if (!cycles_per_step) return fail(FMRX_ERR_ARG, "null pointer");
+    CU(cudaSetDevice(device));
+    LAUNCH(measure_pll_chain(cycles_per_step));
+    return FMRX_OK;
+}
+
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -271,7 +278,7 @@ constexpr int kTickets = 8;    // completion events kept by the asynchronous hos
 
 struct fmrx_batch {
     fmrx_config cfg{};
-    int S = 0, NB = 0, n_audio = 0, nzi_a = 0, audio_taps = 0, up = 1, decim_a = 5, mult = 1;
+    int S = 0, NB = 0, n_audio = 0, nzi_a = 0, nzi_b = 0, audio_taps = 0, up = 1, decim_a = 5, mult = 1;
     bool audio_on = false, rds_on = false, exact = true;
     bool rds_fast = false;  // RDS back end at symbol rate (fmrx_rdsfast.cu) instead of stage by stage
     float *d_W = nullptr, *d_G = nullptr, *d_h2p = nullptr;
@@ -284,7 +291,7 @@ struct fmrx_batch {
     std::vector<float> h_mono, h_stereo, h_anti;
     float rds_phase = 0.f;
     // device
-    float *d_h_mono = nullptr, *d_h_stereo = nullptr, *d_h_anti = nullptr;
+    float *d_h_mono = nullptr, *d_h_stereo = nullptr, *d_h_anti = nullptr, *d_hp_mono = nullptr, *d_hp_stereo = nullptr;
     char *d_state = nullptr;  // one blob: every carried state
     size_t state_bytes = 0;
     float *zi_i, *zi_q, *zi_mono, *zi_pilot, *zi_sbpf, *zi_stereo, *pll_st, *zi_rbpf, *zi_sq, *zi_lpf, *zi_rrc, *zi_anti, *rds_pll_st;
@@ -423,7 +430,7 @@ int enqueue_chain(fmrx_batch *b, const uint8_t *iq, long long ld_iq, int s0, int
             ResampleJob r{};
             r.x = IF(b->demod); r.y = AU2(b->mono); r.zi = b->zi_mono + (long long)s0 * b->nzi_a; r.h = b->d_h_mono; r.ldx = ldif; r.ldy = lda;
             r.n = NIF; r.n_ref = NIF; r.ny = b->n_audio; r.n_blocks = nblk; r.n_streams = ns; r.ntaps = b->audio_taps; r.nzi = b->nzi_a;
-            r.decim = b->decim_a; r.up = b->up; r.gain_up = 0; r.exact = ex;
+            r.decim = b->decim_a; r.up = b->up; r.gain_up = 0; r.exact = ex; r.hp = b->d_hp_mono;
             LAUNCH(launch_resample(r, st));
         } else {
             LAUNCH(fir(IF(b->demod), nullptr, AU2(b->mono), b->zi_mono + (long long)s0 * b->nzi_a, b->nzi_a, b->h_mono.data(), ldif, lda, NIF, 5, SRC_PLAIN, ex, nblk));
@@ -432,11 +439,11 @@ int enqueue_chain(fmrx_batch *b, const uint8_t *iq, long long ld_iq, int s0, int
     if (b->audio_on) {
         if (stereo_live) {
             STAGE(FMRX_STAGE_PILOT_BPF);
-            LAUNCH(fir(IF(b->demod), nullptr, IF2(b->pilot), b->zi_pilot + (long long)s0 * b->nzi_a, b->nzi_a, b->h_pilot, ldif, ldif, NIF, 1, SRC_PLAIN, 1, st_blocks));
+            LAUNCH(fir(IF(b->demod), nullptr, IF2(b->pilot), b->zi_pilot + (long long)s0 * b->nzi_b, b->nzi_b, b->h_pilot, ldif, ldif, NIF, 1, SRC_PLAIN, 1, st_blocks));
         }
         if (stereo_live) {
             STAGE(FMRX_STAGE_STEREO_BPF);
-            LAUNCH(fir(IF(b->demod), nullptr, IF2(b->sbpf), b->zi_sbpf + (long long)s0 * b->nzi_a, b->nzi_a, b->h_sbpf, ldif, ldif, NIF, 1, SRC_PLAIN, ex, st_blocks));
+            LAUNCH(fir(IF(b->demod), nullptr, IF2(b->sbpf), b->zi_sbpf + (long long)s0 * b->nzi_b, b->nzi_b, b->h_sbpf, ldif, ldif, NIF, 1, SRC_PLAIN, ex, st_blocks));
         }
     }
     // ---- rds_thread, filters before the PLL (:395, :400's BPF)
@@ -477,7 +484,7 @@ int enqueue_chain(fmrx_batch *b, const uint8_t *iq, long long ld_iq, int s0, int
                 ResampleJob r{};  // convolveWithDecimMode1(stereo_filt, mixed, stereo_coeff, stereo_initial, 5, 24), :245 (Q14); mode 2: the decimation it meant
                 r.x = IF2(b->mixed); r.y = AU(b->stereo); r.zi = b->zi_stereo + (long long)s0 * b->nzi_a; r.h = b->d_h_stereo; r.ldx = ldif; r.ldy = lda;
                 r.n = NIF; r.n_ref = NIF; r.ny = b->n_audio; r.n_blocks = st_blocks; r.n_streams = ns; r.ntaps = b->audio_taps; r.nzi = b->nzi_a;
-                r.decim = b->cfg.mode == 1 ? 5 : b->decim_a; r.up = b->up; r.gain_up = 0; r.exact = ex;
+                r.decim = b->cfg.mode == 1 ? 5 : b->decim_a; r.up = b->up; r.gain_up = 0; r.exact = ex; r.hp = b->d_hp_stereo;
                 LAUNCH(launch_resample(r, st));
             } else {
                 LAUNCH(fir(IF2(b->mixed), nullptr, AU(b->stereo), b->zi_stereo + (long long)s0 * b->nzi_a, b->nzi_a, b->h_stereo.data(), ldif, lda, NIF, 5, SRC_PLAIN, ex, st_blocks));
@@ -568,6 +575,7 @@ int fmrx_batch_create(const fmrx_config *cfg, fmrx_batch **out) {
     if (cfg->mode == 2) { audio_Fs = 240000.0f * 147.0f; b->decim_a = 800; b->up = 147; b->audio_taps = kTaps * 147; b->mult = 147; }
     b->nzi_a = b->audio_taps - 1;                                  // :189-193
     if (b->nzi_a > NIF - 1) b->nzi_a = NIF - 1;                    // mode 2 only: the reference's update rule zi[i] = x[N - Z - 1 + i] needs Z <= N - 1
+    b->nzi_b = cfg->mode == 2 ? kHist : b->nzi_a;                  // the two 151-tap band-pass filters: :189-193 size them from audio_taps too; mode 2 keeps the 150 live entries
     b->n_audio = (int)(((long long)NIF * b->up) / b->decim_a);
     b->h_mono.resize(b->audio_taps); b->h_stereo.resize(b->audio_taps); b->h_anti.resize(kTaps * 19);
     fmrx_design_lpf(rf_Fs, 100000.0f, kTaps, b->h_rf);                                  // :40-42,75
@@ -590,7 +598,7 @@ int fmrx_batch_create(const fmrx_config *cfg, fmrx_batch **out) {
     struct Seg { void **p; size_t bytes; };
     std::vector<Seg> segs = {
         {(void **)&b->zi_i, S * kHist * 4}, {(void **)&b->zi_q, S * kHist * 4},
-        {(void **)&b->zi_mono, S * b->nzi_a * 4}, {(void **)&b->zi_pilot, S * b->nzi_a * 4}, {(void **)&b->zi_sbpf, S * b->nzi_a * 4}, {(void **)&b->zi_stereo, S * b->nzi_a * 4},
+        {(void **)&b->zi_mono, S * b->nzi_a * 4}, {(void **)&b->zi_pilot, S * b->nzi_b * 4}, {(void **)&b->zi_sbpf, S * b->nzi_b * 4}, {(void **)&b->zi_stereo, S * b->nzi_a * 4},
         {(void **)&b->pll_st, S * 6 * 4}, {(void **)&b->zi_rbpf, S * kHist * 4}, {(void **)&b->zi_sq, S * kHist * 4}, {(void **)&b->zi_lpf, S * kHist * 4},
         {(void **)&b->zi_rrc, S * kHist * 4}, {(void **)&b->zi_anti, S * (kTaps * 19 - 1) * 4}, {(void **)&b->rds_pll_st, S * 6 * 4},
         {(void **)&b->dec_st, S * FMRX_RDS_STATE_WORDS * 4}};
@@ -605,6 +613,17 @@ int fmrx_batch_create(const fmrx_config *cfg, fmrx_batch **out) {
     CU(cudaMemcpy(b->d_h_mono, b->h_mono.data(), b->audio_taps * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(b->d_h_stereo, b->h_stereo.data(), b->audio_taps * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(b->d_h_anti, b->h_anti.data(), kTaps * 19 * 4, cudaMemcpyHostToDevice));
+    if (b->up > 1) {  // phase-major copies for the phase-grouped resampler kernel
+        std::vector<float> hp((size_t)b->up * (kTaps + 1), 0.0f);
+        for (int which = 0; which < 2; ++which) {
+            const std::vector<float> &h = which ? b->h_stereo : b->h_mono;
+            for (int ph = 0; ph < b->up; ++ph)
+                for (int cc = 0; cc < kTaps; ++cc) hp[(size_t)ph * (kTaps + 1) + cc] = h[ph + (size_t)b->up * cc];
+            float *&dst = which ? b->d_hp_stereo : b->d_hp_mono;
+            CU(b->dalloc(dst, hp.size()));
+            CU(cudaMemcpy(dst, hp.data(), hp.size() * 4, cudaMemcpyHostToDevice));
+        }
+    }
     // ---- signals
     CU(b->dalloc(b->d_iq, S * NB * FMRX_BLOCK_BYTES));
     CU(b->dalloc(b->demod, S * NB * NIF));
@@ -643,6 +662,9 @@ int fmrx_batch_create(const fmrx_config *cfg, fmrx_batch **out) {
             const int loops = b->S * (b->rds_on ? 2 : 1), warps = (loops + 31) / 32;
             pll_sms = ((warps + 7) / 8 + 7) / 8 * 8;  // warps / (4 schedulers x 2), rounded up to the split granularity
             if (pll_sms > 64) pll_sms = 64;
+            // mode 2 is bound by its filters (the x147 resamplers): the PLLs can run three warps per scheduler on fewer SMs
+            // (sweep 24 / 32 / 40 SMs: 7.32 / 7.77 / 8.24 ms per step)
+            if (cfg->mode == 2 && pll_sms > 24) pll_sms = 24;
         }
         if (const char *e = getenv("FMRX_PLL_SMS")) pll_sms = atoi(e);
         if (pll_sms > 0) {

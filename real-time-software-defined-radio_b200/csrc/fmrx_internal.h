@@ -69,6 +69,7 @@ struct ResampleJob {
     float *zi;       // [S][nzi]
     const float *h;  // DEVICE taps [ntaps]
     const float *h_host;  // the same taps in HOST memory, or null: lets the tiled fast path (fmrx_resample.cu) pass them by value
+    const float *hp;      // DEVICE, optional: the taps phase-major, hp[ph * 152 + c] = h[ph + up * c] (151 taps per phase): enables the phase-grouped kernel
     long long ldx, ldy;
     // n = samples per block in memory; n_ref = the length the reference's vector had (differs only for the RDS resampler,
     // whose input is the 15361-long mixer output, src/fm_radio.cpp:404-408); ny = outputs per block actually produced
@@ -124,6 +125,7 @@ int rds_fast_tables(const float *h1, const float *h2, const float *hr, float **d
 int launch_rds_fast(const RdsFastJob &j, fmrx_stream_t st);
 
 int measure_fp32_peak(int device, int kind, int reps, double *tera);
+int measure_pll_chain(double *cycles_per_step);
 
 // SM partition (green contexts) for the device-resident pipeline, fmrx_partition.cu.  partition_create returns nullptr
 // when the driver cannot split the device; the caller then falls back to priority streams on the whole device.

@@ -23,7 +23,7 @@
 
 #ifdef __CUDACC__
 #define FMRX_HD __host__ __device__ __forceinline__
-#define FMRX_HD_COLD __host__ __device__ __noinline__
+#define FMRX_HD_COLD inline __host__ __device__ __noinline__
 #else
 #define FMRX_HD inline
 #define FMRX_HD_COLD inline

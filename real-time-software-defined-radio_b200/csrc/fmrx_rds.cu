@@ -12,6 +12,9 @@
 //                           floating-point operations are comparisons of RRC samples.
 #include <cuda_runtime.h>
 
+#include <cstdint>
+#include <cstdlib>
+
 #include "fmrx_internal.h"
 
 namespace fmrx {
@@ -50,6 +53,104 @@ __global__ void resample_kernel(const ResDev a) {
     }
     if (a.gain_up) acc = __fmul_rn(acc, (float)a.up);
     a.y[(long long)s * a.ldy + (long long)b * a.ny + o] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The audio resamplers of modes 1 and 2 (x24 /125, x24 /5 [Q14], x147 /800): same arithmetic, grouped by PHASE.
+//
+// The general kernel above gives a warp 32 consecutive outputs = 32 different phases: every tap load is a 32-line
+// gather (taps k0 + U*c with a different k0 per lane) and the kernel runs at ~10 % of the FIR kernels' rate (mode 1:
+// 1.05 + 1.34 ms per step against 0.15 ms for the same MAC count in mode 0).  Outputs o = r + U*m (same residue r) share
+// their phase (D*o mod U = D*r mod U), so here a warp takes one residue and 32 values of m: the 151 taps of that phase
+// are ONE address per load for the whole warp (phase-major table, broadcast), and the samples x[q_r + D*m - c] are read
+// from a copy of the block staged in shared memory with lane stride D -- conflict-free when D is odd; an even D gets one
+// pad word per D samples (pitch D+1), and because q0 mod D = q_r is the same for all lanes the pad is crossed at a
+// warp-uniform tap count, so the loop just splits there.  One CTA per (station, block).  Tasks whose lanes reach into
+// the history (q0 < 150: the first outputs of a block) run a second form of the loop that selects, per tap, between the
+// staged block and the history value zi[(Z-1-c)/U] -- which depends on the tap count only (Q6), so it is staged once per
+// CTA as 151 floats.  Summation order per output is the reference's (c ascending); EXACT keeps FMUL + FADD.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int TPP_ = kTaps;           // taps per phase
+constexpr int HPITCH = kTaps + 1;     // phase-major table pitch
+
+template <bool EXACT, bool SKEW>
+__global__ void __launch_bounds__(256) resample_phase_kernel(const ResDev a, const float *__restrict__ hp) {
+    constexpr int skew = SKEW ? 1 : 0;
+    extern __shared__ float xs_sh[];                       // block b of the stream, index p + skew * (p / D)
+    __shared__ __align__(16) float hist[TPP_ + 1];         // history value for tap count c (Q6)
+    __shared__ __align__(16) float wtaps[8][HPITCH];       // the current task's taps, per warp
+    const int b = blockIdx.x, s = blockIdx.y, U = a.up, D = a.decim;
+    const float *xb = a.x + (long long)s * a.ldx + (long long)b * a.n;
+    for (int p4 = threadIdx.x; p4 < a.n / 4; p4 += 256) {  // n % 4 == 0 and 16-byte alignment checked by the launcher
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(xb) + p4);
+        const int p = 4 * p4;
+        if (skew) {
+            xs_sh[p + p / D] = v.x; xs_sh[p + 1 + (p + 1) / D] = v.y; xs_sh[p + 2 + (p + 2) / D] = v.z; xs_sh[p + 3 + (p + 3) / D] = v.w;
+        } else {
+            *reinterpret_cast<float4 *>(xs_sh + p) = v;
+        }
+    }
+    if (threadIdx.x < TPP_) {
+        const int j = (a.nzi - 1 - (int)threadIdx.x) / U;
+        hist[threadIdx.x] = b > 0 ? xb[-(long long)a.n + (a.n_ref - a.nzi - 1 + j)] : a.zi[(long long)s * a.nzi + j];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int chunks = ((a.ny + U - 1) / U + 31) / 32;     // 32 values of m per task
+    float *ys = a.y + (long long)s * a.ldy + (long long)b * a.ny;
+    float *wt = wtaps[warp];
+    for (int task = warp; task < U * chunks; task += 8) {
+        const int r = task / chunks, m = 32 * (task % chunks) + lane;
+        const int o = r + U * m;
+        const int ph = (D * r) % U, qr = (D * r) / U;       // q0 = qr + D*m, qr < D
+        const bool valid = o < a.ny;
+        const int q0 = valid ? qr + D * m : 0x3fffffff;
+        const int at = valid ? q0 + skew * m : TPP_;        // staged index of x[q0] (q0 / D = m); idle lanes read inside the block
+        // this phase's 151 taps: one coalesced read per warp, then broadcast reads from shared memory
+        __syncwarp();
+        for (int i2 = lane; i2 < HPITCH; i2 += 32) wt[i2] = __ldg(hp + (long long)ph * HPITCH + i2);
+        __syncwarp();
+        float acc = 0.0f;
+        const float *xp = xs_sh + at;
+        if (__all_sync(0xffffffffu, q0 >= TPP_ - 1)) {      // every tap of every lane is inside the block
+            if (!SKEW) {
+#pragma unroll 2
+                for (int c = 0; c + 4 <= TPP_; c += 4) {
+                    const float4 t = *reinterpret_cast<const float4 *>(wt + c);
+                    const float v0 = xp[-c], v1 = xp[-c - 1], v2 = xp[-c - 2], v3 = xp[-c - 3];
+                    acc = EXACT ? __fadd_rn(acc, __fmul_rn(v0, t.x)) : fmaf(v0, t.x, acc);
+                    acc = EXACT ? __fadd_rn(acc, __fmul_rn(v1, t.y)) : fmaf(v1, t.y, acc);
+                    acc = EXACT ? __fadd_rn(acc, __fmul_rn(v2, t.z)) : fmaf(v2, t.z, acc);
+                    acc = EXACT ? __fadd_rn(acc, __fmul_rn(v3, t.w)) : fmaf(v3, t.w, acc);
+                }
+#pragma unroll
+                for (int c = TPP_ / 4 * 4; c < TPP_; ++c) acc = EXACT ? __fadd_rn(acc, __fmul_rn(xp[-c], wt[c])) : fmaf(xp[-c], wt[c], acc);
+            } else {
+                const int cx = min(qr + 1, TPP_);           // taps c <= qr stay in row m, the rest sit one pad word further down
+#pragma unroll 4
+                for (int c = 0; c < cx; ++c) acc = EXACT ? __fadd_rn(acc, __fmul_rn(xp[-c], wt[c])) : fmaf(xp[-c], wt[c], acc);
+#pragma unroll 4
+                for (int c = cx; c < TPP_; ++c) acc = EXACT ? __fadd_rn(acc, __fmul_rn(xp[-c - 1], wt[c])) : fmaf(xp[-c - 1], wt[c], acc);
+            }
+        } else {                                            // some lane reaches into the history: branch-free select per tap
+            auto tap = [&](int c, float t, float hv) {
+                const int d = q0 - c;                       // >= 0: inside the block
+                const int idx = d >= 0 ? d + (SKEW ? m - (c > qr ? 1 : 0) : 0) : 0;
+                const float xv = xs_sh[idx];
+                const float v = d >= 0 ? xv : hv;
+                acc = EXACT ? __fadd_rn(acc, __fmul_rn(v, t)) : fmaf(v, t, acc);
+            };
+#pragma unroll 2
+            for (int c = 0; c + 4 <= TPP_; c += 4) {
+                const float4 t = *reinterpret_cast<const float4 *>(wt + c), hv = *reinterpret_cast<const float4 *>(hist + c);
+                tap(c, t.x, hv.x); tap(c + 1, t.y, hv.y); tap(c + 2, t.z, hv.z); tap(c + 3, t.w, hv.w);
+            }
+#pragma unroll
+            for (int c = TPP_ / 4 * 4; c < TPP_; ++c) tap(c, wt[c], hist[c]);
+        }
+        if (a.gain_up) acc = __fmul_rn(acc, (float)U);
+        if (valid) ys[o] = acc;
+    }
 }
 
 __global__ void resample_state_kernel(const ResDev a) {
@@ -198,7 +299,20 @@ int launch_resample(const ResampleJob &j, fmrx_stream_t st) {
     d.n = j.n; d.n_ref = j.n_ref;
     d.ny = j.ny; d.n_blocks = j.n_blocks; d.ntaps = j.ntaps; d.nzi = j.nzi; d.decim = j.decim; d.up = j.up; d.gain_up = j.gain_up;
     dim3 grid((j.ny + 127) / 128, j.n_blocks, j.n_streams);
-    if (fast < 0) {
+    // phase-grouped kernel: needs the phase-major tap table, 151 taps per phase, a whole block in shared memory and a lane
+    // stride (D, or D + 1 with the pad) that is odd; an even D below 152 would cross the pad twice inside one output
+    const int skew = (j.decim % 2 == 0) ? 1 : 0;
+    const size_t smem = ((size_t)j.n + (skew ? j.n / j.decim + 1 : 0)) * sizeof(float);
+    static const bool no_phase = [] { const char *v = getenv("FMRX_RESAMPLE"); return v && atoi(v) == 1; }();
+    if (fast < 0 && !no_phase && j.hp && j.ntaps == kTaps * j.up && j.n_ref == j.n && j.n % 4 == 0 && j.ldx % 4 == 0 && ((uintptr_t)j.x & 15) == 0 &&
+        (!skew || j.decim >= kTaps + 1) && j.nzi >= kTaps && j.n_ref >= j.nzi + 1 && j.n > kTaps && smem <= 200 * 1024) {
+        auto kern = j.exact ? (skew ? resample_phase_kernel<true, true> : resample_phase_kernel<true, false>)
+                            : (skew ? resample_phase_kernel<false, true> : resample_phase_kernel<false, false>);
+        cudaError_t ea = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (ea) return (int)ea;
+        kern<<<dim3(j.n_blocks, j.n_streams), 256, smem, st>>>(d, j.hp);
+        launch_counter() += 1;
+    } else if (fast < 0) {
         if (j.exact) resample_kernel<true><<<grid, 128, 0, st>>>(d);
         else resample_kernel<false><<<grid, 128, 0, st>>>(d);
         launch_counter() += 1;

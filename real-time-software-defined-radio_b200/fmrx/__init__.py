@@ -127,6 +127,7 @@ SIGNATURES = {
     "fmrx_pinned_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "fmrx_pinned_free": (C.c_int, [C.c_void_p]),
     "fmrx_measure_fp32_peak": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "fmrx_measure_pll_chain": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
 }
 
 _LIB = None
@@ -292,6 +293,13 @@ def rds_format_block(block_id, initial_offset, events):
     buf = C.create_string_buffer(16384)
     n = lib().fmrx_rds_format_block(block_id, initial_offset, _p(ev, evp) if ev.size else None, ev.size, buf, 16384)
     return buf.raw[:n].decode()
+
+
+def measure_pll_chain(device=0):
+    """SM cycles per step of one PLL loop's dependency chain, run alone from registers (the PLL kernel's latency roofline)."""
+    v = C.c_double(0)
+    check(lib().fmrx_measure_pll_chain(device, C.byref(v)))
+    return v.value
 
 
 def measure_fp32_peak(kind, device=0, reps=5):
