@@ -408,6 +408,14 @@ def run_fmrx_arm(args, rank, world, local_rank):
             tf = 2.0 * macs * S * B * args.steps / (ms * 1e-3) / 1e12
             pk = peak_muladd if exact else 2.0 * peak_ffma
             ent.update({"tflops": round(tf, 2), "fp32_peak_tflops": round(pk, 2), "frac_fp32": round(tf / pk, 4), "rounding": "mul+add (reference-exact)" if exact else "fma"})
+        if name == "rds_symbols":
+            # SURVEY 8(d) counts the three stages this kernel pair replaces (mixer LPF 15360 x 151, resampler and RRC 3648 x 151
+            # each = 22.3 MAC per complex sample); against that figure -- the work the reference does for the same symbols --
+            ref_macs = (NIF + 2 * NRDS) * NT
+            tf_ref = 2.0 * ref_macs * S * B * args.steps / (ms * 1e-3) / 1e12
+            ent.update({"tflops_survey_algorithmic": round(tf_ref, 2), "frac_fp32_survey_algorithmic": round(tf_ref / (2.0 * peak_ffma), 4),
+                        "note": "tflops / frac_fp32 count the MACs this formulation executes (composite filter at the decoder's sampling instants); "
+                                "the *_survey_algorithmic pair counts the MACs of the three full-rate stages it replaces"})
         gbs = STAGE_BYTES[name] * S * B * args.steps / (ms * 1e-3) / 1e9
         ent.update({"hbm_gbs": round(gbs, 1), "frac_hbm": round(gbs / hbm_peak, 4)})
         per[name] = ent

@@ -417,7 +417,7 @@ int enqueue_chain(fmrx_batch *b, const uint8_t *iq, long long ld_iq, int s0, int
     auto fir = [&](const float *x, const float *x2, float *y, float *zi, int nzi, const float *h, long long ldx, long long ldy, int n, int decim, int kind, int exact, int blocks) {
         FirJob j{};
         j.x = x; j.x2 = x2; j.y = y; j.zi = zi; j.h = h; j.ldx = ldx; j.ldy = ldy; j.nzi = nzi; j.n = n; j.n_blocks = blocks; j.n_streams = ns;
-        j.decim = decim; j.kind = kind; j.exact = exact;
+        j.decim = decim; j.kind = kind; j.exact = exact; j.live_state_only = 1;
         return launch_fir(j, st);
     };
     const bool stereo_live = b->cfg.profile == FMRX_PROFILE_INTENT || b->block_id == 0;  // Q7
@@ -430,7 +430,7 @@ int enqueue_chain(fmrx_batch *b, const uint8_t *iq, long long ld_iq, int s0, int
             ResampleJob r{};
             r.x = IF(b->demod); r.y = AU2(b->mono); r.zi = b->zi_mono + (long long)s0 * b->nzi_a; r.h = b->d_h_mono; r.ldx = ldif; r.ldy = lda;
             r.n = NIF; r.n_ref = NIF; r.ny = b->n_audio; r.n_blocks = nblk; r.n_streams = ns; r.ntaps = b->audio_taps; r.nzi = b->nzi_a;
-            r.decim = b->decim_a; r.up = b->up; r.gain_up = 0; r.exact = ex; r.hp = b->d_hp_mono;
+            r.decim = b->decim_a; r.up = b->up; r.gain_up = 0; r.exact = ex; r.hp = b->d_hp_mono; r.live_state_only = 1;
             LAUNCH(launch_resample(r, st));
         } else {
             LAUNCH(fir(IF(b->demod), nullptr, AU2(b->mono), b->zi_mono + (long long)s0 * b->nzi_a, b->nzi_a, b->h_mono.data(), ldif, lda, NIF, 5, SRC_PLAIN, ex, nblk));
@@ -484,7 +484,7 @@ int enqueue_chain(fmrx_batch *b, const uint8_t *iq, long long ld_iq, int s0, int
                 ResampleJob r{};  // convolveWithDecimMode1(stereo_filt, mixed, stereo_coeff, stereo_initial, 5, 24), :245 (Q14); mode 2: the decimation it meant
                 r.x = IF2(b->mixed); r.y = AU(b->stereo); r.zi = b->zi_stereo + (long long)s0 * b->nzi_a; r.h = b->d_h_stereo; r.ldx = ldif; r.ldy = lda;
                 r.n = NIF; r.n_ref = NIF; r.ny = b->n_audio; r.n_blocks = st_blocks; r.n_streams = ns; r.ntaps = b->audio_taps; r.nzi = b->nzi_a;
-                r.decim = b->cfg.mode == 1 ? 5 : b->decim_a; r.up = b->up; r.gain_up = 0; r.exact = ex; r.hp = b->d_hp_stereo;
+                r.decim = b->cfg.mode == 1 ? 5 : b->decim_a; r.up = b->up; r.gain_up = 0; r.exact = ex; r.hp = b->d_hp_stereo; r.live_state_only = 1;
                 LAUNCH(launch_resample(r, st));
             } else {
                 LAUNCH(fir(IF2(b->mixed), nullptr, AU(b->stereo), b->zi_stereo + (long long)s0 * b->nzi_a, b->nzi_a, b->h_stereo.data(), ldif, lda, NIF, 5, SRC_PLAIN, ex, st_blocks));

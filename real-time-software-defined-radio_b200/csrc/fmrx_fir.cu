@@ -247,9 +247,9 @@ __global__ void __launch_bounds__(NT) fir151_kernel(const FirDev a, const __grid
 
 // state after the launch: zi[i] = formed(x[N - nzi - 1 + i]) of the LAST block (mixer: N - nzi + i, no x2)
 template <int KIND>
-__global__ void fir_state_kernel(const float *x, const float *x2, float *zi, long long ldx, int nzi, int n, int n_blocks) {
+__global__ void fir_state_kernel(const float *x, const float *x2, float *zi, long long ldx, int nzi, int n, int n_blocks, int i0) {
     const int s = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nzi) return;
     const int p = n - nzi + i - ((KIND == SRC_MIX_HALF || KIND == SRC_PROD_HALF) ? 0 : 1);
     if (p < 0) return;  // block shorter than the state: entry keeps its old value (never live for a 151-tap filter)
@@ -703,8 +703,9 @@ int launch_fir_k(const FirJob &j, const FirDev &d, dim3 grid, fmrx_stream_t st) 
     else if (j.decim == 10 && KIND == SRC_PLAIN) e = launch_fir_dk<10, SRC_PLAIN>(j, d, grid, st);
     else return (int)cudaErrorInvalidValue;
     if (e) return e;
-    dim3 sg((j.nzi + 127) / 128, j.n_streams);
-    fir_state_kernel<KIND><<<sg, 128, 0, st>>>(j.x, j.x2, j.zi, j.ldx, j.nzi, j.n, j.n_blocks);
+    const int i0 = j.live_state_only && j.nzi > kHist ? j.nzi - kHist : 0;
+    dim3 sg((j.nzi - i0 + 127) / 128, j.n_streams);
+    fir_state_kernel<KIND><<<sg, 128, 0, st>>>(j.x, j.x2, j.zi, j.ldx, j.nzi, j.n, j.n_blocks, i0);
     launch_counter() += 2;
     return (int)cudaGetLastError();
 }

@@ -37,6 +37,8 @@ struct FirJob {
     const float *h;   // HOST pointer to 151 taps (passed to the kernel by value)
     long long ldx, ldy;
     int nzi, n, n_blocks, n_streams, decim, kind, exact;
+    int live_state_only;  // 1: the state update writes only the entries a later call can read (the last 150); the chain sets it --
+                          // mode 1 sizes these states at 3623 (src/fm_radio.cpp:189-193) and nothing ever reads the rest
 };
 int launch_fir(const FirJob &j, fmrx_stream_t st);
 
@@ -74,6 +76,7 @@ struct ResampleJob {
     // n = samples per block in memory; n_ref = the length the reference's vector had (differs only for the RDS resampler,
     // whose input is the 15361-long mixer output, src/fm_radio.cpp:404-408); ny = outputs per block actually produced
     int n, n_ref, ny, n_blocks, n_streams, ntaps, nzi, decim, up, gain_up, exact;
+    int live_state_only;  // 1: update only the state entries the history map (nzi-1-c)/up, c <= 150, can reach (Q6); set by the chain
 };
 int launch_resample(const ResampleJob &j, fmrx_stream_t st);
 // register-tiled fast path for the RDS 19/80 geometry; returns -1 (nothing launched) when `j` is any other job

@@ -153,10 +153,10 @@ __global__ void __launch_bounds__(256) resample_phase_kernel(const ResDev a, con
     }
 }
 
-__global__ void resample_state_kernel(const ResDev a) {
+__global__ void resample_state_kernel(const ResDev a, int i0, int i1) {
     const int s = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.nzi) return;
+    const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= i1) return;
     const int p = a.n_ref - a.nzi - 1 + i;
     if (p < 0 || p >= a.n) return;
     a.zi[(long long)s * a.nzi + i] = a.x[(long long)s * a.ldx + (long long)(a.n_blocks - 1) * a.n + p];
@@ -322,12 +322,16 @@ int launch_resample(const ResampleJob &j, fmrx_stream_t st) {
     const int p0 = j.n_ref - j.nzi - 1;
     const bool vec = (j.nzi & 3) == 0 && (p0 & 3) == 0 && p0 >= 0 && p0 + j.nzi <= j.n && (j.ldx & 3) == 0 && (j.n & 3) == 0 &&
                      (((uintptr_t)j.x | (uintptr_t)j.zi) & 15) == 0;
-    if (vec) {
+    if (j.live_state_only && j.nzi > kTaps) {  // entries (nzi-1-c)/up, c = 0..150
+        const int i0 = (j.nzi - kTaps) / j.up, i1 = (j.nzi - 1) / j.up + 1;
+        dim3 sg((i1 - i0 + 255) / 256, j.n_streams);
+        resample_state_kernel<<<sg, 256, 0, st>>>(d, i0, i1);
+    } else if (vec) {
         dim3 sg((j.nzi / 4 + 255) / 256, j.n_streams);
         resample_state4_kernel<<<sg, 256, 0, st>>>(d);
     } else {
         dim3 sg((j.nzi + 255) / 256, j.n_streams);
-        resample_state_kernel<<<sg, 256, 0, st>>>(d);
+        resample_state_kernel<<<sg, 256, 0, st>>>(d, 0, j.nzi);
     }
     launch_counter() += 1;
     return (int)cudaGetLastError();
