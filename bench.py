@@ -432,8 +432,8 @@ def run_fmrx_arm(args, rank, world, local_rank):
     roofline = {
         "bound": "fp32", "kernel": top, "achieved": per[top]["tflops"], "peak": per[top]["fp32_peak_tflops"], "unit": "TFLOP/s", "frac": per[top]["frac_fp32"],
         # dram__bytes_read.sum + dram__bytes_write.sum of one front-end launch (4096 stations x 1 block) from the committed
-        # `ncu --set full` capture profiles/r3g_kernels.md: 1.390 GB + 0.241 GB, against 1.510 GB algorithmic
-        "traffic": 1.632e9 * (S * B / 4096.0) if top == "frontend" else None, "traffic_unit": "bytes per launch (ncu, profiles/r3g_kernels.md)",
+        # `ncu --set full` capture profiles/r3m_kernels.md: 1.390 GB + 0.241 GB, against 1.510 GB algorithmic
+        "traffic": 1.632e9 * (S * B / 4096.0) if top == "frontend" else None, "traffic_unit": "bytes per launch (ncu, profiles/r3m_kernels.md)",
         "algorithmic_bytes": STAGE_BYTES[top] * S * B,
         "peak_source": "measured in this run by fmrx_measure_fp32_peak: %.2f T FFMA/s (x2 flop), %.2f T FMUL+FADD lane-ops/s; a stage that keeps the "
                        "reference's two roundings per tap is bounded by the latter" % (peak_ffma, peak_muladd),
@@ -467,7 +467,8 @@ def run_fmrx_arm(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100, help="timed steps; the default follows SURVEY 8(d): throughput sustained over >= 100 blocks per stream "
+                    "(the three-phase pipeline needs about two steps to fill, which a 10-step run still shows as +8 %% per step)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="fmrx", choices=["fmrx", "reference"])
     ap.add_argument("--stations", type=int, default=4096, help="stations per GPU")

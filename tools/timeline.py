@@ -1,4 +1,4 @@
-"""Pipelined device-resident run with a per-stage timeline: python tools/timeline.py [stations] [steps]"""
+"""Pipelined device-resident run with a per-stage timeline: python tools/timeline.py [stations] [steps] [mode]"""
 import os
 import sys
 
@@ -10,10 +10,11 @@ import fmrx  # noqa: E402
 
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+mode = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 dev = torch.device("cuda", 0)
 iq = torch.randint(0, 256, (S, fmrx.BLOCK_BYTES), dtype=torch.uint8, device=dev)
 torch.cuda.synchronize()
-rx = fmrx.Batch(S, mode=0, profile=fmrx.PROFILE_INTENT, max_blocks=1)
+rx = fmrx.Batch(S, mode=mode, profile=fmrx.PROFILE_INTENT, max_blocks=1)
 for _ in range(3):
     rx.process_device(iq.data_ptr(), 1, None)
 rx.sync()
