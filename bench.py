@@ -397,6 +397,21 @@ def run_fmrx_arm(args, rank, world, local_rank):
         torch.cuda.empty_cache()
         return out
 
+    # ---- one station alone (BASELINE configs 1-4 are single-stream): host bytes in, host audio + RDS out, one 64 ms block
+    # per call through the synchronous entry point -- the latency a live receiver sees per block
+    single = None
+    if rank == 0 and not args.skip_mode1:
+        one = d_iq[0].cpu().numpy()
+        with fmrx.Batch(1, mode=0, profile=fmrx.PROFILE_INTENT, max_blocks=1, device=local_rank) as r1:
+            for _ in range(3):
+                r1.process(one[:BLOCK_BYTES])
+            t0 = time.perf_counter()
+            for _ in range(20):
+                r1.process(one[:BLOCK_BYTES])
+            ms_blk = (time.perf_counter() - t0) / 20 * 1e3
+        single = {"ms_per_block": round(ms_blk, 3), "block_ms_of_signal": 64.0, "realtime_factor": round(64.0 / ms_blk, 1),
+                  "msps": round(BLOCK_IQ / (ms_blk * 1e-3) / 1e6, 1), "path": "fmrx_batch_process, 1 station x 1 block per call, host buffers, mono+stereo+rds"}
+
     mode1 = mode2 = None
     if not args.skip_mode1:
         rx.close()
@@ -464,7 +479,7 @@ def run_fmrx_arm(args, rank, world, local_rank):
                    "l2": "input per step %.2f GB >> 126 MB L2, no flush needed" % (S * B * BLOCK_BYTES / 1e9), "input_reuse": "same synthesised block replayed each step, state carried",
                    "synth_seconds": round(t_synth, 2), "parity_spot_check": parity, "rank0_numa_node": numa,
                    "e2e_timer": "host clock around K fmrx_batch_submit calls with fmrx_batch_wait on the previous step (two steps in flight), barrier + synchronize on both sides, max over ranks",
-                   "e2e_sync_call_msps": round(e2e_sync_value, 1), "e2e_link": link, "mode1": mode1, "mode2_44k1": mode2},
+                   "e2e_sync_call_msps": round(e2e_sync_value, 1), "e2e_link": link, "single_stream": single, "mode1": mode1, "mode2_44k1": mode2},
         "e2e": {"value": round(e2e_value, 1), "unit": "Msps", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world},  # whole job, like `value`
         "gpu_launches": int(launches),
         "clocks": clocks,
