@@ -374,3 +374,33 @@ def test_rds_symbol_rate_path_equals_staged(nblk):
         worst = float(np.max(np.abs(symf - syms)) / np.sqrt(np.mean(syms ** 2)))
         print(f"nblk {nblk} call {c}: symbols rel-rms {err:.3g}, worst {worst:.3g}")
         assert err < 2e-6 and worst < 2e-5
+
+
+def test_batch_argument_errors_and_ragged_shapes():
+    """The C-ABI never exits or falls back: bad arguments come back as status codes with a message; batch sizes that
+    are not multiples of anything (7 stations; 97 = chunked path with uneven chunks) give the same per-station results
+    as the same stations processed alone."""
+    import ctypes as C
+
+    with pytest.raises(fmrx.FmrxError, match="mode"):
+        fmrx.Batch(1, mode=3)
+    with pytest.raises(fmrx.FmrxError):
+        fmrx.Batch(0)
+    with pytest.raises(fmrx.FmrxError, match="device"):
+        fmrx.Batch(1, device=99)
+    with fmrx.Batch(2, mode=0, profile=1, max_blocks=2) as rx:
+        with pytest.raises(fmrx.FmrxError, match="n_blocks"):
+            rx.process(np.zeros((2, 3 * 307200), np.uint8))   # more blocks than the handle was sized for
+        assert fmrx.lib().fmrx_batch_process(rx.h, None, 1, None) != 0
+        assert b"null" in fmrx.lib().fmrx_last_error()
+    raw1 = synth.synth_station(3, 2, 0)
+    ref = None
+    for S in (1, 7, 97):
+        raw = np.stack([raw1 if s == S - 1 else np.roll(raw1, 2 * (s + 1)) for s in range(S)])
+        with fmrx.Batch(S, mode=0, profile=1, max_blocks=2) as rx:
+            res = rx.process(raw)
+        last = (res["audio"][S - 1].copy(), res["rds_bits"][S - 1].copy(), res["rds_n_bits"][S - 1].copy())
+        if ref is None:
+            ref = last
+        for a, b in zip(last, ref):
+            assert np.array_equal(a, b), f"station processed in a batch of {S} differs from the same station alone"

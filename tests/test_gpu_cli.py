@@ -54,3 +54,20 @@ def test_cli_rds_info_reports_the_programme():
     assert rc == 0, err
     line = [l for l in err.splitlines() if l.startswith("RDS: ")]
     assert len(line) == 1 and 'PI BEEF PTY 3 TP 0 PS "CLI TEST" RT "radiotext through the executable"' in line[0], err
+
+
+def test_cli_empty_and_short_input():
+    """Q9, normalised: only whole 307200-byte blocks are processed -- no input or less than one block gives no audio,
+    exit 0, and still the reference's banner lines."""
+    for n in (0, 1000, 307199):
+        audio, err, rc = run_cli([], np.zeros(n, np.uint8))
+        assert rc == 0 and audio.size == 0, (n, err)
+        lines = err.splitlines()
+        assert lines[0] == "1" and lines[1] == "Operating in mode 0" and lines[2] == "rf_Fs = 2400000"
+
+
+def test_cli_rejects_what_the_reference_rejects():
+    """src/fm_radio.cpp:736-764: exactly "1" selects mode 1; "0", "2", words and unknown options end with exit code 1"""
+    for args in (["0"], ["2"], ["stereo"], ["--no-such-option"], ["1", "--audio-rate", "12345"]):
+        r = subprocess.run([fmrx.CLI_PATH] + args, input=b"", capture_output=True, timeout=60)
+        assert r.returncode == 1 and not r.stdout, args
