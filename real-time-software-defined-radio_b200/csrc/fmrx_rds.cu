@@ -30,10 +30,10 @@ struct ResDev {
 };
 
 template <bool EXACT>
-__global__ void resample_kernel(const ResDev a) {
+__global__ void resample_kernel(const ResDev a, int o_count) {  // outputs o < o_count of every block (o_count = a.ny: all of them)
     const int s = blockIdx.z, b = blockIdx.y;
     const int o = blockIdx.x * blockDim.x + threadIdx.x;
-    if (o >= a.ny) return;
+    if (o >= o_count) return;
     const float *xs = a.x + (long long)s * a.ldx;
     const float *zs = a.zi + (long long)s * a.nzi;
     const long long base = (long long)a.decim * o;
@@ -73,8 +73,24 @@ __global__ void resample_kernel(const ResDev a) {
 constexpr int TPP_ = kTaps;           // taps per phase
 constexpr int HPITCH = kTaps + 1;     // phase-major table pitch
 
+// the exact tap on a pair of lanes, as in csrc/fmrx_fir.cu: fma(x, h, -0) is the rounded product and fma(p, 1, acc) the
+// rounded sum; the -0 and the 1 are kernel parameters so that ptxas cannot fold the pair into one FFMA2 (one rounding)
+struct PairConst {
+    float negzero, one;
+};
+template <bool EXACT>
+__device__ __forceinline__ float2 pair_mac(float2 acc, float2 x, float h, const PairConst &k) {
+    if (EXACT) {
+        const float2 p = __ffma2_rn(x, make_float2(h, h), make_float2(k.negzero, k.negzero));
+        return __ffma2_rn(p, make_float2(k.one, k.one), acc);
+    }
+    return __ffma2_rn(x, make_float2(h, h), acc);
+}
+
 template <bool EXACT, bool SKEW>
-__global__ void __launch_bounds__(256) resample_phase_kernel(const ResDev a, const float *__restrict__ hp) {
+__global__ void __launch_bounds__(256) resample_phase_kernel(const ResDev a, const float *__restrict__ hp, const PairConst pk, int o_skip) {
+    // o_skip: outputs below it are left to the general kernel (the launcher sets it to the number of outputs that reach
+    // into the history when there are few of them, so that every task here runs the all-in-block loop)
     constexpr int skew = SKEW ? 1 : 0;
     extern __shared__ float xs_sh[];                       // block b of the stream, index p + skew * (p / D)
     __shared__ __align__(16) float hist[TPP_ + 1];         // history value for tap count c (Q6)
@@ -99,11 +115,58 @@ __global__ void __launch_bounds__(256) resample_phase_kernel(const ResDev a, con
     const int chunks = ((a.ny + U - 1) / U + 31) / 32;     // 32 values of m per task
     float *ys = a.y + (long long)s * a.ldy + (long long)b * a.ny;
     float *wt = wtaps[warp];
+    if (!SKEW) {
+        // odd D (modes 1): a lane owns TWO outputs of the residue, m and m + 32, and runs them as one packed pair -- half
+        // the FP32 instructions and half the tap loads per MAC; the lane stride inside each half stays D
+        const int chunks2 = ((a.ny + U - 1) / U + 63) / 64;
+        const int qmin = TPP_ - 1;
+        for (int task = warp; task < U * chunks2; task += 8) {
+            const int r = task / chunks2, ma = 64 * (task % chunks2) + lane, mb = ma + 32;
+            const int oa = r + U * ma, ob = r + U * mb;
+            const int ph = (D * r) % U, qr = (D * r) / U;
+            const bool va = oa < a.ny && oa >= o_skip, vb = ob < a.ny && ob >= o_skip;
+            const int q0a = va ? qr + D * ma : 0x3fffffff, q0b = vb ? qr + D * mb : 0x3fffffff;
+            __syncwarp();
+            for (int i2 = lane; i2 < HPITCH; i2 += 32) wt[i2] = __ldg(hp + (long long)ph * HPITCH + i2);
+            __syncwarp();
+            float2 acc = make_float2(0.0f, 0.0f);
+            if (__all_sync(0xffffffffu, q0a >= qmin && q0b >= qmin)) {
+                const float *xa = xs_sh + (va ? q0a : TPP_), *xb2 = xs_sh + (vb ? q0b : TPP_);
+#pragma unroll 2
+                for (int c = 0; c + 4 <= TPP_; c += 4) {
+                    const float4 t = *reinterpret_cast<const float4 *>(wt + c);
+                    acc = pair_mac<EXACT>(acc, make_float2(xa[-c], xb2[-c]), t.x, pk);
+                    acc = pair_mac<EXACT>(acc, make_float2(xa[-c - 1], xb2[-c - 1]), t.y, pk);
+                    acc = pair_mac<EXACT>(acc, make_float2(xa[-c - 2], xb2[-c - 2]), t.z, pk);
+                    acc = pair_mac<EXACT>(acc, make_float2(xa[-c - 3], xb2[-c - 3]), t.w, pk);
+                }
+#pragma unroll
+                for (int c = TPP_ / 4 * 4; c < TPP_; ++c) acc = pair_mac<EXACT>(acc, make_float2(xa[-c], xb2[-c]), wt[c], pk);
+            } else {                                        // some lane reaches into the history: branch-free select per tap
+                auto tap2 = [&](int c, float t, float hv) {
+                    const int da = q0a - c, db = q0b - c;   // >= 0: inside the block
+                    const float xva = xs_sh[da >= 0 ? da : 0], xvb = xs_sh[db >= 0 ? db : 0];
+                    acc = pair_mac<EXACT>(acc, make_float2(da >= 0 ? xva : hv, db >= 0 ? xvb : hv), t, pk);
+                };
+#pragma unroll 2
+                for (int c = 0; c + 4 <= TPP_; c += 4) {
+                    const float4 t = *reinterpret_cast<const float4 *>(wt + c), hv = *reinterpret_cast<const float4 *>(hist + c);
+                    tap2(c, t.x, hv.x); tap2(c + 1, t.y, hv.y); tap2(c + 2, t.z, hv.z); tap2(c + 3, t.w, hv.w);
+                }
+#pragma unroll
+                for (int c = TPP_ / 4 * 4; c < TPP_; ++c) tap2(c, wt[c], hist[c]);
+            }
+            if (a.gain_up) { acc.x = __fmul_rn(acc.x, (float)U); acc.y = __fmul_rn(acc.y, (float)U); }
+            if (va) ys[oa] = acc.x;
+            if (vb) ys[ob] = acc.y;
+        }
+        return;
+    }
     for (int task = warp; task < U * chunks; task += 8) {
         const int r = task / chunks, m = 32 * (task % chunks) + lane;
         const int o = r + U * m;
         const int ph = (D * r) % U, qr = (D * r) / U;       // q0 = qr + D*m, qr < D
-        const bool valid = o < a.ny;
+        const bool valid = o < a.ny && o >= o_skip;
         const int q0 = valid ? qr + D * m : 0x3fffffff;
         const int at = valid ? q0 + skew * m : TPP_;        // staged index of x[q0] (q0 / D = m); idle lanes read inside the block
         // this phase's 151 taps: one coalesced read per warp, then broadcast reads from shared memory
@@ -310,11 +373,24 @@ int launch_resample(const ResampleJob &j, fmrx_stream_t st) {
                             : (skew ? resample_phase_kernel<false, true> : resample_phase_kernel<false, false>);
         cudaError_t ea = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (ea) return (int)ea;
-        kern<<<dim3(j.n_blocks, j.n_streams), 256, smem, st>>>(d, j.hp);
+        // outputs whose taps reach into the history: o < ceil(150 * U / D).  When they are a handful (29 of 2949 for x24 /125)
+        // they go to the general kernel so that every task of the phase kernel runs its all-in-block loop; the Q14 call
+        // (x24 /5: 720 of 2949) keeps them in the phase kernel's select loop, and so does x147 /800 (28 outputs, but the
+        // general kernel gathers from an 89 KB tap table there: 0.2 ms for them against 0.05 ms in the select loop)
+        int o_edge = (int)(((long long)(kTaps - 1) * j.up + j.decim - 1) / j.decim);
+        if (o_edge > j.ny) o_edge = j.ny;
+        const int o_skip = (!skew && o_edge <= 64) ? o_edge : 0;
+        kern<<<dim3(j.n_blocks, j.n_streams), 256, smem, st>>>(d, j.hp, PairConst{-0.0f, 1.0f}, o_skip);
         launch_counter() += 1;
+        if (o_skip > 0) {
+            dim3 ge(1, j.n_blocks, j.n_streams);
+            if (j.exact) resample_kernel<true><<<ge, 64, 0, st>>>(d, o_skip);
+            else resample_kernel<false><<<ge, 64, 0, st>>>(d, o_skip);
+            launch_counter() += 1;
+        }
     } else if (fast < 0) {
-        if (j.exact) resample_kernel<true><<<grid, 128, 0, st>>>(d);
-        else resample_kernel<false><<<grid, 128, 0, st>>>(d);
+        if (j.exact) resample_kernel<true><<<grid, 128, 0, st>>>(d, j.ny);
+        else resample_kernel<false><<<grid, 128, 0, st>>>(d, j.ny);
         launch_counter() += 1;
     }
     cudaError_t e = cudaGetLastError();
