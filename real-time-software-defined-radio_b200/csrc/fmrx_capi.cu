@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <algorithm>
 #include <vector>
 
 #include "fmrx_internal.h"
@@ -655,19 +656,24 @@ int fmrx_batch_create(const fmrx_config *cfg, fmrx_batch **out) {
         CU(cudaDeviceGetStreamPriorityRange(&least, &greatest));
         if (const char *e = getenv("FMRX_PIPE_PRIO")) { if (e[0] == '0') greatest = least; }  // experiment switch: equal priorities
         const int mid = greatest < least ? greatest + 1 : least;
-        // FMRX_PLL_SMS: SMs set aside for the PLL stream (0 = no partition); default 32 once the batch fills the device
-        // two PLL warps per scheduler: 32 SMs for the 8192 loops of 4096 stations with stereo + RDS
+        // FMRX_PLL_SMS: SMs set aside for the PLL stream (0 = no partition).  Default: the split that minimises
+        // max(PLL phase, filter phases) under the measured cost model: the PLL kernel takes 3.9 / 5.0 / 7.0 / 9.4 ms
+        // per 64 ms block at 1 / 2 / 3 / 4 warps per scheduler (one warp = 32 loops), the filters of 4096 stations take
+        // f ms on the whole device and scale with the SMs they are left with.  4096 stations, stereo + RDS: 32 / 116.
         int pll_sms = 0;
-        if (b->S >= 1024 && b->audio_on) {
-            const int loops = b->S * (b->rds_on ? 2 : 1), warps = (loops + 31) / 32;
-            pll_sms = ((warps + 7) / 8 + 7) / 8 * 8;  // warps / (4 schedulers x 2), rounded up to the split granularity
-            // only the pilot loop (mode 1, or RDS off): its filters are light enough to give the PLLs one warp per scheduler
-            // (3.9 instead of 5.0 ms) -- 16 / 32 SMs: 5.04 / 4.75 ms per step
-            if (!b->rds_on) pll_sms *= 2;
-            if (pll_sms > 64) pll_sms = 64;
-            // mode 2 is bound by its filters (the x147 resamplers): the PLLs can run three warps per scheduler on fewer SMs
-            // (sweep 24 / 32 / 40 SMs: 7.32 / 7.77 / 8.24 ms per step)
-            if (cfg->mode == 2 && pll_sms > 24) pll_sms = 24;
+        if (b->S >= 1024 && (b->audio_on || b->rds_on)) {
+            const int loops = b->S * ((b->audio_on ? 1 : 0) + (b->rds_on ? 1 : 0)), warps = (loops + 31) / 32;
+            const double f_audio = cfg->mode == 0 ? 1.52 : cfg->mode == 1 ? 2.35 : 2.97;
+            const double f_ms = (1.43 + (b->audio_on ? f_audio : 0.0) + (b->rds_on ? 1.09 : 0.0)) * b->S / 4096.0;
+            int sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+            double best = 1e30;
+            for (int p = 8; p <= 64 && p < sms; p += 8) {
+                const int w = (warps + 4 * p - 1) / (4 * p);
+                const double t_pll = w <= 1 ? 3.9 : w == 2 ? 5.0 : w == 3 ? 7.0 : w == 4 ? 9.4 : 2.35 * w;
+                const double t = std::max(t_pll, f_ms * sms / (sms - p));
+                if (t < best * 0.98) { best = t; pll_sms = p; }   // ties go to the smaller partition
+            }
         }
         if (const char *e = getenv("FMRX_PLL_SMS")) pll_sms = atoi(e);
         if (pll_sms > 0) {
