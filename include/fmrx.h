@@ -39,7 +39,9 @@ typedef enum {
     FMRX_ERR_ARG = -1,    /* bad argument (null pointer, unsupported size) */
     FMRX_ERR_CUDA = -2,   /* CUDA runtime / driver error, or no device */
     FMRX_ERR_ALLOC = -3,  /* device or pinned-host allocation failed */
-    FMRX_ERR_STATE = -4   /* handle used in the wrong state */
+    FMRX_ERR_STATE = -4,  /* handle used in the wrong state */
+    FMRX_ERR_TIMEOUT = -5, /* fmrx_ring_acquire / fmrx_ring_next: nothing became available in time */
+    FMRX_ERR_EOF = -6     /* fmrx_ring_next after fmrx_ring_close: every committed step has been delivered */
 } fmrx_status;
 
 const char *fmrx_last_error(void);
@@ -198,6 +200,26 @@ int fmrx_batch_stage_times(fmrx_batch *, double *ms /*[FMRX_STAGE_COUNT]*/, long
 size_t fmrx_batch_state_bytes(const fmrx_batch *);
 int fmrx_batch_get_state(fmrx_batch *, void *blob);
 int fmrx_batch_set_state(fmrx_batch *, const void *blob);
+
+/* ---- ingest / egress ring ------------------------------------------------------------------
+ * A bounded ring of page-locked host slots in front of a batch handle: what replaces rf_thread -> queue -> consumer
+ * threads (src/fm_radio.cpp:86-138: five-slot ring, condition variables) when one process feeds many stations.
+ * ONE producer thread acquires a free slot (blocking while every slot is in flight: that is the back-pressure the
+ * reference gets from its bounded queues), fills iq[S][n_blocks][307200] and commits it, which enqueues the H2D copy,
+ * the three-phase pipeline and the D2H copy of the results; ONE consumer thread (the same or another) takes the steps in
+ * order with fmrx_ring_next -- it blocks until that step's results are in the slot's host buffers -- and releases the
+ * slot for reuse.  While a ring is attached no other process / submit call may be made on the handle. */
+typedef struct fmrx_ring fmrx_ring;
+int fmrx_ring_create(fmrx_batch *, int n_slots, int n_blocks, fmrx_ring **out);
+void fmrx_ring_destroy(fmrx_ring *);
+int fmrx_ring_acquire(fmrx_ring *, int timeout_ms, uint8_t **iq);   /* producer; timeout_ms < 0: wait for ever; FMRX_ERR_TIMEOUT */
+int fmrx_ring_commit(fmrx_ring *);                                   /* producer: submit the acquired slot */
+int fmrx_ring_close(fmrx_ring *);                                    /* producer: end of input */
+/* consumer: oldest committed step.  `out` receives pointers into the slot's pinned buffers (audio, rds_bits, rds_n_bits,
+ * rds_events, rds_n_events; audio_f is not carried), valid until fmrx_ring_release.  FMRX_ERR_TIMEOUT / FMRX_ERR_EOF. */
+int fmrx_ring_next(fmrx_ring *, int timeout_ms, fmrx_outputs *out);
+int fmrx_ring_release(fmrx_ring *);
+int fmrx_ring_in_flight(fmrx_ring *);                                /* committed and not yet released */
 
 /* page-locked host memory for the ingest / egress rings (fmrx_batch_process copies asynchronously only from/to it) */
 int fmrx_pinned_alloc(void **ptr, size_t bytes);

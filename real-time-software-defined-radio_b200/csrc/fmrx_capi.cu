@@ -546,6 +546,12 @@ int copy_outputs(fmrx_batch *b, int s0, int ns, int nblk, const fmrx_outputs &o,
 
 }  // namespace
 
+namespace fmrx {
+void batch_shape(const fmrx_batch *b, int *n_streams, int *max_blocks, int *audio_per_block, int *audio_on, int *rds_on) {
+    *n_streams = b->S; *max_blocks = b->NB; *audio_per_block = b->n_audio; *audio_on = b->audio_on ? 1 : 0; *rds_on = b->rds_on ? 1 : 0;
+}
+}  // namespace fmrx
+
 extern "C" {
 
 int fmrx_batch_create(const fmrx_config *cfg, fmrx_batch **out) {

@@ -129,6 +129,8 @@ int launch_rds_fast(const RdsFastJob &j, fmrx_stream_t st);
 
 int measure_fp32_peak(int device, int kind, int reps, double *tera);
 int measure_pll_chain(double *cycles_per_step);
+// shape of a batch handle, for the host-side layers that sit on top of the C-ABI (fmrx_ring.cpp)
+void batch_shape(const fmrx_batch *b, int *n_streams, int *max_blocks, int *audio_per_block, int *audio_on, int *rds_on);
 
 // SM partition (green contexts) for the device-resident pipeline, fmrx_partition.cu.  partition_create returns nullptr
 // when the driver cannot split the device; the caller then falls back to priority streams on the whole device.

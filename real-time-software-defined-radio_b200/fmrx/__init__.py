@@ -128,6 +128,14 @@ SIGNATURES = {
     "fmrx_pinned_free": (C.c_int, [C.c_void_p]),
     "fmrx_measure_fp32_peak": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "fmrx_measure_pll_chain": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
+    "fmrx_ring_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "fmrx_ring_destroy": (None, [C.c_void_p]),
+    "fmrx_ring_acquire": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "fmrx_ring_commit": (C.c_int, [C.c_void_p]),
+    "fmrx_ring_close": (C.c_int, [C.c_void_p]),
+    "fmrx_ring_next": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "fmrx_ring_release": (C.c_int, [C.c_void_p]),
+    "fmrx_ring_in_flight": (C.c_int, [C.c_void_p]),
 }
 
 _LIB = None
@@ -557,3 +565,70 @@ class Batch:
         blob = np.ascontiguousarray(blob, np.uint8)
         check(lib().fmrx_batch_set_state(self.h, blob.ctypes.data_as(C.c_void_p)))
         self.block_id = int(blob[:8].view(np.int64)[0])
+
+
+ERR_TIMEOUT, ERR_EOF = -5, -6
+
+
+class Ring:
+    """Bounded ring of pinned host slots in front of a Batch (fmrx_ring_*): one producer thread acquires / fills /
+    commits, one consumer thread takes the steps in order.  `acquire` and `next` return numpy views of the slot's
+    pinned buffers; `next` returns None at end of input (after close()).  timeout_ms < 0 waits for ever; a timeout
+    raises TimeoutError."""
+
+    def __init__(self, batch: "Batch", n_slots=4, n_blocks=1):
+        self.batch, self.n_blocks = batch, n_blocks
+        self.h = C.c_void_p()
+        check(lib().fmrx_ring_create(batch.h, n_slots, n_blocks, C.byref(self.h)))
+
+    def close_ring(self):
+        if getattr(self, "h", None) and self.h.value:
+            lib().fmrx_ring_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close_ring()
+
+    @staticmethod
+    def _status(st):
+        if st == ERR_TIMEOUT:
+            raise TimeoutError(lib().fmrx_last_error().decode())
+        check(st)
+
+    def acquire(self, timeout_ms=-1):
+        p = C.c_void_p()
+        self._status(lib().fmrx_ring_acquire(self.h, timeout_ms, C.byref(p)))
+        n = self.batch.S * self.n_blocks * BLOCK_BYTES
+        return np.ctypeslib.as_array(C.cast(p, u8p), shape=(n,)).reshape(self.batch.S, self.n_blocks * BLOCK_BYTES)
+
+    def commit(self):
+        check(lib().fmrx_ring_commit(self.h))
+
+    def close(self):
+        check(lib().fmrx_ring_close(self.h))
+
+    def next(self, timeout_ms=-1):
+        o = Outputs()
+        st = lib().fmrx_ring_next(self.h, timeout_ms, C.byref(o))
+        if st == ERR_EOF:
+            return None
+        self._status(st)
+        S, B, na = self.batch.S, self.n_blocks, self.batch.n_audio
+        res = {}
+        if o.audio:
+            res["audio"] = np.ctypeslib.as_array(o.audio, shape=(S, B, 2 * na))
+        if o.rds_bits:
+            res["rds_bits"] = np.ctypeslib.as_array(o.rds_bits, shape=(S, B, MAX_BITS))
+            res["rds_n_bits"] = np.ctypeslib.as_array(o.rds_n_bits, shape=(S, B))
+            res["rds_n_events"] = np.ctypeslib.as_array(o.rds_n_events, shape=(S, B))
+        return res
+
+    def release(self):
+        check(lib().fmrx_ring_release(self.h))
+
+    @property
+    def in_flight(self):
+        return lib().fmrx_ring_in_flight(self.h)
