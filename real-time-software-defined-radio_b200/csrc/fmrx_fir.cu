@@ -622,11 +622,14 @@ __global__ void __launch_bounds__(128) frontend_edge_kernel(const IqDev a, const
     const int b = live ? sbi % a.n_blocks : 0, s = live ? sbi / a.n_blocks : 0;
     float yi = 0.0f, yq = 0.0f;
     if (live) {
-#pragma unroll 1
-        for (int k = 0; k < kTaps; ++k) {
-            const float2 v = source_iq<true>(a, s, b, 10 * n - k);
-            yi = mac<EXACT>(yi, v.x, taps.h[k]);
-            yq = mac<EXACT>(yq, v.y, taps.h[k]);
+        // the loads do not depend on the sums: fetch eight samples at a time, then accumulate in order
+        for (int k0 = 0; k0 < kTaps; k0 += 8) {
+            float2 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = k0 + u < kTaps ? source_iq<true>(a, s, b, 10 * n - k0 - u) : make_float2(0.0f, 0.0f);
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (k0 + u < kTaps) { yi = mac<EXACT>(yi, v[u].x, taps.h[k0 + u]); yq = mac<EXACT>(yq, v[u].y, taps.h[k0 + u]); }
         }
     }
     float pi_ = __shfl_up_sync(0xffffffffu, yi, 1, EDGE_OUT), pq_ = __shfl_up_sync(0xffffffffu, yq, 1, EDGE_OUT);
