@@ -38,7 +38,8 @@ def main():
     rf_coeff = signal.firwin(rf_taps, rf_Fc / (rf_Fs / 2), window=("hann"))
     audio_coeff = signal.firwin(audio_taps, audio_Fc / (audio_Fs / 2), window=("hann"))
     bp = signal.firwin(rf_taps, [18.5e3 / (audio_Fs / 2), 19.5e3 / (audio_Fs / 2)], window=("hann"), pass_zero="bandpass")
-    si, sq, sa, sr = (np.zeros(rf_taps - 1) for _ in range(4))
+    ext = signal.firwin(rf_taps, [22e3 / (audio_Fs / 2), 54e3 / (audio_Fs / 2)], window=("hann"), pass_zero="bandpass")
+    si, sq, sa, sr, se, ss = (np.zeros(rf_taps - 1) for _ in range(6))
     phase = 0.0
     pll_state = [0.0, 0.0, 1.0, 0.0, 1.0, 0.0]
     d = dict(rf_coeff=rf_coeff, audio_coeff=audio_coeff, bp_coeff=bp, nblk=NBLK, block=BLOCK)
@@ -52,7 +53,20 @@ def main():
         audio_block = audio_filt[::audio_decim]
         bpf, sr = signal.lfilter(bp, 1.0, fm_demod, zi=sr)
         nco, ncoq, pll_state = fmPll(bpf, 19e3, 240e3, pll_state, 2)
-        d[f"i_ds_{b}"], d[f"demod_{b}"], d[f"audio_{b}"], d[f"pilot_{b}"], d[f"nco_{b}"] = i_ds, fm_demod, audio_block, bpf, nco
+        d[f"i_ds_{b}"], d[f"demod_{b}"], d[f"audio_{b}"], d[f"pilot_{b}"], d[f"nco_{b}"] = i_ds, fm_demod, audio_block.copy(), bpf, nco
+        # stereo channel extraction, mixing, low-pass, decimation and the combiner exactly as the script writes them
+        # (fmMonoBlock.py:150-175) -- including `combined_l_block, combined_r_block = audio_block, audio_block`, which makes
+        # all three names one array, so that what the script stores in combined_l AND combined_r is (audio - stereo) / 4
+        bpf_ext, se = signal.lfilter(ext, 1.0, fm_demod, zi=se)
+        mixed = np.multiply(nco[0:len(bpf_ext):1], bpf_ext) * 2
+        stereo_filt, ss = signal.lfilter(audio_coeff, 1.0, mixed, zi=ss)
+        stereo_block = stereo_filt[::5]
+        combined_l_block, combined_r_block = audio_block, audio_block
+        for i in range(len(audio_block)):
+            combined_l_block[i] = (audio_block[i] + stereo_block[i]) / 2
+            combined_r_block[i] = (audio_block[i] - stereo_block[i]) / 2
+        d[f"stereo_{b}"], d[f"combined_{b}"] = stereo_block, combined_l_block.copy()
+        assert combined_l_block is combined_r_block
     d["phase"], d["pll_state"] = phase, np.array(pll_state)
     # the RDS resampler's arithmetic (fmRDSblock.py:188-199): zero-stuff by 19, anti-image lfilter, [::80], x19
     rng = np.random.default_rng(8)
