@@ -138,6 +138,59 @@ def cpu_reference_run(n_blocks, procs, mode=0):
     return procs * n_blocks * BLOCK_IQ / dt / 1e6, kind, dt
 
 
+def cpu_stage_times(reps=3):
+    """the reference's own functions (oracle/_ref/libfmref.so: the unmodified reference objects behind a
+    C shim; the oracle port where that was not built) on ONE host core, one mode-0 block, per stage of the chain --
+    milliseconds per block, the figure to hold against the GPU's stage time / stations.  Returns (dict, kind)."""
+    from fmrx import synth
+    from oracle.ref import ref_available
+
+    if ref_available():
+        from oracle.ref import Ref
+        r, kind = Ref(), "reference"
+    else:
+        from oracle import Port
+        r, kind = Port(), "port"
+    F = np.float32
+    raw = synth.synth_iq(1, 0, seed=1)
+    z = lambda n=150: np.zeros(n, F)  # noqa: E731
+    h_rf, h_a = r.lpf(2.4e6, 1e5, 151), r.lpf(240e3, 16e3, 151)
+    h_p, h_s = r.bpf(18.5e3, 19.5e3, 240e3, 151), r.bpf(22e3, 54e3, 240e3, 151)
+    h_r, h_q, h_l = r.bpf(54e3, 60e3, 240e3, 151), r.bpf(113.5e3, 114.5e3, 240e3, 151), r.lpf(240e3, 3e3, 151)
+    h_anti, h_rrc = r.lpf(240e3 * 19, 57000 // 2, 151 * 19), r.rrc(57e3, 151)
+    pll0 = lambda: np.array([0, 0, 1, 0, 0, 1], F)  # noqa: E731
+    phase = F(float(F(np.pi / 3.3 - np.pi / 1.5)) - np.pi / 1.4)
+    out = {}
+
+    def timed(name, fn):
+        best, res = 1e9, None
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            res = fn()
+            best = min(best, time.perf_counter() - t0)
+        out[name] = round(best * 1e3, 3)
+        return res
+
+    iq = timed("unpack", lambda: r.unpack(raw))
+    i_, q_ = iq[0::2].copy(), iq[1::2].copy()
+    yi, yq = timed("frontend_fir", lambda: r.fir_decim_iq(i_, q_, h_rf, z(), z(), 10))
+    demod = timed("discriminator", lambda: r.demod(yi, yq))
+    out["frontend"] = round(out["unpack"] + out["frontend_fir"] + out["discriminator"], 3)
+    timed("mono", lambda: r.fir_decim(demod, h_a, z(), 5))
+    pilot = timed("pilot_bpf", lambda: r.fir_decim(demod, h_p, z(), 1))
+    sb = timed("stereo_bpf", lambda: r.fir_decim(demod, h_s, z(), 1))
+    nco = timed("pll_pilot", lambda: r.pll(pilot, 19e3, 240e3, 2.0, 0.0, 0.01, pll0()))
+    timed("stereo_lpf", lambda: r.fir_decim((sb * nco[:sb.size]).astype(F), h_a, z(), 5))
+    rb = timed("rds_bpf", lambda: r.fir_decim(demod, h_r, z(), 1))
+    _, rnco = timed("rds_sq_bpf_and_pll", lambda: r.pll_combine(rb, h_q, z(), 114e3, 240e3, 0.5, phase, 0.001, pll0()))
+    lp = timed("rds_mix_lpf", lambda: r.fir_mixer(rnco, rb, h_l, z()))
+    res_fn = getattr(r, "resample_rds", None)
+    rr = timed("rds_resample", (lambda: res_fn(lp, h_anti, z(151 * 19 - 1), 80, 19)) if res_fn else (lambda: r.resample(lp, h_anti, z(151 * 19 - 1), 80, 19, True)))
+    timed("rds_rrc", lambda: r.fir_decim(rr, h_rrc, z(), 1))
+    out["sum"] = round(sum(v for k, v in out.items() if k not in ("unpack", "frontend_fir", "discriminator")), 3)
+    return out, kind
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -470,6 +523,11 @@ def run_fmrx_arm(args, rank, world, local_rank):
     }
     cores = host_cores()
     cpu_msps, cpu_kind, cpu_dt = cpu_reference_run(args.cpu_blocks, cores)
+    cpu1_msps, _, cpu1_dt = cpu_reference_run(args.cpu_blocks, 1)
+    try:
+        cpu_stages, cpu_stage_kind = cpu_stage_times()
+    except Exception as e:  # the per-stage table is an explanation, not a result: never let it take the bench line down
+        cpu_stages, cpu_stage_kind = {"error": repr(e)}, "unavailable"
     line = {
         "metric": "IQ Msps (complex samples/s, whole job)", "value": round(value, 1), "unit": "Msps", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_dev / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -485,7 +543,11 @@ def run_fmrx_arm(args, rank, world, local_rank):
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": {"value": round(cpu_msps, 3), "unit": "Msps", "cores": cores, "kind": cpu_kind,
-                         "sample": f"{cores} concurrent processes x {args.cpu_blocks} blocks of the same mode-0 workload ({cpu_dt:.1f} s wall)"},
+                         "sample": f"{cores} concurrent processes x {args.cpu_blocks} blocks of the same mode-0 workload ({cpu_dt:.1f} s wall)",
+                         "single_process": {"value": round(cpu1_msps, 3), "unit": "Msps", "sample": f"1 process x {args.cpu_blocks} blocks ({cpu1_dt:.1f} s)"},
+                         "stages_ms_per_block_one_core": cpu_stages, "stages_kind": cpu_stage_kind,
+                         "stages_note": "the reference's functions on one host core, one mode-0 block per call (SURVEY 8d ii); hold against "
+                                        "roofline.stages[*].ms_per_step / stations_per_gpu for the GPU's time per station-block"},
     }
     print(json.dumps(line), flush=True)
     if world > 1:
