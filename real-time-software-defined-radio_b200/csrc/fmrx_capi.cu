@@ -15,6 +15,7 @@
 #include <cstring>
 #include <new>
 #include <algorithm>
+#include <atomic>
 #include <vector>
 
 #include "fmrx_internal.h"
@@ -325,7 +326,7 @@ struct fmrx_batch {
     uint8_t *d_iq2 = nullptr;
     cudaEvent_t e_h2d[2]{}, e_iqfree[2]{}, e_d2h = nullptr, ev_ticket[kTickets]{};
     bool iqfree_valid[2] = {false, false}, d2h_valid = false;
-    long long submits = 0;
+    std::atomic<long long> submits{0};  // read by fmrx_batch_wait, which a consumer thread may call while a producer thread submits (fmrx_ring)
     long long calls = 0;
     int last_set = 0;
     size_t set_if = 0, set_au = 0;  // elements per set of an IF-rate / audio-rate signal
@@ -804,7 +805,8 @@ int fmrx_batch_submit(fmrx_batch *b, const uint8_t *iq, int n_blocks, const fmrx
     const fmrx_outputs &o = out ? *out : none;
     if (b->was_serial) { if (int e = fmrx_batch_sync(b)) return e; b->was_serial = false; }
     if (!b->d_iq2) CU(b->dalloc(b->d_iq2, (size_t)b->S * b->NB * FMRX_BLOCK_BYTES));
-    const int slot = (int)(b->submits & 1);
+    const long long nsub = b->submits.load();
+    const int slot = (int)(nsub & 1);
     uint8_t *dst = slot ? b->d_iq2 : b->d_iq;
     const long long row = (long long)n_blocks * FMRX_BLOCK_BYTES;
     // ingest: this slot's previous contents must have been consumed by the front end two submits ago
@@ -826,9 +828,9 @@ int fmrx_batch_submit(fmrx_batch *b, const uint8_t *iq, int n_blocks, const fmrx
     if (int e = copy_outputs(b, 0, b->S, n_blocks, o, cudaMemcpyDeviceToHost, b->s_out)) return e;
     CU(cudaEventRecord(b->e_d2h, b->s_out));
     b->d2h_valid = true;
-    *ticket = b->submits;
-    CU(cudaEventRecord(b->ev_ticket[b->submits % kTickets], b->s_out));
-    b->submits += 1;
+    *ticket = nsub;
+    CU(cudaEventRecord(b->ev_ticket[nsub % kTickets], b->s_out));
+    b->submits.store(nsub + 1);
     b->calls += 1;
     b->block_id += n_blocks;
     b->last_blocks = n_blocks;
@@ -837,7 +839,8 @@ int fmrx_batch_submit(fmrx_batch *b, const uint8_t *iq, int n_blocks, const fmrx
 
 int fmrx_batch_wait(fmrx_batch *b, long long ticket) {
     if (!b) return fail(FMRX_ERR_ARG, "null handle");
-    if (ticket < 0 || ticket >= b->submits) return fail(FMRX_ERR_ARG, "ticket %lld was never issued (next is %lld)", ticket, b->submits);
+    const long long issued = b->submits.load();
+    if (ticket < 0 || ticket >= issued) return fail(FMRX_ERR_ARG, "ticket %lld was never issued (next is %lld)", ticket, issued);
     CU(cudaSetDevice(b->cfg.device));
     // the slot holds this ticket's event or, once recycled, that of a later submit on the same in-order stream
     CU(cudaEventSynchronize(b->ev_ticket[ticket % kTickets]));
