@@ -404,3 +404,18 @@ def test_batch_argument_errors_and_ragged_shapes():
             ref = last
         for a, b in zip(last, ref):
             assert np.array_equal(a, b), f"station processed in a batch of {S} differs from the same station alone"
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_parity_sweep_256_stations(mode):
+    """tools/parity_sweep.py at a size the oracle finishes in seconds: 256 distinct stations x 1 block through the GPU
+    chain and through the oracle on every host core -- no float audio sample, int16 sample or RDS bit may differ
+    (the 4096-station run of the same tool is kept in profiles/r3u_parity_sweep.txt)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "parity_sweep.py"), "256", "1", str(mode)], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "float audio samples that differ: 0   int16 samples that differ: 0   blocks with different RDS bits: 0" in r.stdout, r.stdout
