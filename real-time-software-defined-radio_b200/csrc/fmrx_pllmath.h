@@ -50,6 +50,26 @@ FMRX_HD double fma_(double a, double b, double c) {
 #endif
 }
 
+FMRX_HD int hi_word_(double v) {
+#ifdef __CUDA_ARCH__
+    return __double2hiint(v);
+#else
+    uint64_t u;
+    memcpy(&u, &v, 8);
+    return (int)(uint32_t)(u >> 32);
+#endif
+}
+FMRX_HD double make_double_(int hi, int lo) {
+#ifdef __CUDA_ARCH__
+    return __hiloint2double(hi, lo);
+#else
+    const uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
+    double v;
+    memcpy(&v, &u, 8);
+    return v;
+#endif
+}
+
 struct SinCos {
     double sn, cs;  // sin(T), cos(T)
     double r;       // T = n*(pi/2) + r, |r| <~ pi/4
@@ -84,10 +104,11 @@ FMRX_HD SinCos sincos_cw(double T) {
     const double cp = fma_(z4, cc, fma_(z2, cb, ca));
     const double s = fma_(rz, sp, r);   // sin r
     const double c = fma_(z2, cp, hz);  // cos r
-    o.sn = (o.q & 1) ? c : s;
-    o.cs = (o.q & 1) ? s : c;
-    if (o.q == 1 || o.q == 2) o.cs = -o.cs;
-    if (o.q >= 2) o.sn = -o.sn;
+    // quadrant: swap for odd n, then the signs -- sin is negative for q in {2, 3}, cos for q in {1, 2}.  The negation is a
+    // flip of the sign bit of the high word (one integer op on the dependency chain instead of a DADD and two selects)
+    const double sn0 = (o.q & 1) ? c : s, cs0 = (o.q & 1) ? s : c;
+    o.sn = make_double_(hi_word_(sn0) ^ (int)(((unsigned)o.q & 2u) << 30), lo_word(sn0));
+    o.cs = make_double_(hi_word_(cs0) ^ (int)((((unsigned)o.q + 1u) & 2u) << 30), lo_word(cs0));
     return o;
 }
 
