@@ -513,8 +513,8 @@ def run_fmrx_arm(args, rank, world, local_rank):
     roofline = {
         "bound": "fp32", "kernel": top, "achieved": per[top]["tflops"], "peak": per[top]["fp32_peak_tflops"], "unit": "TFLOP/s", "frac": per[top]["frac_fp32"],
         # dram__bytes_read.sum + dram__bytes_write.sum of one front-end launch (4096 stations x 1 block) from the committed
-        # `ncu --set full` capture profiles/r3q_kernels.md: 1.390 GB + 0.241 GB, against 1.510 GB algorithmic
-        "traffic": 1.632e9 * (S * B / 4096.0) if top == "frontend" else None, "traffic_unit": "bytes per launch (ncu, profiles/r3q_kernels.md)",
+        # `ncu --set full` capture profiles/r3v_kernels.md: 1.390 GB + 0.241 GB, against 1.510 GB algorithmic
+        "traffic": 1.632e9 * (S * B / 4096.0) if top == "frontend" else None, "traffic_unit": "bytes per launch (ncu, profiles/r3v_kernels.md)",
         "algorithmic_bytes": STAGE_BYTES[top] * S * B,
         "peak_source": "measured in this run by fmrx_measure_fp32_peak: %.2f T FFMA/s (x2 flop), %.2f T FMUL+FADD lane-ops/s; a stage that keeps the "
                        "reference's two roundings per tap is bounded by the latter" % (peak_ffma, peak_muladd),
