@@ -326,6 +326,7 @@ struct fmrx_batch {
     uint8_t *d_iq2 = nullptr;
     cudaEvent_t e_h2d[2]{}, e_iqfree[2]{}, e_d2h = nullptr, ev_ticket[kTickets]{};
     bool iqfree_valid[2] = {false, false}, d2h_valid = false;
+    bool want_audio_f = false;  // set per call: combine_kernel writes the float audio only when the caller takes it
     std::atomic<long long> submits{0};  // read by fmrx_batch_wait, which a consumer thread may call while a producer thread submits (fmrx_ring)
     long long calls = 0;
     int last_set = 0;
@@ -495,7 +496,7 @@ int enqueue_chain(fmrx_batch *b, const uint8_t *iq, long long ld_iq, int s0, int
         }
         STAGE(FMRX_STAGE_COMBINE);
         CombineJob c{};
-        c.mono = AU2(b->mono); c.stereo = stereo; c.audio = b->audio + (long long)s0 * lda * 2; c.audio_f = b->audio_f + (long long)s0 * lda * 2;
+        c.mono = AU2(b->mono); c.stereo = stereo; c.audio = b->audio + (long long)s0 * lda * 2; c.audio_f = b->want_audio_f ? b->audio_f + (long long)s0 * lda * 2 : nullptr;  // the float copy is 2/3 of this kernel's writes: only when asked for
         c.ld = lda; c.n_total = nblk * b->n_audio; c.n_streams = ns; c.mult = b->mult;
         LAUNCH(launch_combine(c, st));
     }
@@ -758,6 +759,7 @@ int fmrx_batch_process_device(fmrx_batch *b, const uint8_t *iq_device, int n_blo
         b->was_serial = serial;
     }
     cudaStream_t sa = serial ? b->s_ser : b->s_a, sp = serial ? b->s_ser : b->s_p, sc = serial ? b->s_ser : b->s_c;
+    b->want_audio_f = o.audio_f != nullptr;
     if (int e = enqueue_chain(b, iq_device, (long long)n_blocks * FMRX_BLOCK_BYTES, 0, b->S, n_blocks, o, set, sa, sp, sc)) return e;
     if (int e = copy_outputs(b, 0, b->S, n_blocks, o, cudaMemcpyDeviceToDevice, sc)) return e;
     CU(cudaEventRecord(b->ev_c[set], sc));
@@ -785,6 +787,7 @@ int fmrx_batch_process(fmrx_batch *b, const uint8_t *iq, int n_blocks, const fmr
         CU(cudaMemcpyAsync(b->d_iq + (size_t)s0 * row, iq + (size_t)s0 * row, (size_t)ns * row, cudaMemcpyHostToDevice, b->s_in));
         CU(cudaEventRecord(b->e_in[c], b->s_in));
         CU(cudaStreamWaitEvent(cs, b->e_in[c], 0));
+        b->want_audio_f = o.audio_f != nullptr;
         if (int e = enqueue_chain(b, b->d_iq, row, s0, ns, n_blocks, o, 0, cs, cs, cs)) return e;
         CU(cudaEventRecord(b->e_done[c], cs));
         CU(cudaStreamWaitEvent(b->s_out, b->e_done[c], 0));
@@ -818,6 +821,7 @@ int fmrx_batch_submit(fmrx_batch *b, const uint8_t *iq, int n_blocks, const fmrx
     const int set = (int)(b->calls % kSets);
     if (b->ev_c_valid[set]) CU(cudaStreamWaitEvent(b->s_a, b->ev_c[set], 0));
     if (b->d2h_valid) CU(cudaStreamWaitEvent(b->s_c, b->e_d2h, 0));  // phase C overwrites the result buffers the previous copy-out reads
+    b->want_audio_f = o.audio_f != nullptr;
     if (int e = enqueue_chain(b, dst, row, 0, b->S, n_blocks, none, set, b->s_a, b->s_p, b->s_c)) return e;
     CU(cudaEventRecord(b->e_iqfree[slot], b->s_a));
     b->iqfree_valid[slot] = true;
