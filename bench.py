@@ -283,7 +283,8 @@ def run_fmrx_arm(args, rank, world, local_rank):
     torch.cuda.synchronize()
     t_synth = time.perf_counter() - t0
 
-    rx = fmrx.Batch(S, mode=0, profile=fmrx.PROFILE_INTENT, max_blocks=B, device=local_rank)
+    numerics = {"reference": fmrx.NUMERICS_REFERENCE, "strict": fmrx.NUMERICS_STRICT, "fma": fmrx.NUMERICS_FMA}[args.numerics]
+    rx = fmrx.Batch(S, mode=0, profile=fmrx.PROFILE_INTENT, max_blocks=B, device=local_rank, numerics=numerics)
     na = rx.n_audio
     d_audio = torch.empty((S, B, 2 * na), dtype=torch.int16, device=dev)
     d_bits = torch.zeros((S, B, fmrx.MAX_BITS), dtype=torch.uint8, device=dev)
@@ -565,6 +566,7 @@ def main():
     ap.add_argument("--blocks", type=int, default=1, help="blocks per station per step")
     ap.add_argument("--cpu-blocks", type=int, default=48, help="blocks per process of the CPU baseline sample")
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--numerics", default="reference", choices=["reference", "strict", "fma"], help="include/fmrx.h FMRX_NUMERICS_*")
     ap.add_argument("--skip-mode1", action="store_true", help="do not measure the secondary figures of the other modes (config.mode1, config.mode2_44k1)")
     ap.add_argument("--skip-e2e", action="store_true", help="for the ncu launch list: stop after the device-resident and per-stage passes (ncu's "
                     "measurement library fails with LaunchFailed on the first kernel that waits on an event recorded in another context's stream, "

@@ -26,12 +26,14 @@
 extern "C" {
 #endif
 
-#define FMRX_VERSION 100
+#define FMRX_VERSION 101
 #define FMRX_BLOCK_BYTES 307200 /* src/fm_radio.cpp:23 */
 #define FMRX_IF_PER_BLOCK 15360  /* 307200 / 2 / 10 */
 #define FMRX_RDS_PER_BLOCK 3648  /* floor(15361*19/80), src/filter.cpp:304 */
 #define FMRX_MAX_TAPS 151        /* register-tiled FIR kernels are specialised for the reference's 151 taps */
-#define FMRX_MAX_EVENTS 96       /* per stream per block */
+/* per stream per block: the sliding syndrome window of frame_thread takes at most 77 positions in a block (27 carried bits +
+ * 76 new ones, src/fm_radio.cpp:631-713) and each can print one syndrome line and one re-sync line (:649-704): 154 */
+#define FMRX_MAX_EVENTS 160
 #define FMRX_MAX_BITS 80         /* per stream per block */
 
 typedef enum {
@@ -114,7 +116,17 @@ enum { FMRX_PROFILE_BINARY = 0, FMRX_PROFILE_INTENT = 1 };   /* SURVEY App. A */
  * Without it (the default) those three filters run as one composite polyphase filter evaluated only at the 152 samples
  * per block the decoder reads (csrc/fmrx_rdsfast.cu); the RRC tap then holds just those samples. */
 enum { FMRX_PATH_AUDIO = 1, FMRX_PATH_RDS = 2, FMRX_PATH_RDS_STAGES = 4 };
-enum { FMRX_NUMERICS_REFERENCE = 0, FMRX_NUMERICS_FMA = 1 }; /* audio-path FIR rounding, see `exact` above */
+/* FMRX_NUMERICS_REFERENCE (default): every filter of the audio path and every filter ahead of the 19 kHz loop with the
+ *   reference's two roundings per tap (bit-identical float audio); on the RDS branch the 54-60 kHz band-pass likewise,
+ *   the squared-input filter of pllCombine and everything behind the 114 kHz loop fused-multiply-add.
+ * FMRX_NUMERICS_STRICT: additionally pllCombine's filter with the reference's double products accumulated into a float
+ *   sum (src/helper.cpp:139), so the 114 kHz loop, its NCO and the mixer product are bit-identical to the reference's;
+ *   with FMRX_PATH_RDS_STAGES the mixer filter, the 19/80 resampler and the RRC keep two roundings per tap as well and the
+ *   whole RDS branch is bit-identical (decoded bits then equal the reference's by construction, whatever the input).
+ * FMRX_NUMERICS_FMA: fused multiply-add wherever the stated tolerance (1e-5 relative RMS on float audio) allows: the mono
+ *   and stereo low-pass, the 22-54 kHz band-pass and the whole RDS branch; only the pilot band-pass stays exact (anything
+ *   ahead of a PLL decides the fp32 rounding of the oscillator argument, src/helper.cpp:41). */
+enum { FMRX_NUMERICS_REFERENCE = 0, FMRX_NUMERICS_FMA = 1, FMRX_NUMERICS_STRICT = 2 };
 
 typedef struct {
     int32_t mode;       /* 0: 2.4 Msps, /10, /5, +RDS ; 1: 2.5 Msps, /10, x24 /125, no RDS (src/fm_radio.cpp:36-37,174-180);
@@ -196,10 +208,13 @@ int fmrx_batch_profile(fmrx_batch *, int enable); /* 0 off, 1 serialised per-sta
 int fmrx_batch_timeline(fmrx_batch *, int cap, int32_t *stage, float *t0_ms, float *t1_ms);
 int fmrx_batch_stage_times(fmrx_batch *, double *ms /*[FMRX_STAGE_COUNT]*/, long long *count /*[FMRX_STAGE_COUNT] or NULL*/);
 
-/* opaque state blob (all filter histories, PLL states, decoder states, block counter) for checkpoint / resume */
+/* opaque state blob (all filter histories, PLL states, decoder states, block counter) for checkpoint / resume.  The blob
+ * starts with a header (magic, layout version, mode, profile, n_streams, paths, size); set_state returns FMRX_ERR_ARG for a
+ * blob that is truncated, was written by another layout version or comes from a handle of another shape. */
 size_t fmrx_batch_state_bytes(const fmrx_batch *);
-int fmrx_batch_get_state(fmrx_batch *, void *blob);
-int fmrx_batch_set_state(fmrx_batch *, const void *blob);
+int fmrx_batch_get_state(fmrx_batch *, void *blob, size_t bytes);
+int fmrx_batch_set_state(fmrx_batch *, const void *blob, size_t bytes);
+long long fmrx_batch_block_id(const fmrx_batch *); /* blocks consumed per stream so far */
 
 /* ---- ingest / egress ring ------------------------------------------------------------------
  * A bounded ring of page-locked host slots in front of a batch handle: what replaces rf_thread -> queue -> consumer
@@ -213,12 +228,15 @@ typedef struct fmrx_ring fmrx_ring;
 int fmrx_ring_create(fmrx_batch *, int n_slots, int n_blocks, fmrx_ring **out);
 void fmrx_ring_destroy(fmrx_ring *);
 int fmrx_ring_acquire(fmrx_ring *, int timeout_ms, uint8_t **iq);   /* producer; timeout_ms < 0: wait for ever; FMRX_ERR_TIMEOUT */
-int fmrx_ring_commit(fmrx_ring *);                                   /* producer: submit the acquired slot */
+int fmrx_ring_commit(fmrx_ring *);                                   /* producer: submit the acquired slot (n_blocks blocks per station) */
+/* the same for a slot that holds fewer blocks -- the short last step at end of input; arrays of that step are [S][n][..] */
+int fmrx_ring_commit_blocks(fmrx_ring *, int n_blocks);
 int fmrx_ring_close(fmrx_ring *);                                    /* producer: end of input */
 /* consumer: oldest committed step.  `out` receives pointers into the slot's pinned buffers (audio, rds_bits, rds_n_bits,
  * rds_events, rds_n_events; audio_f is not carried), valid until fmrx_ring_release.  FMRX_ERR_TIMEOUT / FMRX_ERR_EOF. */
 int fmrx_ring_next(fmrx_ring *, int timeout_ms, fmrx_outputs *out);
 int fmrx_ring_release(fmrx_ring *);
+int fmrx_ring_step_blocks(fmrx_ring *);                              /* consumer: blocks per station of the step taken and not yet released */
 int fmrx_ring_in_flight(fmrx_ring *);                                /* committed and not yet released */
 
 /* page-locked host memory for the ingest / egress rings (fmrx_batch_process copies asynchronously only from/to it) */

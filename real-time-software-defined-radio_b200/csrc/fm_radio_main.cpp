@@ -5,20 +5,23 @@
 //   stderr the reference's diagnostics: argc, mode line, rf_Fs, and in mode 0 the frame_thread lines (:516,:619-701)
 // Extensions (after the mode argument, all optional): --profile binary|intent (default binary = byte-compatible with
 // the shipped executable), --blocks N (blocks per GPU call, default 1), --device D, --quiet,
+// --numerics reference|strict|fma (include/fmrx.h),
 // --audio-rate 44100 (mode 0 only: audio through the x147 /800 polyphase resampler, 2822 samples per block; the 44.1 kHz
 // mode of the project the reference never implemented), --rds-info (PI / PS / RadioText from the decoded bits, at exit).
 // EOF handling is normalised (Q9): only whole blocks are processed.
 //
-// The reference's four threads and three bounded queues are replaced by: a reader thread filling a ring of pinned host
-// slots, the GPU pipeline behind fmrx_batch_process (copy-in stream / compute streams / copy-out stream), and the main
-// thread draining results to stdout/stderr.  Back-pressure is a real bounded ring (while-loops on the condition
-// variables), not the reference's `if`-guarded waits.
-#include <condition_variable>
+// The reference's four threads and three bounded queues (:86-138, :212-223, :376-387, :414-423) are replaced by the
+// library's ingest / egress ring (fmrx_ring_*, csrc/fmrx_ring.cpp): a reader thread acquires a page-locked slot, fills
+// it from stdin and commits it (H2D copy + the three-phase pipeline + D2H copy, all asynchronous), the main thread
+// takes the finished steps in order and writes stdout / stderr.  Block k+1 is read and copied in while block k is on the
+// GPU; a full ring blocks the reader (back-pressure), a slow stdout blocks the main thread and, through the ring, stdin.
+#include <unistd.h>
+
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
-#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -28,26 +31,19 @@
 namespace {
 constexpr int kSlots = 4;  // QUEUE_BLOCKS - 1 of the reference (:22)
 
-struct Ring {
-    std::mutex m;
-    std::condition_variable cv;
-    int filled[kSlots] = {0};  // blocks in the slot, -1 = end of stream
-    bool ready[kSlots] = {false};
-};
-
 size_t read_fully(uint8_t *dst, size_t n) {
     size_t got = 0;
     while (got < n) {
-        size_t r = fread(dst + got, 1, n - got, stdin);
-        if (r == 0) break;
-        got += r;
+        const ssize_t r = read(0, dst + got, n - got);  // unbuffered: a block is handed on as soon as its last byte has arrived
+        if (r <= 0) break;
+        got += (size_t)r;
     }
     return got;
 }
 }  // namespace
 
 int main(int argc, char *argv[]) {
-    int mode = 0, lib_mode = -1, profile = FMRX_PROFILE_BINARY, blocks = 1, device = 0;
+    int mode = 0, lib_mode = -1, profile = FMRX_PROFILE_BINARY, blocks = 1, device = 0, numerics = FMRX_NUMERICS_REFERENCE;
     bool quiet = false, rds_info = false;
     int pos = 1;
     std::cerr << ((argc >= 2 && argv[1][0] != '-') ? 2 : 1) << std::endl;  // the reference prints argc first (:738); options are not counted
@@ -66,6 +62,13 @@ int main(int argc, char *argv[]) {
         else if (a == "--blocks") blocks = std::max(1, atoi(next()));
         else if (a == "--device") device = atoi(next());
         else if (a == "--quiet") quiet = true;
+        else if (a == "--numerics") {  // extension: reference (default) | strict | fma, see include/fmrx.h
+            const std::string v = next();
+            if (v == "reference") numerics = FMRX_NUMERICS_REFERENCE;
+            else if (v == "strict") numerics = FMRX_NUMERICS_STRICT;
+            else if (v == "fma") numerics = FMRX_NUMERICS_FMA;
+            else { std::cerr << "Usage " << argv[0] << std::endl; return 1; }
+        }
         else if (a == "--audio-rate") {  // extension: 44100 selects the x147 /800 audio resampler (library mode 2); only with the 2.4 Msps front end
             const int rate = atoi(next());
             if ((rate != 48000 && rate != 44100) || (rate == 44100 && mode != 0)) { std::cerr << "Usage " << argv[0] << std::endl; return 1; }
@@ -77,98 +80,69 @@ int main(int argc, char *argv[]) {
     std::cerr << "Operating in mode " << mode << std::endl;            // :741,:756
     std::cerr << "rf_Fs = " << (mode == 1 ? 2500000 : 2400000) << std::endl;  // :61
 
+    auto die = [](const char *what) {
+        // fatal: the reader may sit in read(0) for ever, so the process leaves without joining it
+        std::cerr << "fm_radio: " << what << ": " << fmrx_last_error() << std::endl;
+        fflush(stdout);
+        _exit(2);
+    };
     fmrx_config cfg{};
-    cfg.mode = lib_mode >= 0 ? lib_mode : mode; cfg.profile = profile; cfg.n_streams = 1; cfg.max_blocks = blocks; cfg.device = device;
+    cfg.mode = lib_mode >= 0 ? lib_mode : mode; cfg.profile = profile; cfg.n_streams = 1; cfg.max_blocks = blocks; cfg.device = device; cfg.numerics = numerics;
     fmrx_batch *rx = nullptr;
-    if (fmrx_batch_create(&cfg, &rx) != FMRX_OK) {
-        std::cerr << "fm_radio: " << fmrx_last_error() << std::endl;
-        return 2;
-    }
+    if (fmrx_batch_create(&cfg, &rx) != FMRX_OK) die("fmrx_batch_create");
     const int na = fmrx_batch_audio_per_block(rx);
-    const size_t slot_bytes = (size_t)blocks * FMRX_BLOCK_BYTES;
-    uint8_t *slots[kSlots];
-    for (auto &s : slots)
-        if (fmrx_pinned_alloc((void **)&s, slot_bytes) != FMRX_OK) { std::cerr << "fm_radio: " << fmrx_last_error() << std::endl; return 2; }
-    int16_t *audio = nullptr;
-    fmrx_pinned_alloc((void **)&audio, (size_t)blocks * 2 * na * sizeof(int16_t));
-    std::vector<fmrx_rds_event> ev((size_t)blocks * FMRX_MAX_EVENTS);
-    std::vector<int32_t> nev(blocks);
-    std::vector<uint8_t> bits((size_t)blocks * FMRX_MAX_BITS);
-    std::vector<int32_t> nbits(blocks);
+    fmrx_ring *ring = nullptr;
+    if (fmrx_ring_create(rx, kSlots, blocks, &ring) != FMRX_OK) die("fmrx_ring_create");
     fmrx_rds_app *app = nullptr;
-    if (rds_info && mode == 0 && fmrx_rds_app_create(1, &app) != FMRX_OK) { std::cerr << "fm_radio: " << fmrx_last_error() << std::endl; return 2; }
+    if (rds_info && mode == 0 && fmrx_rds_app_create(1, &app) != FMRX_OK) die("fmrx_rds_app_create");
 
-    Ring ring;
+    std::atomic<int> reader_rc{0};
+    const size_t slot_bytes = (size_t)blocks * FMRX_BLOCK_BYTES;
     std::thread reader([&] {
-        for (int i = 0;; i = (i + 1) % kSlots) {
-            {
-                std::unique_lock<std::mutex> lk(ring.m);
-                ring.cv.wait(lk, [&] { return !ring.ready[i]; });
-            }
-            const size_t got = read_fully(slots[i], slot_bytes);
+        for (;;) {
+            uint8_t *iq = nullptr;
+            if (fmrx_ring_acquire(ring, -1, &iq) != FMRX_OK) { reader_rc = 2; break; }
+            const size_t got = read_fully(iq, slot_bytes);
             const int nb = (int)(got / FMRX_BLOCK_BYTES);  // whole blocks only (Q9)
-            {
-                std::lock_guard<std::mutex> lk(ring.m);
-                ring.filled[i] = nb > 0 ? nb : -1;
-                ring.ready[i] = true;
+            if (nb > 0 && fmrx_ring_commit_blocks(ring, nb) != FMRX_OK) {
+                std::cerr << "fm_radio: " << fmrx_last_error() << std::endl;
+                reader_rc = 2;
+                break;
             }
-            ring.cv.notify_all();
-            if (got < slot_bytes) {
-                if (nb > 0) {  // publish the end marker in the next slot
-                    const int j = (i + 1) % kSlots;
-                    std::unique_lock<std::mutex> lk(ring.m);
-                    ring.cv.wait(lk, [&] { return !ring.ready[j]; });
-                    ring.filled[j] = -1;
-                    ring.ready[j] = true;
-                    ring.cv.notify_all();
-                }
-                return;
-            }
+            if (got < slot_bytes) break;
         }
+        fmrx_ring_close(ring);  // end of input (or a failed commit): the main thread drains what was committed and stops
     });
 
     long long block_id = 0;
-    int rc = 0;
     std::vector<int32_t> offset(1, 0);
-    for (int i = 0;; i = (i + 1) % kSlots) {
-        int nb;
-        {
-            std::unique_lock<std::mutex> lk(ring.m);
-            ring.cv.wait(lk, [&] { return ring.ready[i]; });
-            nb = ring.filled[i];
-        }
-        if (nb < 0) break;
+    for (;;) {
         fmrx_outputs out{};
-        out.audio = audio;
-        if (mode == 0) { out.rds_events = ev.data(); out.rds_n_events = nev.data(); }
-        if (app) { out.rds_bits = bits.data(); out.rds_n_bits = nbits.data(); }
-        if (fmrx_batch_process(rx, slots[i], nb, &out) != FMRX_OK) {
-            std::cerr << "fm_radio: " << fmrx_last_error() << std::endl;
-            rc = 2;
-            break;
+        const int st = fmrx_ring_next(ring, -1, &out);
+        if (st == FMRX_ERR_EOF) break;
+        if (st != FMRX_OK) die("fmrx_ring_next");
+        const int nb = fmrx_ring_step_blocks(ring);
+        if (fwrite(out.audio, sizeof(int16_t), (size_t)nb * 2 * na, stdout) != (size_t)nb * 2 * na) {  // :302; a closed pipe downstream ends the run
+            std::cerr << "fm_radio: short write on stdout" << std::endl;
+            _exit(2);
         }
-        fwrite(audio, sizeof(int16_t), (size_t)nb * 2 * na, stdout);  // :302
-        if (app) fmrx_rds_app_feed(app, bits.data(), nbits.data(), nb, nullptr, 0, nullptr);
+        fflush(stdout);  // one write per block, like the reference: a player downstream gets its 64 ms as soon as they exist
+        if (app) fmrx_rds_app_feed(app, out.rds_bits, out.rds_n_bits, nb, nullptr, 0, nullptr);
         if (mode == 0 && !quiet) {
             if (block_id == 0) fmrx_batch_rds_offsets(rx, offset.data());
-            char text[8192];
+            char text[16384];
             for (int b = 0; b < nb; ++b) {
-                fmrx_rds_format_block((int)(block_id + b), offset[0], ev.data() + (size_t)b * FMRX_MAX_EVENTS, nev[b], text, sizeof(text));
+                fmrx_rds_format_block((int)(block_id + b), offset[0], out.rds_events + (size_t)b * FMRX_MAX_EVENTS, out.rds_n_events[b], text, sizeof(text));
                 std::cerr << text;
             }
         }
         block_id += nb;
-        {
-            std::lock_guard<std::mutex> lk(ring.m);
-            ring.ready[i] = false;
-        }
-        ring.cv.notify_all();
+        if (fmrx_ring_release(ring) != FMRX_OK) die("fmrx_ring_release");
     }
     fflush(stdout);
-    if (rc != 0) { fclose(stdin); }
     reader.join();
-    for (auto &s : slots) fmrx_pinned_free(s);
-    fmrx_pinned_free(audio);
+    const int rc = reader_rc.load();
+    fmrx_ring_destroy(ring);
     fmrx_batch_destroy(rx);
     if (app) {
         fmrx_rds_station st;

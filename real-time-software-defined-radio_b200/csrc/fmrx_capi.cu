@@ -155,7 +155,7 @@ int fmrx_fir_mixer(float *y, const float *nco, const float *sig, int n_streams, 
     CU(da.up(nco, nx)); CU(db.up(sig, nx)); CU(dy.alloc(nx)); CU(dz.up(zi, nz));
     FirJob j{};
     j.x = da.p; j.x2 = db.p; j.y = dy.p; j.zi = dz.p; j.h = h; j.ldx = j.ldy = (long long)n_blocks * n;
-    j.nzi = kHist; j.n = n; j.n_blocks = n_blocks; j.n_streams = n_streams; j.decim = 1; j.kind = SRC_MIX_HALF; j.exact = 0;
+    j.nzi = kHist; j.n = n; j.n_blocks = n_blocks; j.n_streams = n_streams; j.decim = 1; j.kind = SRC_MIX_HALF; j.exact = 1;  // ((x*x1)*h)*2 == ((x*x1)*2)*h: scaling by two is exact
     LAUNCH(launch_fir(j, nullptr));
     CU(dy.down(y, nx)); CU(dz.down(zi, nz));
     return FMRX_OK;
@@ -192,7 +192,7 @@ int fmrx_pll_combine(float *y, float *nco, const float *x, int n_streams, int n_
     CU(dx.up(x, nx)); CU(dy.alloc(nx)); CU(dn.alloc(nx)); CU(dz.up(zi, nz)); CU(ds.up(state, (size_t)n_streams * 6));
     FirJob j{};
     j.x = dx.p; j.y = dy.p; j.zi = dz.p; j.h = h; j.ldx = j.ldy = (long long)n_blocks * n;
-    j.nzi = kHist; j.n = n; j.n_blocks = n_blocks; j.n_streams = n_streams; j.decim = 1; j.kind = SRC_SQUARE; j.exact = 0;
+    j.nzi = kHist; j.n = n; j.n_blocks = n_blocks; j.n_streams = n_streams; j.decim = 1; j.kind = SRC_SQUARE; j.exact = 1;  // double products into a float sum, src/helper.cpp:139
     LAUNCH(launch_fir(j, nullptr));
     PllParams p{freq, Fs, scale, phase_adj, bw};
     LAUNCH(launch_pll_blocks(dy.p, dn.p, p, ds.p, nullptr, nullptr, p, nullptr, (long long)n_blocks * n, n_streams, n, n_blocks, nullptr));
@@ -282,6 +282,7 @@ struct fmrx_batch {
     fmrx_config cfg{};
     int S = 0, NB = 0, n_audio = 0, nzi_a = 0, nzi_b = 0, audio_taps = 0, up = 1, decim_a = 5, mult = 1;
     bool audio_on = false, rds_on = false, exact = true;
+    bool strict = false;    // FMRX_NUMERICS_STRICT: the squared-input filter in front of the 114 kHz PLL with the reference's double products, staged RDS back end exact
     bool rds_fast = false;  // RDS back end at symbol rate (fmrx_rdsfast.cu) instead of stage by stage
     float *d_W = nullptr, *d_G = nullptr, *d_h2p = nullptr;
     int32_t *d_off = nullptr;
@@ -451,9 +452,11 @@ int enqueue_chain(fmrx_batch *b, const uint8_t *iq, long long ld_iq, int s0, int
     }
     // ---- rds_thread, filters before the PLL (:395, :400's BPF)
     if (b->rds_on) {
-        { STAGE(FMRX_STAGE_RDS_BPF); LAUNCH(fir(IF(b->demod), nullptr, IF2(b->rbpf), b->zi_rbpf + (long long)s0 * kHist, kHist, b->h_rbpf, ldif, ldif, NIF, 1, SRC_PLAIN, 0, nblk)); }
+        // REFERENCE: the 54-60 kHz band-pass with the reference's two roundings per tap (src/filter.cpp:126-154); STRICT: also the
+        // squared-input filter with its double products (src/helper.cpp:139), so that the 114 kHz loop sees the reference's input bit for bit
+        { STAGE(FMRX_STAGE_RDS_BPF); LAUNCH(fir(IF(b->demod), nullptr, IF2(b->rbpf), b->zi_rbpf + (long long)s0 * kHist, kHist, b->h_rbpf, ldif, ldif, NIF, 1, SRC_PLAIN, ex, nblk)); }
         STAGE(FMRX_STAGE_RDS_SQ_BPF);
-        LAUNCH(fir(IF2(b->rbpf), nullptr, IF2(b->rsq), b->zi_sq + (long long)s0 * kHist, kHist, b->h_sq, ldif, ldif, NIF, 1, SRC_SQUARE, 0, nblk));
+        LAUNCH(fir(IF2(b->rbpf), nullptr, IF2(b->rsq), b->zi_sq + (long long)s0 * kHist, kHist, b->h_sq, ldif, ldif, NIF, 1, SRC_SQUARE, b->strict ? 1 : 0, nblk));
     }
     // ---- both PLLs, one lane per (stream, loop) (:233/:262 and :400)
     if (piped) { CU(cudaEventRecord(b->ev_a[set], stA)); CU(cudaStreamWaitEvent(stP, b->ev_a[set], 0)); }
@@ -511,13 +514,13 @@ int enqueue_chain(fmrx_batch *b, const uint8_t *iq, long long ld_iq, int s0, int
             STAGE(FMRX_STAGE_RDS_SYMBOLS);
             LAUNCH(launch_rds_fast(q, st));
         } else {
-            { STAGE(FMRX_STAGE_RDS_MIX_LPF); LAUNCH(fir(IF2(b->rmixed), nullptr, IF(b->rlpf), b->zi_lpf + (long long)s0 * kHist, kHist, b->h_lpf3k, ldif, ldif, NIF, 1, SRC_PROD_HALF, 0, nblk)); }
+            { STAGE(FMRX_STAGE_RDS_MIX_LPF); LAUNCH(fir(IF2(b->rmixed), nullptr, IF(b->rlpf), b->zi_lpf + (long long)s0 * kHist, kHist, b->h_lpf3k, ldif, ldif, NIF, 1, SRC_PROD_HALF, b->strict ? 1 : 0, nblk)); }
             ResampleJob r{};
             r.x = IF(b->rlpf); r.y = RD(b->rres); r.zi = b->zi_anti + (long long)s0 * (kTaps * 19 - 1); r.h = b->d_h_anti; r.h_host = b->h_anti.data(); r.ldx = ldif; r.ldy = ldr;
             r.n = NIF; r.n_ref = NIF + 1; r.ny = NRDS; r.n_blocks = nblk; r.n_streams = ns; r.ntaps = kTaps * 19; r.nzi = kTaps * 19 - 1;
-            r.decim = 80; r.up = 19; r.gain_up = 1; r.exact = 0;
+            r.decim = 80; r.up = 19; r.gain_up = 1; r.exact = b->strict ? 1 : 0;
             { STAGE(FMRX_STAGE_RDS_RESAMPLE); LAUNCH(launch_resample(r, st)); }
-            { STAGE(FMRX_STAGE_RDS_RRC); LAUNCH(fir(RD(b->rres), nullptr, RD(b->rrrc), b->zi_rrc + (long long)s0 * kHist, kHist, b->h_rrc, ldr, ldr, NRDS, 1, SRC_PLAIN, 0, nblk)); }
+            { STAGE(FMRX_STAGE_RDS_RRC); LAUNCH(fir(RD(b->rres), nullptr, RD(b->rrrc), b->zi_rrc + (long long)s0 * kHist, kHist, b->h_rrc, ldr, ldr, NRDS, 1, SRC_PLAIN, b->strict ? 1 : 0, nblk)); }
         }
         STAGE(FMRX_STAGE_RDS_DECODE);
         LAUNCH(launch_rds_decode(RD(b->rrrc), ldr, ns, nblk, NRDS, b->bits + (long long)s0 * nblk * FMRX_MAX_BITS, b->nbits + (long long)s0 * nblk,
@@ -559,7 +562,7 @@ extern "C" {
 int fmrx_batch_create(const fmrx_config *cfg, fmrx_batch **out) {
     if (!cfg || !out) return fail(FMRX_ERR_ARG, "fmrx_batch_create: null pointer");
     *out = nullptr;
-    if (cfg->mode < 0 || cfg->mode > 2 || cfg->n_streams <= 0 || cfg->max_blocks <= 0 || cfg->n_streams > 65535 || cfg->max_blocks > 65535)
+    if (cfg->mode < 0 || cfg->mode > 2 || cfg->numerics < 0 || cfg->numerics > 2 || cfg->n_streams <= 0 || cfg->max_blocks <= 0 || cfg->n_streams > 65535 || cfg->max_blocks > 65535)
         return fail(FMRX_ERR_ARG, "fmrx_batch_create: mode must be 0, 1 or 2, 1 <= n_streams,max_blocks <= 65535");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(FMRX_ERR_CUDA, "no CUDA device: libfmrx has no CPU fallback"); }
@@ -574,7 +577,8 @@ int fmrx_batch_create(const fmrx_config *cfg, fmrx_batch **out) {
     b->audio_on = (paths & FMRX_PATH_AUDIO) != 0;
     b->rds_on = (paths & FMRX_PATH_RDS) != 0 && cfg->mode != 1;  // src/fm_radio.cpp:324,446 (mode 2 has mode 0's 240 kHz IF)
     b->rds_fast = b->rds_on && !(paths & FMRX_PATH_RDS_STAGES);
-    b->exact = cfg->numerics == FMRX_NUMERICS_REFERENCE;
+    b->exact = cfg->numerics != FMRX_NUMERICS_FMA;
+    b->strict = cfg->numerics == FMRX_NUMERICS_STRICT;
     // ---- constants of the thread bodies
     const float rf_Fs = cfg->mode == 1 ? 2500000.0f : 2400000.0f;  // :36-37
     float audio_Fs = 240000.0f;                                    // :153
@@ -760,6 +764,7 @@ int fmrx_batch_process_device(fmrx_batch *b, const uint8_t *iq_device, int n_blo
     }
     cudaStream_t sa = serial ? b->s_ser : b->s_a, sp = serial ? b->s_ser : b->s_p, sc = serial ? b->s_ser : b->s_c;
     b->want_audio_f = o.audio_f != nullptr;
+    if (b->d2h_valid) CU(cudaStreamWaitEvent(sc, b->e_d2h, 0));  // a copy-out of fmrx_batch_submit may still be reading the (single) result buffers
     if (int e = enqueue_chain(b, iq_device, (long long)n_blocks * FMRX_BLOCK_BYTES, 0, b->S, n_blocks, o, set, sa, sp, sc)) return e;
     if (int e = copy_outputs(b, 0, b->S, n_blocks, o, cudaMemcpyDeviceToDevice, sc)) return e;
     CU(cudaEventRecord(b->ev_c[set], sc));
@@ -882,25 +887,58 @@ int fmrx_batch_tap(fmrx_batch *b, int which, float *dst) {
     return FMRX_OK;
 }
 
-size_t fmrx_batch_state_bytes(const fmrx_batch *b) { return b ? b->state_bytes + sizeof(long long) : 0; }
+// checkpoint blob = header + the device state blob.  The header pins everything the layout of the state depends on, so a
+// blob from a handle of another shape, a truncated one or one written by another layout version is refused, not applied.
+namespace {
+struct StateHeader {
+    uint32_t magic, version;      // 'FMRX' little endian, kStateLayout
+    int32_t mode, profile, n_streams, paths, rds_fast, reserved;
+    uint64_t state_bytes;
+    long long block_id;
+};
+constexpr uint32_t kStateMagic = 0x58524D46u, kStateLayout = 2;  // bump kStateLayout when a segment or the decoder words (fmrx_rds.cu W_*) change
+StateHeader make_header(const fmrx_batch *b) {
+    StateHeader h{};
+    h.magic = kStateMagic; h.version = kStateLayout; h.mode = b->cfg.mode; h.profile = b->cfg.profile; h.n_streams = b->S;
+    h.paths = (b->audio_on ? FMRX_PATH_AUDIO : 0) | (b->rds_on ? FMRX_PATH_RDS : 0); h.rds_fast = b->rds_fast ? 1 : 0;
+    h.state_bytes = b->state_bytes; h.block_id = b->block_id;
+    return h;
+}
+}  // namespace
 
-int fmrx_batch_get_state(fmrx_batch *b, void *blob) {
+size_t fmrx_batch_state_bytes(const fmrx_batch *b) { return b ? b->state_bytes + sizeof(StateHeader) : 0; }
+
+int fmrx_batch_get_state(fmrx_batch *b, void *blob, size_t bytes) {
     if (!b || !blob) return fail(FMRX_ERR_ARG, "null pointer");
+    if (bytes < fmrx_batch_state_bytes(b)) return fail(FMRX_ERR_ARG, "state buffer of %zu bytes, %zu needed", bytes, fmrx_batch_state_bytes(b));
     CU(cudaSetDevice(b->cfg.device));
     if (int e = fmrx_batch_sync(b)) return e;
-    std::memcpy(blob, &b->block_id, sizeof(long long));
-    CU(cudaMemcpy((char *)blob + sizeof(long long), b->d_state, b->state_bytes, cudaMemcpyDeviceToHost));
+    const StateHeader h = make_header(b);
+    std::memcpy(blob, &h, sizeof(h));
+    CU(cudaMemcpy((char *)blob + sizeof(h), b->d_state, b->state_bytes, cudaMemcpyDeviceToHost));
     return FMRX_OK;
 }
 
-int fmrx_batch_set_state(fmrx_batch *b, const void *blob) {
+int fmrx_batch_set_state(fmrx_batch *b, const void *blob, size_t bytes) {
     if (!b || !blob) return fail(FMRX_ERR_ARG, "null pointer");
+    StateHeader h{};
+    if (bytes < sizeof(h)) return fail(FMRX_ERR_ARG, "state blob of %zu bytes is shorter than its header", bytes);
+    std::memcpy(&h, blob, sizeof(h));
+    const StateHeader want = make_header(b);
+    if (h.magic != kStateMagic || h.version != kStateLayout) return fail(FMRX_ERR_ARG, "not a state blob of this library version (magic %08x, layout %u; expected layout %u)", h.magic, h.version, kStateLayout);
+    if (h.mode != want.mode || h.profile != want.profile || h.n_streams != want.n_streams || h.paths != want.paths || h.state_bytes != want.state_bytes)  // rds_fast is informational: both back ends keep the same state
+        return fail(FMRX_ERR_ARG, "state blob is from a handle of another shape (mode %d profile %d streams %d paths %d, %llu bytes; this handle: %d %d %d %d, %llu)",
+                    h.mode, h.profile, h.n_streams, h.paths, (unsigned long long)h.state_bytes, want.mode, want.profile, want.n_streams, want.paths, (unsigned long long)want.state_bytes);
+    if (bytes < sizeof(h) + b->state_bytes) return fail(FMRX_ERR_ARG, "state blob truncated: %zu bytes, %zu needed", bytes, sizeof(h) + b->state_bytes);
+    if (h.block_id < 0) return fail(FMRX_ERR_ARG, "state blob carries a negative block counter");
     CU(cudaSetDevice(b->cfg.device));
     if (int e = fmrx_batch_sync(b)) return e;
-    std::memcpy(&b->block_id, blob, sizeof(long long));
-    CU(cudaMemcpy(b->d_state, (const char *)blob + sizeof(long long), b->state_bytes, cudaMemcpyHostToDevice));
+    b->block_id = h.block_id;
+    CU(cudaMemcpy(b->d_state, (const char *)blob + sizeof(h), b->state_bytes, cudaMemcpyHostToDevice));
     return FMRX_OK;
 }
+
+long long fmrx_batch_block_id(const fmrx_batch *b) { return b ? b->block_id : -1; }
 
 int fmrx_batch_profile(fmrx_batch *b, int enable) {
     if (!b) return fail(FMRX_ERR_ARG, "null handle");

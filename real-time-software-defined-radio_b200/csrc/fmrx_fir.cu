@@ -245,6 +245,131 @@ __global__ void __launch_bounds__(NT) fir151_kernel(const FirDev a, const __grid
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// pllCombine's filter with the reference's own arithmetic (src/helper.cpp:139): an in-block tap is
+//     y[n] += pow(x[p], 2) * h[k]     -- the square and the product are DOUBLE, y[n] is a float,
+// i.e. acc <- (float)((double)acc + ((double)x * (double)x) * (double)h[k]); a history tap (:144) is the plain
+// float multiply-add on the stored float square.  Every partial sum is therefore rounded to 53 bits and then to 24.
+//
+// Per tap: DMUL, DADD, and the rounding to the nearest float (ties to even) done on the bit pattern of the double
+// with integer instructions -- the accumulator stays a double that holds a float value, so there is no conversion
+// instruction on the path (F2F runs at a quarter of the DFMA rate; the integer pipe at twice).  The integer rounding
+// is right while the rounded sum is a normal float; one more integer pair per tap ORs the exponent into a
+// violation mask (exponent outside [2^-126, 4) -- zero included, because a zero sum after the first tap means silence or
+// a complete cancellation), and a thread whose mask is set, whose window reaches into the history (first tile of a
+// block) or whose tile holds a non-finite sample recomputes its outputs with the conversion instructions, tap by tap,
+// exactly as the expression above is written.
+// Tile = 128 threads x 8 consecutive outputs; squares staged once per CTA as doubles (pitch 9: conflict-free LDS.64).
+// ------------------------------------------------------------------------------------------------------------------
+struct TapsD {
+    double h[kTaps + 1];
+};
+
+constexpr int SQ_NT = 128, SQ_RO = 8, SQ_LEAD = 152;           // staged samples ahead of the tile's first output (>= 150, multiple of 4)
+constexpr int SQ_N = SQ_NT * SQ_RO + SQ_LEAD;                  // staged samples per tile
+__host__ __device__ constexpr int sq_phys(int i) { return i + i / SQ_RO; }
+
+__device__ __forceinline__ double round_to_float_kept_double(double s, unsigned &viol) {
+    unsigned long long u = (unsigned long long)__double_as_longlong(s);
+    u += 0x0FFFFFFFull + ((u >> 29) & 1ull);
+    u &= ~0x1FFFFFFFull;
+    viol |= ((unsigned)(u >> 32) - 0x38100000u) & 0x78000000u;  // 0 iff 2^-126 <= |result| < 4
+    return __longlong_as_double((long long)u);
+}
+
+__global__ void __launch_bounds__(SQ_NT) fir151_sq_exact_kernel(const FirDev a, const __grid_constant__ Taps taps, const __grid_constant__ TapsD tapsd) {
+    __shared__ double q[sq_phys(SQ_N) + 1];    // in-block: x^2 (exact in double); history: the stored float square
+    __shared__ double hd[kTaps + 1];
+    const int s = blockIdx.z, b = blockIdx.y, n0 = blockIdx.x * (SQ_NT * SQ_RO);
+    const float *xs = a.x + (long long)s * a.ldx;
+    const float *zs = a.zi + (long long)s * a.nzi;
+    const int P0 = n0 - SQ_LEAD;
+    bool finite = true;
+    for (int i = threadIdx.x; i < SQ_N; i += SQ_NT) {
+        const int p = P0 + i;
+        double v = 0.0;
+        if (p >= 0 && p < a.n) {
+            const double x = (double)xs[(long long)b * a.n + p];
+            v = __dmul_rn(x, x);
+            finite = finite && (v <= 1.0e300);  // false for inf and NaN
+        } else if (p < 0 && p >= -kHist) {
+            v = (double)source<SRC_SQUARE>(a, xs, nullptr, zs, b, p);
+        }
+        q[sq_phys(i)] = v;
+    }
+    for (int i = threadIdx.x; i <= kTaps; i += SQ_NT) hd[i] = tapsd.h[i];
+    const bool tile_finite = __syncthreads_and(finite);
+
+    const int t = threadIdx.x, o0 = n0 + SQ_RO * t;   // first output of this thread
+    float out[SQ_RO];
+    unsigned viol = (o0 < kHist || !tile_finite) ? 1u : 0u;
+    if (!viol) {
+        // sample j of the walk is block position o0 + 7 - j = staged index 8t + 159 - j; output r takes it with tap r - 7 + j
+        const int base = SQ_RO * t + SQ_LEAD + SQ_RO - 1;
+        double acc[SQ_RO];
+#pragma unroll
+        for (int r = 0; r < SQ_RO; ++r) acc[r] = 0.0;
+        // ramp up: outputs join one by one (static tap validity); a zero tap is skipped -- x^2 * (+-0) added to a sum that is
+        // never -0 changes nothing, and the reference's filters start with h[0] = 0 (window sin^2), which would only
+        // trip the zero check
+#pragma unroll
+        for (int j = 0; j < SQ_RO; ++j) {
+            const double x2 = q[sq_phys(base - j)];
+#pragma unroll
+            for (int r = SQ_RO - 1 - j; r < SQ_RO; ++r) {
+                const double h = hd[r - (SQ_RO - 1) + j];
+                if (h != 0.0) acc[r] = round_to_float_kept_double(__dadd_rn(acc[r], __dmul_rn(x2, h)), viol);
+            }
+        }
+        // steady state: all eight outputs take every sample; the eight taps in flight slide by one per sample
+        double hw[SQ_RO];
+#pragma unroll
+        for (int r = 0; r < SQ_RO; ++r) hw[r] = hd[r + 1];     // taps of j = 8: r - 7 + 8
+#pragma unroll 8
+        for (int j = SQ_RO; j < kTaps; ++j) {
+            const double x2 = q[sq_phys(base - j)];
+#pragma unroll
+            for (int r = 0; r < SQ_RO; ++r) acc[r] = round_to_float_kept_double(__dadd_rn(acc[r], __dmul_rn(x2, hw[r])), viol);
+#pragma unroll
+            for (int r = 0; r < SQ_RO - 1; ++r) hw[r] = hw[r + 1];
+            hw[SQ_RO - 1] = hd[j + 1];                             // hd[151] = 0: loaded after the last steady sample, never used
+        }
+        // ramp down: outputs leave one by one
+#pragma unroll
+        for (int j = kTaps; j < kTaps + SQ_RO - 1; ++j) {
+            const double x2 = q[sq_phys(base - j)];
+#pragma unroll
+            for (int r = 0; r < SQ_RO - 1 - (j - kTaps); ++r)
+                acc[r] = round_to_float_kept_double(__dadd_rn(acc[r], __dmul_rn(x2, hd[r - (SQ_RO - 1) + j])), viol);
+        }
+#pragma unroll
+        for (int r = 0; r < SQ_RO; ++r) out[r] = (float)acc[r];
+    }
+    if (viol) {
+        // the expression as written, with conversion instructions: history taps in float, in-block taps through double
+        for (int r = 0; r < SQ_RO; ++r) {
+            const int n = o0 + r;
+            float acc = 0.0f;
+            for (int k = 0; k < kTaps; ++k) {
+                const int p = n - k;
+                const double v = q[sq_phys(p - P0)];
+                if (p >= 0) acc = (float)__dadd_rn((double)acc, __dmul_rn(v, hd[k]));
+                else acc = __fadd_rn(acc, __fmul_rn((float)v, taps.h[k]));
+            }
+            out[r] = acc;
+        }
+    }
+    float *ys = a.y + (long long)s * a.ldy + (long long)b * a.ny + o0;
+    if (o0 + SQ_RO <= a.ny && ((reinterpret_cast<uintptr_t>(ys) & 15) == 0)) {
+        reinterpret_cast<float4 *>(ys)[0] = make_float4(out[0], out[1], out[2], out[3]);
+        reinterpret_cast<float4 *>(ys)[1] = make_float4(out[4], out[5], out[6], out[7]);
+    } else {
+#pragma unroll
+        for (int r = 0; r < SQ_RO; ++r)
+            if (o0 + r < a.ny) ys[r] = out[r];
+    }
+}
+
 // state after the launch: zi[i] = formed(x[N - nzi - 1 + i]) of the LAST block (mixer: N - nzi + i, no x2)
 template <int KIND>
 __global__ void fir_state_kernel(const float *x, const float *x2, float *zi, long long ldx, int nzi, int n, int n_blocks, int i0) {
@@ -701,7 +826,15 @@ template <int KIND>
 int launch_fir_k(const FirJob &j, const FirDev &d, dim3 grid, fmrx_stream_t st) {
     int e;
     // only the (kind, decimation) pairs the receive chain and the function-level API use are instantiated
-    if (j.decim == 1) e = launch_fir_dk<1, KIND>(j, d, grid, st);
+    if (KIND == SRC_SQUARE && j.exact) {  // reference-exact pllCombine filter: double products rounded into a float sum
+        if (j.decim != 1) return (int)cudaErrorInvalidValue;
+        TapsD td;
+        for (int k = 0; k < kTaps; ++k) td.h[k] = (double)j.h[k];
+        td.h[kTaps] = 0.0;
+        dim3 g((d.ny + SQ_NT * SQ_RO - 1) / (SQ_NT * SQ_RO), j.n_blocks, j.n_streams);
+        fir151_sq_exact_kernel<<<g, SQ_NT, 0, st>>>(d, make_taps(j.h), td);
+        e = (int)cudaGetLastError();
+    } else if (j.decim == 1) e = launch_fir_dk<1, KIND>(j, d, grid, st);
     else if (j.decim == 5 && (KIND == SRC_PLAIN || KIND == SRC_MIX_LATE)) e = launch_fir_dk<5, (KIND == SRC_PLAIN || KIND == SRC_MIX_LATE) ? KIND : SRC_PLAIN>(j, d, grid, st);
     else if (j.decim == 10 && KIND == SRC_PLAIN) e = launch_fir_dk<10, SRC_PLAIN>(j, d, grid, st);
     else return (int)cudaErrorInvalidValue;

@@ -24,7 +24,6 @@
 // buffer.  FMRX_PATH_RDS_STAGES selects the staged kernels instead (every stage materialised, debug taps available).
 #include <cuda_runtime.h>
 
-#include <mutex>
 #include <vector>
 
 #include "fmrx_internal.h"
@@ -317,11 +316,8 @@ int launch_rds_fast(const RdsFastJob &j, fmrx_stream_t st) {
         d.off = j.off_state; d.off_stride = j.off_state_stride;
     }
     rds_head_kernel<false><<<dim3(j.n_blocks, j.n_streams), 256, 0, st>>>(d, h1, hr);
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaError_t e0 = cudaFuncSetAttribute(rds_symbol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NIF * (int)sizeof(float))) return (int)e0;
-        attr_set = true;
-    }
+    // per device (per context), so set on every launch: a process may hold handles on several GPUs (fmrx_config.device)
+    if (cudaError_t e0 = cudaFuncSetAttribute(rds_symbol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NIF * (int)sizeof(float))) return (int)e0;
     rds_symbol_kernel<<<dim3(j.n_blocks, j.n_streams), 256, NIF * sizeof(float), st>>>(d, h1);
     launch_counter() += 2;
     return (int)cudaGetLastError();

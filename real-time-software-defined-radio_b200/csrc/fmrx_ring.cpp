@@ -25,6 +25,7 @@ struct fmrx_ring {
         int32_t *nbits = nullptr, *nev = nullptr;
         fmrx_rds_event *ev = nullptr;
         long long ticket = -1;
+        int blocks = 0;  // blocks committed in this slot (<= n_blocks: a short last step at end of input)
     };
     fmrx_batch *b = nullptr;
     int n_blocks = 0;
@@ -102,15 +103,19 @@ int fmrx_ring_acquire(fmrx_ring *r, int timeout_ms, uint8_t **iq) {
     return FMRX_OK;
 }
 
-int fmrx_ring_commit(fmrx_ring *r) {
+int fmrx_ring_commit(fmrx_ring *r) { return r ? fmrx_ring_commit_blocks(r, r->n_blocks) : fmrx::fail(FMRX_ERR_ARG, "null handle"); }
+
+int fmrx_ring_commit_blocks(fmrx_ring *r, int n_blocks) {
     if (!r) return fmrx::fail(FMRX_ERR_ARG, "null handle");
+    if (n_blocks <= 0 || n_blocks > r->n_blocks) return fmrx::fail(FMRX_ERR_ARG, "fmrx_ring_commit_blocks: 1 <= n_blocks <= %d", r->n_blocks);
     std::unique_lock<std::mutex> lk(r->m);
     if (r->acquired != r->committed + 1) return fmrx::fail(FMRX_ERR_STATE, "fmrx_ring_commit: no slot acquired");
     fmrx_ring::Slot &s = r->slots[r->committed % (long long)r->slots.size()];
     fmrx_outputs o{};
     o.audio = s.audio; o.rds_bits = s.bits; o.rds_n_bits = s.nbits; o.rds_events = s.ev; o.rds_n_events = s.nev;
     // the submit itself only enqueues (copies and kernels are asynchronous); holding the lock keeps handle calls serial
-    if (int e = fmrx_batch_submit(r->b, s.iq, r->n_blocks, &o, &s.ticket)) { r->acquired -= 1; return e; }
+    if (int e = fmrx_batch_submit(r->b, s.iq, n_blocks, &o, &s.ticket)) { r->acquired -= 1; return e; }
+    s.blocks = n_blocks;
     r->committed += 1;
     lk.unlock();
     r->committed_cv.notify_all();
@@ -162,6 +167,13 @@ int fmrx_ring_release(fmrx_ring *r) {
     }
     r->freed.notify_all();
     return FMRX_OK;
+}
+
+int fmrx_ring_step_blocks(fmrx_ring *r) {
+    if (!r) return 0;
+    std::lock_guard<std::mutex> lk(r->m);
+    if (r->taken != r->released + 1) return 0;
+    return r->slots[r->released % (long long)r->slots.size()].blocks;
 }
 
 int fmrx_ring_in_flight(fmrx_ring *r) {

@@ -24,12 +24,12 @@ CLI_PATH = os.path.join(PKG_DIR, "fm_radio")
 BLOCK_BYTES = 307200
 IF_PER_BLOCK = 15360
 RDS_PER_BLOCK = 3648
-MAX_EVENTS = 96
+MAX_EVENTS = 160
 MAX_BITS = 80
 RDS_STATE_WORDS = 160
 PROFILE_BINARY, PROFILE_INTENT = 0, 1
 PATH_AUDIO, PATH_RDS, PATH_RDS_STAGES = 1, 2, 4
-NUMERICS_REFERENCE, NUMERICS_FMA = 0, 1
+NUMERICS_REFERENCE, NUMERICS_FMA, NUMERICS_STRICT = 0, 1, 2
 TAPS = dict(demod=0, mono=1, pilot=2, nco=3, stereo_bpf=4, stereo=5, rds_bpf=6, rds_sq=7, rds_nco=8, rds_lpf=9, rds_res=10, rds_rrc=11)
 
 STAGES = ("frontend", "mono", "pilot_bpf", "stereo_bpf", "rds_bpf", "rds_sq_bpf", "pll", "stereo_lpf", "combine", "rds_mix_lpf",
@@ -107,8 +107,9 @@ SIGNATURES = {
     "fmrx_batch_tap_len": (C.c_int, [C.c_void_p, C.c_int]),
     "fmrx_batch_tap": (C.c_int, [C.c_void_p, C.c_int, fp]),
     "fmrx_batch_state_bytes": (C.c_size_t, [C.c_void_p]),
-    "fmrx_batch_get_state": (C.c_int, [C.c_void_p, C.c_void_p]),
-    "fmrx_batch_set_state": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "fmrx_batch_get_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "fmrx_batch_set_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "fmrx_batch_block_id": (C.c_longlong, [C.c_void_p]),
     "fmrx_batch_partition": (C.c_int, [C.c_void_p, i32p, i32p]),
     "fmrx_batch_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Outputs), C.POINTER(C.c_longlong)]),
     "fmrx_batch_wait": (C.c_int, [C.c_void_p, C.c_longlong]),
@@ -132,6 +133,8 @@ SIGNATURES = {
     "fmrx_ring_destroy": (None, [C.c_void_p]),
     "fmrx_ring_acquire": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "fmrx_ring_commit": (C.c_int, [C.c_void_p]),
+    "fmrx_ring_commit_blocks": (C.c_int, [C.c_void_p, C.c_int]),
+    "fmrx_ring_step_blocks": (C.c_int, [C.c_void_p]),
     "fmrx_ring_close": (C.c_int, [C.c_void_p]),
     "fmrx_ring_next": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "fmrx_ring_release": (C.c_int, [C.c_void_p]),
@@ -285,7 +288,7 @@ def frontend(raw, h, zii, ziq, decim=10, want_iq=False):
 
 def rds_decode(rrc, state):
     """rrc: [n] | [B][n] | [S][B][n]; state: int32 [S][160] updated in place.
-    Returns (bits [S][B][80] u8, n_bits [S][B], events [S][B][96] structured, n_events [S][B])."""
+    Returns (bits [S][B][80] u8, n_bits [S][B], events [S][B][MAX_EVENTS] structured, n_events [S][B])."""
     r3 = _as3(rrc)
     S, B, n = r3.shape
     bits = np.zeros((S, B, MAX_BITS), np.uint8)
@@ -558,13 +561,13 @@ class Batch:
 
     def get_state(self):
         buf = np.zeros(lib().fmrx_batch_state_bytes(self.h), np.uint8)
-        check(lib().fmrx_batch_get_state(self.h, buf.ctypes.data_as(C.c_void_p)))
+        check(lib().fmrx_batch_get_state(self.h, buf.ctypes.data_as(C.c_void_p), buf.size))
         return buf
 
     def set_state(self, blob, block_id=None):
         blob = np.ascontiguousarray(blob, np.uint8)
-        check(lib().fmrx_batch_set_state(self.h, blob.ctypes.data_as(C.c_void_p)))
-        self.block_id = int(blob[:8].view(np.int64)[0])
+        check(lib().fmrx_batch_set_state(self.h, blob.ctypes.data_as(C.c_void_p), blob.size))
+        self.block_id = int(lib().fmrx_batch_block_id(self.h))
 
 
 ERR_TIMEOUT, ERR_EOF = -5, -6
@@ -604,8 +607,8 @@ class Ring:
         n = self.batch.S * self.n_blocks * BLOCK_BYTES
         return np.ctypeslib.as_array(C.cast(p, u8p), shape=(n,)).reshape(self.batch.S, self.n_blocks * BLOCK_BYTES)
 
-    def commit(self):
-        check(lib().fmrx_ring_commit(self.h))
+    def commit(self, n_blocks=None):
+        check(lib().fmrx_ring_commit(self.h) if n_blocks is None else lib().fmrx_ring_commit_blocks(self.h, n_blocks))
 
     def close(self):
         check(lib().fmrx_ring_close(self.h))
@@ -616,7 +619,7 @@ class Ring:
         if st == ERR_EOF:
             return None
         self._status(st)
-        S, B, na = self.batch.S, self.n_blocks, self.batch.n_audio
+        S, B, na = self.batch.S, lib().fmrx_ring_step_blocks(self.h), self.batch.n_audio
         res = {}
         if o.audio:
             res["audio"] = np.ctypeslib.as_array(o.audio, shape=(S, B, 2 * na))
@@ -624,6 +627,7 @@ class Ring:
             res["rds_bits"] = np.ctypeslib.as_array(o.rds_bits, shape=(S, B, MAX_BITS))
             res["rds_n_bits"] = np.ctypeslib.as_array(o.rds_n_bits, shape=(S, B))
             res["rds_n_events"] = np.ctypeslib.as_array(o.rds_n_events, shape=(S, B))
+            res["rds_events"] = np.ctypeslib.as_array(C.cast(o.rds_events, i32p), shape=(S, B, MAX_EVENTS, 4)).view(EVENT_DTYPE)[..., 0]
         return res
 
     def release(self):

@@ -25,6 +25,8 @@ def weak_range(per_rank: int, rank: int) -> range:
 
 def owner_of(station: int, n_total: int, world: int) -> int:
     """Inverse of shard_range."""
+    if world <= 0 or n_total < 0 or not 0 <= station < n_total:
+        raise ValueError(f"station {station} is not one of the {n_total} stations dealt over {world} ranks")
     base, extra = divmod(n_total, world)
     split = extra * (base + 1)
     if station < split:

@@ -144,9 +144,12 @@ def station_params(s: int) -> dict:
 
 
 def synth_iq(n_blocks: int, mode: int = 0, seed: int = 1, f_l: float = 1000.0, f_r: float = 3000.0, rds: bool = True,
-             rds_level: float = 0.05, pilot_level: float = 0.08, audio_level: float = 0.45, rds_payload=None) -> np.ndarray:
+             rds_level: float = 0.05, pilot_level: float = 0.08, audio_level: float = 0.45, rds_payload=None, cnr_db=None,
+             noise_seed: int = 0) -> np.ndarray:
     """Returns n_blocks*307200 bytes of interleaved u8 I,Q.  `rds_payload`: a callable n_bits -> bit array (e.g. a
-    programme from rds_group_bits) replacing the random groups of `seed`."""
+    programme from rds_group_bits) replacing the random groups of `seed`.  `cnr_db`: carrier-to-noise ratio of white
+    Gaussian noise added to I and Q ahead of the 8-bit quantiser (carrier power 1, noise power 2 sigma^2 over the full
+    RF rate; None = noiseless), drawn from default_rng(noise_seed)."""
     fs = rf_rate(mode)
     n = n_blocks * BLOCK_IQ
     t = np.arange(n, dtype=np.float64) / fs
@@ -160,8 +163,14 @@ def synth_iq(n_blocks: int, mode: int = 0, seed: int = 1, f_l: float = 1000.0, f
         m = m + rds_level * rds_baseband(rds_chips(bits), t - RDS_T0) * np.cos(3 * th)
     phi = 2 * np.pi * 75e3 * np.cumsum(m) / fs
     out = np.empty(2 * n, dtype=np.uint8)
-    out[0::2] = np.clip(np.rint(127.0 * np.cos(phi) + 128.0), 0, 255).astype(np.uint8)
-    out[1::2] = np.clip(np.rint(127.0 * np.sin(phi) + 128.0), 0, 255).astype(np.uint8)
+    ci, cq = np.cos(phi), np.sin(phi)
+    if cnr_db is not None:
+        sigma = np.sqrt(0.5 * 10.0 ** (-float(cnr_db) / 10.0))
+        rng = np.random.default_rng(noise_seed)
+        ci = ci + sigma * rng.standard_normal(n)
+        cq = cq + sigma * rng.standard_normal(n)
+    out[0::2] = np.clip(np.rint(127.0 * ci + 128.0), 0, 255).astype(np.uint8)
+    out[1::2] = np.clip(np.rint(127.0 * cq + 128.0), 0, 255).astype(np.uint8)
     return out
 
 

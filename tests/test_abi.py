@@ -26,7 +26,7 @@ def test_header_symbols_exported_and_bound():
         assert hasattr(lib, n), f"{n} declared in include/fmrx.h but not exported by libfmrx.so"
         assert n in fmrx.SIGNATURES, f"{n} has no ctypes signature in fmrx.SIGNATURES"
     assert set(fmrx.SIGNATURES) == set(names)
-    assert fmrx.lib().fmrx_version() == 100
+    assert fmrx.lib().fmrx_version() == 101
 
 
 def test_struct_layouts_match_header():

@@ -169,19 +169,46 @@ def test_pll_many_lanes_vs_oracle(port):
 
 
 def test_pll_combine_and_mixer(golden, port):
-    """pllCombine's filter accumulates a double product into fp32 in the reference; here it is one FFMA per tap, so
-    y is within tolerance rather than bit-exact; the loop itself is then compared on IDENTICAL input, bit-exact."""
+    """pllCombine (src/helper.cpp:108-173): the filter accumulates DOUBLE products pow(x,2)*h[k] into a float sum, the loop runs
+    on that sum -- y, the NCO and the carried state bit-exact against the reference's own output; then the mixer filter
+    (src/filter.cpp:373-401, x*x1*h*2 with the half-weight history, Q8), bit-exact too."""
     g = golden["functions"]
     st, zi = np.array(PLL0, F), np.zeros(150, F)
     y, nco = fmrx.pll_combine(g["pllc_x"], g["bpf_sq"], zi, 114000, 240000, 0.5, RDS_PHASE, 0.001, st)
-    assert rel_rms(y, g["pllc_y"]) < TOL
-    z = np.array(PLL0, F)
+    assert_bits(y, g["pllc_y"], "pllCombine y (double products rounded into a float sum)")
+    assert_bits(nco, g["pllc_nco"][:, :-1], "pllCombine NCO")
+    assert_bits(st, g["pllc_state"], "state (ncoLast = the reference's untrimmed element)")
+    z, zo = np.array(PLL0, F), np.zeros(150, F)
     for b in range(y.shape[0]):
-        assert_bits(nco[b], port.pll(y[b], 114000, 240000, 0.5, RDS_PHASE, 0.001, z), "114 kHz loop on the GPU's own y")
-    assert_bits(st, z, "state (ncoLast = the reference's untrimmed element)")
+        ry, rn = port.pll_combine(g["pllc_x"][b], g["bpf_sq"], zo, 114000, 240000, 0.5, RDS_PHASE, 0.001, z)
+        assert_bits(y[b], ry, f"y vs oracle block {b}"); assert_bits(nco[b], rn[:-1], f"nco vs oracle block {b}")
+    assert_bits(zi, zo, "filter state (float squares, one late)")
     zl = np.zeros(150, F)
     m = fmrx.fir_mixer(g["pllc_nco"][:, :-1], g["pllc_x"], g["lpf_3k"], zl)
-    assert rel_rms(m, g["mixer_y"]) < TOL
+    assert_bits(m, g["mixer_y"], "mixer filter")
+
+
+def test_pll_combine_exact_filter_corner_cases(port):
+    """The integer rounding of the exact squared-input filter is valid for normal-float partial sums below 4; everything else
+    (silence, sums in the subnormal-float range, large inputs, a ragged length that leaves a partial tile, history taps at the
+    start of every block) takes the conversion path.  All of it must equal the oracle bit for bit."""
+    rng = np.random.default_rng(11)
+    h = fmrx.design_bpf(113500.0, 114500.0, 240000.0, 151)
+    n = 2500
+    cases = {
+        "noise": rng.standard_normal((3, n)).astype(F) * F(0.2),
+        "large": rng.standard_normal((3, n)).astype(F) * F(40.0),          # sums beyond 4: conversion path
+        "tiny": rng.standard_normal((3, n)).astype(F) * F(3e-19),          # squares ~1e-37: partial sums in the subnormal-float range
+        "silence_then_noise": np.concatenate([np.zeros((3, 1200), F), rng.standard_normal((3, n - 1200)).astype(F)], 1),
+    }
+    for name, x in cases.items():
+        st, zi = np.array(PLL0, F), np.zeros(150, F)
+        y, nco = fmrx.pll_combine(x, h, zi, 114000, 240000, 0.5, RDS_PHASE, 0.001, st)
+        z, zo = np.array(PLL0, F), np.zeros(150, F)
+        for b in range(3):
+            ry, rn = port.pll_combine(x[b], h, zo, 114000, 240000, 0.5, RDS_PHASE, 0.001, z)
+            assert_bits(y[b], ry, f"{name}: y block {b}"); assert_bits(nco[b], rn[:-1], f"{name}: nco block {b}")
+        assert_bits(zi, zo, name + ": state")
 
 
 def test_rds_decoder_bit_exact(golden):

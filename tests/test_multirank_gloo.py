@@ -30,6 +30,9 @@ def test_shard_range_rejects_bad_requests():
         with pytest.raises(ValueError):
             shard.shard_range(*args)
     assert list(shard.weak_range(4, 2)) == [8, 9, 10, 11]
+    for args in [(4096, 4096, 8), (-1, 4096, 8), (5, 5, 8), (0, 0, 3), (3, 10, 0)]:  # a station outside the job has no owner
+        with pytest.raises(ValueError):
+            shard.owner_of(*args)
 
 
 def _free_port():
