@@ -251,14 +251,19 @@ __global__ void __launch_bounds__(NT) fir151_kernel(const FirDev a, const __grid
 // i.e. acc <- (float)((double)acc + ((double)x * (double)x) * (double)h[k]); a history tap (:144) is the plain
 // float multiply-add on the stored float square.  Every partial sum is therefore rounded to 53 bits and then to 24.
 //
-// Per tap: DMUL, DADD, and the rounding to the nearest float (ties to even) done on the bit pattern of the double
-// with integer instructions -- the accumulator stays a double that holds a float value, so there is no conversion
-// instruction on the path (F2F runs at a quarter of the DFMA rate; the integer pipe at twice).  The integer rounding
-// is right while the rounded sum is a normal float; one more integer pair per tap ORs the exponent into a
-// violation mask (exponent outside [2^-126, 4) -- zero included, because a zero sum after the first tap means silence or
-// a complete cancellation), and a thread whose mask is set, whose window reaches into the history (first tile of a
-// block) or whose tile holds a non-finite sample recomputes its outputs with the conversion instructions, tap by tap,
-// exactly as the expression above is written.
+// Per tap: DMUL, DADD, and the rounding to the nearest float (ties to even) done without a conversion instruction: the
+// accumulator stays a double that holds a float value, and RN24(s) = (s + M) - M with M = 1.5 * 2^(e + 29), e the
+// exponent of s -- the first DADD rounds s on the grid ulp53(M) = 2^(e - 23), which is the float grid at s (M's own
+// mantissa is even on that grid, so ties go to even exactly as in the conversion), the second DADD is exact.  Clamping
+// e at -126 makes the grid 2^-149 below the smallest normal float, which is the conversion's gradual underflow.  M is
+// built from the high word of s with three integer instructions (first version: the whole rounding on the bit pattern,
+// 6-7 integer instructions per tap on the half-rate ALU pipe: 3.7 ms per step against 2 ms of FP64 pipe).
+// Two things the identity does not cover are excluded by bounds checked per tile and on the taps -- x = 0 or 1e-8 <= |x| <= 1e12,
+// h = 0 or 1e-12 <= |h| <= 1e10: sums cannot overflow a float (151 * 1e34 < FLT_MAX), and a non-zero sum cannot round to
+// zero, whose sign the identity would lose ((s + M) - M = +0 for a tiny negative s where the conversion gives -0): every
+// non-zero product is >= 2^-93, so every partial sum is a multiple of 2^-149 and representable down to the last subnormal.
+// A tile or tap set outside the bounds, and a thread whose window reaches into the history (first tile of a block), take
+// the expression as written, tap by tap, with the conversion instructions.
 // Tile = 128 threads x 8 consecutive outputs; squares staged once per CTA as doubles (pitch 9: conflict-free LDS.64).
 // ------------------------------------------------------------------------------------------------------------------
 struct TapsD {
@@ -269,15 +274,13 @@ constexpr int SQ_NT = 128, SQ_RO = 8, SQ_LEAD = 152;           // staged samples
 constexpr int SQ_N = SQ_NT * SQ_RO + SQ_LEAD;                  // staged samples per tile
 __host__ __device__ constexpr int sq_phys(int i) { return i + i / SQ_RO; }
 
-__device__ __forceinline__ double round_to_float_kept_double(double s, unsigned &viol) {
-    unsigned long long u = (unsigned long long)__double_as_longlong(s);
-    u += 0x0FFFFFFFull + ((u >> 29) & 1ull);
-    u &= ~0x1FFFFFFFull;
-    viol |= ((unsigned)(u >> 32) - 0x38100000u) & 0x78000000u;  // 0 iff 2^-126 <= |result| < 4
-    return __longlong_as_double((long long)u);
+__device__ __forceinline__ double round_to_float_kept_double(double s) {
+    const int e = max(__double2hiint(s) & 0x7FF00000, 0x38100000);       // exponent field, not below 2^-126
+    const double M = __hiloint2double(e + 0x01D80000, 0);                // 1.5 * 2^(e + 29)
+    return __dsub_rn(__dadd_rn(s, M), M);
 }
 
-__global__ void __launch_bounds__(SQ_NT) fir151_sq_exact_kernel(const FirDev a, const __grid_constant__ Taps taps, const __grid_constant__ TapsD tapsd) {
+__global__ void __launch_bounds__(SQ_NT) fir151_sq_exact_kernel(const FirDev a, const __grid_constant__ Taps taps, const __grid_constant__ TapsD tapsd, int taps_bounded) {
     __shared__ double q[sq_phys(SQ_N) + 1];    // in-block: x^2 (exact in double); history: the stored float square
     __shared__ double hd[kTaps + 1];
     const int s = blockIdx.z, b = blockIdx.y, n0 = blockIdx.x * (SQ_NT * SQ_RO);
@@ -291,7 +294,7 @@ __global__ void __launch_bounds__(SQ_NT) fir151_sq_exact_kernel(const FirDev a, 
         if (p >= 0 && p < a.n) {
             const double x = (double)xs[(long long)b * a.n + p];
             v = __dmul_rn(x, x);
-            finite = finite && (v <= 1.0e300);  // false for inf and NaN
+            finite = finite && (v == 0.0 || (v >= 1.0e-16 && v <= 1.0e24));  // false for inf and NaN too
         } else if (p < 0 && p >= -kHist) {
             v = (double)source<SRC_SQUARE>(a, xs, nullptr, zs, b, p);
         }
@@ -302,23 +305,20 @@ __global__ void __launch_bounds__(SQ_NT) fir151_sq_exact_kernel(const FirDev a, 
 
     const int t = threadIdx.x, o0 = n0 + SQ_RO * t;   // first output of this thread
     float out[SQ_RO];
-    unsigned viol = (o0 < kHist || !tile_finite) ? 1u : 0u;
-    if (!viol) {
+    const bool slow = o0 < kHist || !tile_finite || !taps_bounded;
+    if (!slow) {
         // sample j of the walk is block position o0 + 7 - j = staged index 8t + 159 - j; output r takes it with tap r - 7 + j
         const int base = SQ_RO * t + SQ_LEAD + SQ_RO - 1;
         double acc[SQ_RO];
 #pragma unroll
         for (int r = 0; r < SQ_RO; ++r) acc[r] = 0.0;
-        // ramp up: outputs join one by one (static tap validity); a zero tap is skipped -- x^2 * (+-0) added to a sum that is
-        // never -0 changes nothing, and the reference's filters start with h[0] = 0 (window sin^2), which would only
-        // trip the zero check
+        // ramp up: outputs join one by one (static tap validity)
 #pragma unroll
         for (int j = 0; j < SQ_RO; ++j) {
             const double x2 = q[sq_phys(base - j)];
 #pragma unroll
             for (int r = SQ_RO - 1 - j; r < SQ_RO; ++r) {
-                const double h = hd[r - (SQ_RO - 1) + j];
-                if (h != 0.0) acc[r] = round_to_float_kept_double(__dadd_rn(acc[r], __dmul_rn(x2, h)), viol);
+                acc[r] = round_to_float_kept_double(__dadd_rn(acc[r], __dmul_rn(x2, hd[r - (SQ_RO - 1) + j])));
             }
         }
         // steady state: all eight outputs take every sample; the eight taps in flight slide by one per sample
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(SQ_NT) fir151_sq_exact_kernel(const FirDev a, 
         for (int j = SQ_RO; j < kTaps; ++j) {
             const double x2 = q[sq_phys(base - j)];
 #pragma unroll
-            for (int r = 0; r < SQ_RO; ++r) acc[r] = round_to_float_kept_double(__dadd_rn(acc[r], __dmul_rn(x2, hw[r])), viol);
+            for (int r = 0; r < SQ_RO; ++r) acc[r] = round_to_float_kept_double(__dadd_rn(acc[r], __dmul_rn(x2, hw[r])));
 #pragma unroll
             for (int r = 0; r < SQ_RO - 1; ++r) hw[r] = hw[r + 1];
             hw[SQ_RO - 1] = hd[j + 1];                             // hd[151] = 0: loaded after the last steady sample, never used
@@ -340,12 +340,12 @@ __global__ void __launch_bounds__(SQ_NT) fir151_sq_exact_kernel(const FirDev a, 
             const double x2 = q[sq_phys(base - j)];
 #pragma unroll
             for (int r = 0; r < SQ_RO - 1 - (j - kTaps); ++r)
-                acc[r] = round_to_float_kept_double(__dadd_rn(acc[r], __dmul_rn(x2, hd[r - (SQ_RO - 1) + j])), viol);
+                acc[r] = round_to_float_kept_double(__dadd_rn(acc[r], __dmul_rn(x2, hd[r - (SQ_RO - 1) + j])));
         }
 #pragma unroll
         for (int r = 0; r < SQ_RO; ++r) out[r] = (float)acc[r];
     }
-    if (viol) {
+    if (slow) {
         // the expression as written, with conversion instructions: history taps in float, in-block taps through double
         for (int r = 0; r < SQ_RO; ++r) {
             const int n = o0 + r;
@@ -819,7 +819,11 @@ int launch_fir_dke(const FirJob &j, const FirDev &d, fmrx_stream_t st) {
 
 template <int D, int KIND>
 int launch_fir_dk(const FirJob &j, const FirDev &d, dim3, fmrx_stream_t st) {
-    return j.exact ? launch_fir_dke<D, KIND, true>(j, d, st) : launch_fir_dke<D, KIND, false>(j, d, st);
+    // D = 5: the exact kernel's tile (4 outputs per row, 128 threads) is also the faster one -- 0.146 ms against 0.357 ms for the mono
+    // low-pass of 4096 stations with the fused-multiply-add form (8 outputs per row: a 190-sample window per thread) -- so the
+    // decimating low-pass filters keep the reference's rounding whatever the numerics setting
+    if constexpr (D == 5) return launch_fir_dke<D, KIND, true>(j, d, st);
+    else return j.exact ? launch_fir_dke<D, KIND, true>(j, d, st) : launch_fir_dke<D, KIND, false>(j, d, st);
 }
 
 template <int KIND>
@@ -832,7 +836,12 @@ int launch_fir_k(const FirJob &j, const FirDev &d, dim3 grid, fmrx_stream_t st) 
         for (int k = 0; k < kTaps; ++k) td.h[k] = (double)j.h[k];
         td.h[kTaps] = 0.0;
         dim3 g((d.ny + SQ_NT * SQ_RO - 1) / (SQ_NT * SQ_RO), j.n_blocks, j.n_streams);
-        fir151_sq_exact_kernel<<<g, SQ_NT, 0, st>>>(d, make_taps(j.h), td);
+        int bounded = 1;
+        for (int k = 0; k < kTaps; ++k) {
+            const float m = j.h[k] < 0 ? -j.h[k] : j.h[k];
+            bounded &= (m == 0.0f || (m >= 1e-12f && m <= 1e10f)) ? 1 : 0;  // false for NaN
+        }
+        fir151_sq_exact_kernel<<<g, SQ_NT, 0, st>>>(d, make_taps(j.h), td, bounded);
         e = (int)cudaGetLastError();
     } else if (j.decim == 1) e = launch_fir_dk<1, KIND>(j, d, grid, st);
     else if (j.decim == 5 && (KIND == SRC_PLAIN || KIND == SRC_MIX_LATE)) e = launch_fir_dk<5, (KIND == SRC_PLAIN || KIND == SRC_MIX_LATE) ? KIND : SRC_PLAIN>(j, d, grid, st);
