@@ -52,6 +52,85 @@ STAGE_BYTES = {
 }
 
 
+PROFILE_TAG = "r4"  # profiles/<tag>_ncu_kernels.csv (tools/ncu_trim.py) and profiles/<tag>_sass_mix.json (tools/sass_mix.py)
+# which kernel launches of one chain step make up a bench stage (names as tools/ncu_trim.py shortens them; in launch order)
+STAGE_KERNELS = {
+    "frontend": ("frontend_stream4_kernel<1>", "frontend_edge_kernel<1>", "iq_state_kernel<1>"),
+    "pll": ("pll_kernel",), "combine": ("combine_kernel",), "rds_decode": ("rds_decode_kernel",),
+    "rds_symbols": ("rds_head_kernel<1>", "rds_head_kernel<0>", "rds_symbol_kernel"),
+}
+
+
+def ncu_profile():
+    """{kernel: [rows]} from the tracked ncu summary, or {} when it is missing.  One capture = one chain step of 4096 stations."""
+    import csv
+
+    path = os.path.join(ROOT, "profiles", f"{PROFILE_TAG}_ncu_kernels.csv")
+    out = {}
+    if os.path.exists(path):
+        for r in csv.DictReader(open(path)):
+            out.setdefault(r["kernel"], []).append(r)
+    return out, os.path.relpath(path, ROOT)
+
+
+def stage_traffic(prof, stage, fir_order):
+    """dram read + write bytes of the launches that make up `stage` in the committed capture (4096 stations x 1 block), or None"""
+    def tot(rows):
+        return sum(float(r["dram_read_bytes"]) + float(r["dram_write_bytes"]) for r in rows)
+
+    if stage in STAGE_KERNELS:
+        rows = [r for k in STAGE_KERNELS[stage] for r in prof.get(k, [])]
+        return tot(rows) if rows else None
+    if stage in fir_order:  # the FIR stages share one kernel template: identify the launch by its position among the fir151 launches
+        firs = sorted((r for k, v in prof.items() if k.startswith("fir151") for r in v), key=lambda r: int(r["launch"]))
+        i = fir_order.index(stage)
+        return tot([firs[i]]) if i < len(firs) else None
+    return None
+
+
+def sass_mix():
+    path = os.path.join(ROOT, "profiles", f"{PROFILE_TAG}_sass_mix.json")
+    return (json.load(open(path)) if os.path.exists(path) else {}), os.path.relpath(path, ROOT)
+
+
+def python_models_baseline(blocks=2):
+    """the reference's Python block models on one host core, seconds per 307200-byte block of signal.  Where the
+    reference's model directory is mounted (the authoring container) the UNMODIFIED scripts are timed through runpy (kind
+    "reference"); on the GPU box, where it does not exist, the oracle's statement-by-statement port of the same loops is timed
+    (kind "port": oracle/model_rds.py, pinned bit for bit to the scripts by tests/test_model_rds.py)."""
+    from fmrx import synth
+
+    out = {"cores": 1}
+    model_dir = "/root/reference/model"
+    raw = synth.synth_iq(blocks + 1, 0, seed=2)
+    if os.path.isdir(model_dir):
+        sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+        from make_model_rds_golden import run_script
+
+        t0 = time.perf_counter()
+        _, _, g = run_script(raw[:(blocks + 1) * BLOCK_BYTES])
+        dt = time.perf_counter() - t0
+        out["fmRDSblock"] = {"s_per_block": round(dt / max(1, int(g["block_count"])), 3), "blocks": int(g["block_count"]), "kind": "reference"}
+    from oracle.model_rds import ModelMonoPort, ModelRdsPort
+
+    port = ModelRdsPort()
+    t0 = time.perf_counter()
+    for b in range(blocks):
+        port.block(raw[b * BLOCK_BYTES:(b + 1) * BLOCK_BYTES])
+    out["fmRDSblock_port"] = {"s_per_block": round((time.perf_counter() - t0) / blocks, 3), "blocks": blocks, "kind": "port"}
+    iq = ((raw[:blocks * BLOCK_BYTES].astype(np.float32) - 128.0) / 128.0).astype(np.float32)
+    mono = ModelMonoPort()
+    t0 = time.perf_counter()
+    for b in range(blocks * 3):  # the mono script's block is 102400 values: three per 307200
+        mono.block(iq[b * 102400:(b + 1) * 102400])
+    out["fmMonoBlock_port"] = {"s_per_block": round((time.perf_counter() - t0) / blocks, 3), "blocks": blocks, "kind": "port",
+                               "note": "mono + stereo loop of fmMonoBlock.py, three of its 102400-value blocks per 307200-byte block"}
+    for k in ("fmRDSblock", "fmRDSblock_port", "fmMonoBlock_port"):
+        if k in out:
+            out[k]["msps"] = round(BLOCK_IQ / out[k]["s_per_block"] / 1e6, 3)
+    return out
+
+
 def env_int(name, default):
     return int(os.environ.get(name, default))
 

@@ -300,7 +300,8 @@ int fmrx_model_pll(double *nco, double *nco_q, const double *x, int n_streams, i
 
 /* ---- measurement helpers (used by bench.py; not part of the receive path) ---------------------------------- */
 /* runs an FP32 issue-rate microbenchmark on `device` and returns the best-of-`reps` rate in T lane-ops/s:
- * kind 0 = FFMA, 1 = FMUL+FADD pairs, 2 = packed FFMA2, 3 = packed FMUL2+FADD2 */
+ * kind 0 = FFMA, 1 = FMUL+FADD pairs, 2 = packed FFMA2, 3 = packed FMUL2+FADD2; and the pipes the PLL step leans on:
+ * 4 = DFMA (FP64), 5 = float<->double conversions (F2F pairs), 6 = integer ALU (SHF+LOP3 pairs) */
 int fmrx_measure_fp32_peak(int device, int kind, int reps, double *tera_ops_per_s);
 /* latency roofline of the PLL kernel: SM cycles per step of ONE loop's dependency chain (phase detector -> loop filter ->
  * oscillator, src/helper.cpp:32-45 as csrc/fmrx_pllmath.h computes it) run alone on one warp from registers */

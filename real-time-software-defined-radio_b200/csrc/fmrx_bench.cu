@@ -5,6 +5,10 @@
 //   kind 1: FMUL + FADD     (the reference-exact tap: two roundings, two lane-ops)
 //   kind 2: FFMA2           (sm_100 packed fp32x2: two FMAs per lane per instruction)
 //   kind 3: FMUL2 + FADD2
+// and the issue rates the PLL kernel's bound is made of (its step is ~1/3 FP64 and ~1/8 conversions, csrc/fmrx_pllmath.h):
+//   kind 4: DFMA            (FP64 pipe)
+//   kind 5: F2F.F64.F32 + F2F.F32.F64 pairs (the conversion pipe; 1 lane-op = one conversion)
+//   kind 6: SHF + LOP3      (integer ALU pipe)
 // Reported as tera lane-ops per second.
 #include <cuda_runtime.h>
 
@@ -68,6 +72,67 @@ __global__ void __launch_bounds__(256) fp32_rate_kernel(float *sink, float a, fl
 }
 
 template <int KIND>
+__global__ void __launch_bounds__(256) pipe_rate_kernel(float *sink, double a, double b, int iters) {
+    double d[ILP];
+    float f[ILP];
+    unsigned u[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) { d[i] = threadIdx.x * 1e-3 + i; f[i] = threadIdx.x * 1e-3f + i; u[i] = threadIdx.x * 2654435761u + i; }
+    const unsigned k1 = (unsigned)__double2loint(a) | 1u, k2 = (unsigned)__double2hiint(b);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) {
+            if (KIND == 4) d[i] = __fma_rn(d[i], a, b);
+            if (KIND == 5) {  // F2F.F64.F32 then F2F.F32.F64, kept by the volatile asm (the compiler would fold the round trip away)
+                double t;
+                asm volatile("cvt.f64.f32 %0, %1;" : "=d"(t) : "f"(f[i]));
+                asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(f[i]) : "d"(t));
+            }
+            if (KIND == 6) u[i] = __funnelshift_l(u[i], u[i], 7) ^ (k1 + k2);  // SHF + LOP3
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) s += d[i] + (double)f[i] + (double)u[i];
+    if (s == 123.456) sink[0] = (float)s;
+}
+
+template <int KIND>
+int run_pipe(int reps, double *tera) {
+    cudaDeviceProp prop;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaError_t e = cudaGetDeviceProperties(&prop, dev);
+    if (e) return (int)e;
+    float *sink = nullptr;
+    e = cudaMalloc(&sink, 4);
+    if (e) return (int)e;
+    const int grid = prop.multiProcessorCount * 8, iters = 1024;
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0); cudaEventCreate(&t1);
+    double best = 0.0;
+    for (int r = 0; r < reps + 2; ++r) {
+        cudaEventRecord(t0);
+        pipe_rate_kernel<KIND><<<grid, 256>>>(sink, 0.99999, 1e-4, iters);
+        cudaEventRecord(t1);
+        e = cudaEventSynchronize(t1);
+        if (e) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, t0, t1);
+        // lane-ops per (i, it) per thread: one DFMA; two conversions; two integer instructions
+        const double ops = (double)grid * 256 * iters * ILP * (KIND == 4 ? 1.0 : 2.0);
+        const double rate = ops / (ms * 1e-3) / 1e12;
+        if (r >= 2 && rate > best) best = rate;
+    }
+    launch_counter() += reps + 2;
+    cudaEventDestroy(t0); cudaEventDestroy(t1);
+    cudaFree(sink);
+    if (e) return (int)e;
+    *tera = best;
+    return (int)cudaGetLastError();
+}
+
+template <int KIND>
 int run(int reps, double *tera) {
     cudaDeviceProp prop;
     int dev = 0;
@@ -128,6 +193,9 @@ int measure_fp32_peak(int, int kind, int reps, double *tera) {
         case 1: return run<1>(reps, tera);
         case 2: return run<2>(reps, tera);
         case 3: return run<3>(reps, tera);
+        case 4: return run_pipe<4>(reps, tera);
+        case 5: return run_pipe<5>(reps, tera);
+        case 6: return run_pipe<6>(reps, tera);
         default: return (int)cudaErrorInvalidValue;
     }
 }
