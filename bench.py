@@ -47,8 +47,9 @@ STAGE_MACS = {
 # algorithmic HBM bytes per station-block for the kernel split actually used (u8 in, fp32 intermediates, int16 out)
 STAGE_BYTES = {
     "frontend": BLOCK_BYTES + 4 * NIF, "mono": 4 * NIF + 4 * NAUD, "pilot_bpf": 8 * NIF, "stereo_bpf": 8 * NIF, "rds_bpf": 8 * NIF,
-    "rds_sq_bpf": 8 * NIF, "pll": 16 * NIF, "stereo_lpf": 8 * NIF + 4 * NAUD, "combine": 8 * NAUD + 12 * NAUD * 2 // 2, "rds_mix_lpf": 12 * NIF,
-    "rds_resample": 4 * NIF + 4 * NRDS, "rds_rrc": 8 * NRDS, "rds_decode": 4 * NRDS, "rds_symbols": 4 * NIF + 4 * 152,
+    # pll: two loops, each reads its input and the signal it is mixed with and writes the NCO and the product: 4 x 4 B per loop-sample
+    "rds_sq_bpf": 8 * NIF, "pll": 32 * NIF, "stereo_lpf": 4 * NIF + 4 * NAUD, "combine": 8 * NAUD + 4 * NAUD, "rds_mix_lpf": 8 * NIF,
+    "rds_resample": 4 * NIF + 4 * NRDS, "rds_rrc": 8 * NRDS, "rds_decode": 4 * 152 + 80 + 8 + 2 * 4 * 160, "rds_symbols": 4 * NIF + 4 * 152,
 }
 
 
@@ -302,6 +303,69 @@ def bind_to_gpu_numa_node(index):
         return None
 
 
+def pick_gpu(rank, world, local_rank):
+    """Which visible GPU this rank drives.  With as many ranks as GPUs (or one rank) it is LOCAL_RANK.  With FEWER ranks than visible
+    GPUs the choice matters for the end-to-end figure: on the 8-GPU boxes of this pool four of the GPUs share one host-side limit
+    (GPUs 0-3 together ingest 115 GB/s from page-locked memory, GPUs 4-7 together 214 GB/s, any pair 111 GB/s: profiles/r4_h2d_probe8.json;
+    the virtual PCI tree is flat and reports no NUMA node, so sysfs does not say which).  Rank 0 therefore MEASURES it before anything
+    else runs -- concurrent host-to-device copies only, no kernels -- and grows the set greedily: starting from GPU 0, add the GPU that
+    gives the largest aggregate rate together with those already chosen (ties to the lowest index).  The map is handed to the other
+    ranks through a file in /dev/shm keyed by the launcher's pid (the ranks have no process group yet).  FMRX_GPU_MAP=identity disables it."""
+    import torch
+
+    n_vis = torch.cuda.device_count()
+    info = {"visible_gpus": n_vis, "policy": "identity", "chosen": None}
+    if world == 1 or n_vis <= world or os.environ.get("FMRX_GPU_MAP", "") == "identity":
+        return local_rank, info
+    path = f"/dev/shm/fmrx_gpumap_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}.json"
+    if rank == 0:
+        nbytes, reps = 256 << 20, 3
+        dev, host, streams = [], [], []
+        for i in range(n_vis):
+            torch.cuda.set_device(i)
+            dev.append(torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{i}"))
+            host.append(torch.empty(nbytes, dtype=torch.uint8).pin_memory())
+            streams.append(torch.cuda.Stream(device=i))
+
+        def rate(group):
+            for rep in range(reps + 1):
+                if rep == 1:
+                    for i in group:
+                        streams[i].synchronize()
+                    t0 = time.perf_counter()
+                for i in group:
+                    with torch.cuda.stream(streams[i]):
+                        dev[i].copy_(host[i], non_blocking=True)
+            for i in group:
+                streams[i].synchronize()
+            return len(group) * reps * nbytes / (time.perf_counter() - t0) / 1e9
+
+        chosen, trace = [0], []
+        while len(chosen) < world:
+            cand = {c: rate(chosen + [c]) for c in range(n_vis) if c not in chosen}
+            best = max(cand.values())
+            pick = min(c for c, v in cand.items() if v >= 0.97 * best)
+            trace.append({"with": pick, "gbs": round(cand[pick], 1), "worst_alternative_gbs": round(min(cand.values()), 1)})
+            chosen.append(pick)
+        info.update({"policy": "greedy on measured concurrent H2D rate (rank 0, copies only)", "chosen": chosen, "trace": trace,
+                     "identity_gbs": round(rate(list(range(world))), 1), "chosen_gbs": round(rate(chosen), 1)})
+        del dev, host, streams
+        torch.cuda.empty_cache()
+        tmp = path + ".tmp"
+        json.dump(info, open(tmp, "w"))
+        os.replace(tmp, path)
+    else:
+        t0 = time.time()
+        while not os.path.exists(path) and time.time() - t0 < 300:
+            time.sleep(0.05)
+        if os.path.exists(path):
+            info = json.load(open(path))
+        else:
+            info["policy"] = "identity (no map from rank 0 within 300 s)"
+    chosen = info.get("chosen") or list(range(world))
+    return chosen[local_rank % len(chosen)], info
+
+
 def run_reference_arm(args, rank):
     if rank != 0:
         return
@@ -337,6 +401,8 @@ def run_fmrx_arm(args, rank, world, local_rank):
     import fmrx
     from fmrx import shard, synth
 
+    gpu_index, gpu_map = pick_gpu(rank, world, local_rank)
+    local_rank = gpu_index  # from here on: the CUDA device this rank drives
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None  # pinned buffers are first-touched on the GPU's own node
@@ -423,6 +489,16 @@ def run_fmrx_arm(args, rank, world, local_rank):
     rx.profile(False)
     units = world * S * B * BLOCK_IQ * args.steps
     value = units / (ms_dev * 1e-3) / 1e6
+    # ---- the PLL kernel as it runs in the timed region: pipelined, on its own SM partition, beside the filters of the neighbouring
+    # steps.  Timeline mode keeps the three-stream pipeline and brackets every stage with events on the stream it runs on.
+    n_tl = min(args.steps, 30)
+    rx.profile(2)
+    for _ in range(n_tl):
+        rx.process_device(d_iq.data_ptr(), B, dout)
+    tl = rx.timeline()
+    rx.profile(False)
+    pll_tl = [t1 - t0 for name, t0, t1 in tl if name == "pll"][3:]  # the first steps fill the pipeline
+    pll_pipelined_ms = sum(pll_tl) / len(pll_tl) if pll_tl else None
 
     pll_sms, filter_sms = rx.partition()
     if args.device_only or args.skip_e2e:
@@ -487,9 +563,84 @@ def run_fmrx_arm(args, rank, world, local_rank):
     c1.record()
     torch.cuda.synchronize()
     link_gbs = 5 * h2d / (c0.elapsed_time(c1) * 1e-3) / 1e9
-    link = {"h2d_copy_alone_gbs": round(link_gbs, 1), "h2d_achieved_gbs": round(S * B * BLOCK_BYTES * args.steps / s_e2e / 1e9, 1),
-            "frac_of_link": round(S * B * BLOCK_BYTES * args.steps / s_e2e / 1e9 / link_gbs, 3),
-            "note": "per GPU; the end-to-end path moves 2 bytes per complex sample over PCIe, so the link rate / 2 is its ceiling"}
+    # the same with every rank copying at once, between barriers: the box's ceiling for this many GPUs ingesting together
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        d_iq.copy_(h_iq[0], non_blocking=True)
+    torch.cuda.synchronize()
+    t_all = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    all_gbs = world * 5 * h2d / t_all / 1e9
+    ach_gbs = world * S * B * BLOCK_BYTES * args.steps / s_e2e / 1e9
+    link = {"h2d_copy_alone_gbs": round(link_gbs, 1), "all_ranks_copying_gbs": round(all_gbs, 1), "h2d_achieved_gbs": round(ach_gbs, 1),
+            "frac_of_link": round(ach_gbs / all_gbs, 3), "e2e_ceiling_msps": round(all_gbs / 2.0 * 1e3, 1),
+            "note": "whole job; h2d_copy_alone is this rank's buffer copied back to back while the other ranks do the same without a barrier, all_ranks_copying the "
+                    "same between barriers (the box's ceiling for this many GPUs ingesting at once); the end-to-end path moves 2 bytes per complex sample "
+                    "over PCIe, so that rate / 2 is its ceiling; frac_of_link = achieved / all_ranks_copying"}
+
+    # ---- the same stations through other configurations of the chain, device-resident (each its own handle, same input bytes)
+    def side_figure(n_streams, steps, **kw):
+        with fmrx.Batch(n_streams, mode=0, max_blocks=B, device=local_rank, **kw) as rxs:
+            for _ in range(max(3, args.warmup)):
+                rxs.process_device(d_iq.data_ptr(), B, None)
+            rxs.sync()
+            barrier()
+            s_first = torch.cuda.ExternalStream(fmrx.lib().fmrx_batch_cuda_stream_phase(rxs.h, 0), device=dev)
+            s_last = torch.cuda.ExternalStream(fmrx.lib().fmrx_batch_cuda_stream(rxs.h), device=dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(s_first)
+            for _ in range(steps):
+                rxs.process_device(d_iq.data_ptr(), B, None)
+            e1.record(s_last)
+            rxs.sync()
+            barrier()
+            ms = max_over_ranks(e0.elapsed_time(e1))
+            return ms / steps, dict(zip(("pll_sms", "filter_sms"), rxs.partition()))
+
+    side_steps = max(10, args.steps // 2)
+    sides = {}
+    if not args.skip_mode1:
+        # the north_star's own target figure: the batched MONO front end (front end + mono low-pass + quantiser).  `binary` profile with
+        # the audio path only: the stereo branch is dead after block 0 there, so every timed step is mono only
+        ms, part = side_figure(S, side_steps, profile=fmrx.PROFILE_BINARY, paths=fmrx.PATH_AUDIO)
+        v = world * S * B * BLOCK_IQ / (ms * 1e-3) / 1e6
+        sides["mono_only"] = {"value_msps": round(v, 1), "ms_per_step": round(ms, 4), "realtime_streams": int(v / 2.4), "paths": "front end + mono low-pass + quantiser (binary profile, audio path only)",
+                              "target": "north_star: >= 1000 Msps per B200 on the batched mono front end", "sm_partition": part}
+        for name, num in (("numerics_fma", fmrx.NUMERICS_FMA), ("numerics_strict", fmrx.NUMERICS_STRICT), ("numerics_reference", fmrx.NUMERICS_REFERENCE)):
+            if num == numerics:
+                continue
+            ms, part = side_figure(S, side_steps, profile=fmrx.PROFILE_INTENT, numerics=num)
+            v = world * S * B * BLOCK_IQ / (ms * 1e-3) / 1e6
+            sides[name] = {"value_msps": round(v, 1), "ms_per_step": round(ms, 4), "sm_partition": part}
+        sides["numerics_note"] = ("headline numerics = %s.  reference: audio path and both band-pass filters ahead of / beside the PLLs with the reference's two roundings per tap; "
+                                  "strict: also pllCombine's filter with its double products (whole RDS branch up to the mixer product bit-identical); fma: fused multiply-add "
+                                  "wherever the 1e-5 tolerance allows (include/fmrx.h)" % args.numerics)
+    # ---- BASELINE config 5 as written: 4096 stations in TOTAL, dealt over the ranks (strong scaling); device-resident and end to end
+    strong = None
+    if world > 1 and not args.skip_mode1:
+        mine = shard.shard_range(args.stations, world, rank)
+        Sn = len(mine)
+        ms, part = side_figure(Sn, side_steps, profile=fmrx.PROFILE_INTENT, numerics=numerics)
+        v = args.stations * B * BLOCK_IQ / (ms * 1e-3) / 1e6
+        strong = {"stations_total": args.stations, "stations_per_gpu": Sn, "value_msps": round(v, 1), "ms_per_step": round(ms, 4), "realtime_streams": int(v / 2.4),
+                  "sm_partition": part, "scaling": "strong", "note": "per-GPU batches below 1024 stations sit on the PLL's latency floor (one 64 ms block = 15360 serial steps)"}
+        with fmrx.Batch(Sn, mode=0, profile=fmrx.PROFILE_INTENT, max_blocks=B, device=local_rank, numerics=numerics) as rxs:
+            def steps_e2e(n):
+                tk = []
+                for k in range(n):
+                    tk.append(rxs.submit(h_iq[k % 2].data_ptr(), B, hsets[k % 2]["out"]))
+                    if k >= 1:
+                        rxs.wait(tk[k - 1])
+                rxs.wait(tk[-1])
+            steps_e2e(3)
+            barrier()
+            t0 = time.perf_counter()
+            steps_e2e(side_steps)
+            torch.cuda.synchronize()
+            dt = max_over_ranks(time.perf_counter() - t0)
+            barrier()
+        strong["e2e_msps"] = round(args.stations * B * BLOCK_IQ * side_steps / dt / 1e6, 1)
 
     # ---- the other mode (the metric is per mode): mode 1 = 2.5 Msps, x24 / 125 polyphase audio resamplers, mono + stereo, no RDS
     # (src/fm_radio.cpp:174-180,324); device-resident, same batch size, reported beside the headline in config.mode1
@@ -555,20 +706,33 @@ def run_fmrx_arm(args, rank, world, local_rank):
 
     if rank != 0:
         return
-    # ---- FP32 roofline of the dominant kernel, measured in this run (MEASURED_PEAKS.json has no FP32 figure)
+    # ---- rooflines, every denominator measured in this run (MEASURED_PEAKS.json carries HBM and bf16-tensor peaks only)
     peak_ffma = fmrx.measure_fp32_peak(0, local_rank)      # T FMA/s  -> 2 flop each
     peak_muladd = fmrx.measure_fp32_peak(1, local_rank)    # T lane-ops/s, 1 flop each (the reference-exact tap)
+    rate_dfma = fmrx.measure_fp32_peak(4, local_rank)      # T DFMA/s
+    rate_cvt = fmrx.measure_fp32_peak(5, local_rank)       # T float<->double conversions/s
+    rate_alu = fmrx.measure_fp32_peak(6, local_rank)       # T integer ALU lane-ops/s
     hbm_peak, hbm_src = measured_peaks()
+    prof, prof_path = ncu_profile()
+    mixes, mix_path = sass_mix()
+    fir_order = [n for n in ("mono", "pilot_bpf", "stereo_bpf", "rds_bpf", "rds_sq_bpf", "stereo_lpf") if stage.get(n, (0, 0))[1]]
+    exact_now = {"rds_bpf": numerics != fmrx.NUMERICS_FMA, "rds_sq_bpf": False, "stereo_bpf": numerics != fmrx.NUMERICS_FMA}
     per = {}
     for name, (ms, cnt) in stage.items():
         if cnt == 0:
             continue
         ent = {"ms_per_step": round(ms / args.steps, 4), "share": round(ms / sum(v[0] for v in stage.values()), 4)}
-        if name in STAGE_MACS:
+        if name in STAGE_MACS and not (name == "rds_sq_bpf" and numerics == fmrx.NUMERICS_STRICT):
             macs, exact = STAGE_MACS[name]
+            exact = exact_now.get(name, exact)
             tf = 2.0 * macs * S * B * args.steps / (ms * 1e-3) / 1e12
             pk = peak_muladd if exact else 2.0 * peak_ffma
             ent.update({"tflops": round(tf, 2), "fp32_peak_tflops": round(pk, 2), "frac_fp32": round(tf / pk, 4), "rounding": "mul+add (reference-exact)" if exact else "fma"})
+        if name == "rds_sq_bpf" and numerics == fmrx.NUMERICS_STRICT:
+            # double products rounded into a float sum: 4 FP64 instructions per tap (DMUL, DADD and the DADD pair that rounds to float)
+            taps = NIF * NT * S * B * args.steps
+            ent.update({"fp64_ops_per_tap": 4, "tera_fp64_ops": round(4 * taps / (ms * 1e-3) / 1e12, 2), "fp64_peak_tera_ops": round(rate_dfma, 2),
+                        "frac_fp64": round(4 * taps / (ms * 1e-3) / 1e12 / rate_dfma, 4), "rounding": "double product into a float sum (src/helper.cpp:139)"})
         if name == "rds_symbols":
             # SURVEY 8(d) counts the three stages this kernel pair replaces (mixer LPF 15360 x 151, resampler and RRC 3648 x 151
             # each = 22.3 MAC per complex sample); against that figure -- the work the reference does for the same symbols --
@@ -578,32 +742,78 @@ def run_fmrx_arm(args, rank, world, local_rank):
                         "note": "tflops / frac_fp32 count the MACs this formulation executes (composite filter at the decoder's sampling instants); "
                                 "the *_survey_algorithmic pair counts the MACs of the three full-rate stages it replaces"})
         gbs = STAGE_BYTES[name] * S * B * args.steps / (ms * 1e-3) / 1e9
-        ent.update({"hbm_gbs": round(gbs, 1), "frac_hbm": round(gbs / hbm_peak, 4)})
+        tr = stage_traffic(prof, name, fir_order)
+        ent.update({"hbm_gbs": round(gbs, 1), "frac_hbm": round(gbs / hbm_peak, 4), "algorithmic_bytes": STAGE_BYTES[name] * S * B,
+                    "traffic": None if tr is None else round(tr * S * B / 4096.0), "traffic_over_algorithmic": None if tr is None else round(tr / (STAGE_BYTES[name] * 4096.0), 3)})
         per[name] = ent
-    # the PLL stage has no throughput roofline: 8192 loops = 256 warps on 592 schedulers, each one dependency chain per
-    # sample.  Its bound is the latency of one step of that chain, measured here on one warp running alone from registers.
-    if "pll" in per:
-        sm_mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965
+    # ---- the dominant kernel: pll_kernel.  It is not a throughput kernel on the whole device -- 8192 loops = 256 warps on 592
+    # schedulers, one dependency chain per sample -- so it runs on its own SM partition (2 warps per scheduler on 32 SMs) beside the
+    # filters, and what bounds it THERE is instruction issue: one step is `total` warp-instructions of which `fp64` go down the FP64
+    # pipe and `cvt` + `mufu` down the XU pipe (static SASS count, profiles/*_sass_pll_kernel.txt).  The bound per warp-step on a
+    # scheduler is the largest of the per-pipe issue times at the rates measured above and the one-instruction-per-cycle issue slot.
+    pll = None
+    if "pll" in per and "pll_kernel" in mixes:
+        mx, spi = mixes["pll_kernel"]["per_iteration"], mixes["pll_kernel"]["steps_per_iteration"]
+        sms_total = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        clk = peak_ffma * 1e12 / (sms_total * 128.0)                           # effective SM clock during the microbenchmarks, Hz (FFMA: 128 lanes per clock per SM)
+        per_sched = lambda rate: rate * 1e12 / (sms_total * 4.0) / clk / 32.0  # noqa: E731  warp-instructions per cycle per scheduler on that pipe
+        cyc = {"issue": mx["total"] / spi,
+               "fp64": mx.get("fp64", 0) / spi / per_sched(rate_dfma),
+               "xu": (mx.get("cvt", 0) + mx.get("mufu", 0)) / spi / per_sched(rate_cvt),
+               "alu": mx.get("alu", 0) / spi / per_sched(rate_alu),
+               "fma": (mx.get("fp32", 0) + mx.get("fp32_packed", 0)) / spi / per_sched(peak_ffma)}
+        bound_cyc = max(cyc.values())
+        lanes = S * 2
+        warps = (lanes + 31) // 32
+        steps_total = NIF * B
+        use_sms = pll_sms if pll_sms else sms_total
+        t_used = pll_pipelined_ms if (pll_pipelined_ms and pll_sms) else per["pll"]["ms_per_step"]
+        # time the partition's schedulers need for all warp-steps at the bound; a scheduler cannot be shared below one warp
+        scheds = use_sms * 4
+        t_bound_ms = -(-warps // scheds) * steps_total * bound_cyc / clk * 1e3  # ceil(warps / schedulers) warps take turns on the busiest scheduler
+        ach = lanes * steps_total / (t_used * 1e-3) / 1e9
+        pk = lanes * steps_total / (t_bound_ms * 1e-3) / 1e9
         chain = fmrx.measure_pll_chain(local_rank)
-        cyc = per["pll"]["ms_per_step"] * 1e-3 * sm_mhz * 1e6 / (15360 * B)
-        per["pll"].update({"bound": "latency of the per-sample dependency chain (one loop per lane, 1 warp per scheduler when run alone)",
-                           "cycles_per_step": round(cyc, 1), "chain_latency_cycles": round(chain, 1), "frac_latency": round(chain / cyc, 3),
-                           "sm_mhz_used": sm_mhz})
-    top = max((n for n in per if n in STAGE_MACS), key=lambda n: per[n]["ms_per_step"])
-    roofline = {
+        pll = {"kernel": "pll_kernel", "bound": "issue", "achieved": round(ach, 2), "peak": round(pk, 2), "unit": "G loop-steps/s", "frac": round(ach / pk, 4),
+               "ms_per_launch": round(t_used, 4), "measured": "CUDA events around the kernel on its stream, inside the pipelined run (timeline pass, %d steps), on its %d-SM partition" % (n_tl, use_sms) if (pll_pipelined_ms and pll_sms)
+               else "serialised stage pass on the whole device",
+               "sms": use_sms, "warps": warps, "warps_per_scheduler": round(warps / scheds, 2), "steps_per_launch": steps_total,
+               "scheduler_cycles_per_warp_step": round(t_used * 1e-3 * clk / steps_total / max(1, -(-warps // scheds)), 1),
+               "bound_cycles_per_warp_step": round(bound_cyc, 1), "bound_by_pipe": {k: round(v, 1) for k, v in cyc.items()},
+               "instructions_per_step": {k: round(v / spi, 2) for k, v in mx.items()}, "instruction_mix_source": mix_path,
+               "pipe_rates_tera_lane_ops": {"ffma": round(peak_ffma, 2), "dfma": round(rate_dfma, 2), "f2f": round(rate_cvt, 2), "alu": round(rate_alu, 2)},
+               "clock_hz_effective": round(clk), "alone_on_whole_device_ms": per["pll"]["ms_per_step"],
+               "chain_latency_cycles": round(chain, 1), "latency_floor_ms": round(steps_total * chain / clk * 1e3, 3),
+               "note": "alone on the whole device the kernel sits on its latency floor (one warp per scheduler at most: alone_on_whole_device_ms vs latency_floor_ms); "
+                       "on the partition two warps share a scheduler and the issue bound is the one that matters",
+               "traffic": per["pll"]["traffic"], "algorithmic_bytes": per["pll"]["algorithmic_bytes"], "traffic_source": prof_path}
+        per["pll"].update({"cycles_per_step_alone": round(per["pll"]["ms_per_step"] * 1e-3 * clk / steps_total, 1), "chain_latency_cycles": round(chain, 1)})
+    top = max((n for n in per if n in STAGE_MACS and "tflops" in per[n]), key=lambda n: per[n]["ms_per_step"])
+    fir_roof = {
         "bound": "fp32", "kernel": top, "achieved": per[top]["tflops"], "peak": per[top]["fp32_peak_tflops"], "unit": "TFLOP/s", "frac": per[top]["frac_fp32"],
-        # dram__bytes_read.sum + dram__bytes_write.sum of one front-end launch (4096 stations x 1 block) from the committed
-        # `ncu --set full` capture profiles/r3v_kernels.md: 1.390 GB + 0.241 GB, against 1.510 GB algorithmic
-        "traffic": 1.632e9 * (S * B / 4096.0) if top == "frontend" else None, "traffic_unit": "bytes per launch (ncu, profiles/r3v_kernels.md)",
-        "algorithmic_bytes": STAGE_BYTES[top] * S * B,
+        "traffic": per[top]["traffic"], "traffic_unit": "bytes per launch: dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu capture, " + prof_path,
+        "algorithmic_bytes": per[top]["algorithmic_bytes"],
         "peak_source": "measured in this run by fmrx_measure_fp32_peak: %.2f T FFMA/s (x2 flop), %.2f T FMUL+FADD lane-ops/s; a stage that keeps the "
                        "reference's two roundings per tap is bounded by the latter" % (peak_ffma, peak_muladd),
         "hbm": {"achieved": per[top]["hbm_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": per[top]["frac_hbm"], "peak_source": hbm_src},
-        "stages": per,
     }
+    if pll:
+        roofline = dict(pll)
+        roofline.update({"largest_filter_kernel": fir_roof, "stages": per})
+    else:
+        roofline = dict(fir_roof)
+        roofline["stages"] = per
+    chain_alg = sum(STAGE_BYTES[n] for n in per) * S * B
+    chain_tr = [per[n]["traffic"] for n in per]
+    roofline["chain_traffic"] = {"algorithmic_bytes_per_step": chain_alg, "traffic_bytes_per_step": None if any(t is None for t in chain_tr) else int(sum(chain_tr)),
+                                 "fused_floor_bytes_per_step": int(2.08 * BLOCK_IQ * S * B), "source": prof_path}
     cores = host_cores()
     cpu_msps, cpu_kind, cpu_dt = cpu_reference_run(args.cpu_blocks, cores)
     cpu1_msps, _, cpu1_dt = cpu_reference_run(args.cpu_blocks, 1)
+    try:
+        py_models = python_models_baseline()
+    except Exception as e:  # same rule as the per-stage table below
+        py_models = {"error": repr(e)}
     try:
         cpu_stages, cpu_stage_kind = cpu_stage_times()
     except Exception as e:  # the per-stage table is an explanation, not a result: never let it take the bench line down
@@ -612,10 +822,11 @@ def run_fmrx_arm(args, rank, world, local_rank):
         "metric": "IQ Msps (complex samples/s, whole job)", "value": round(value, 1), "unit": "Msps", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_dev / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "batch4096_mode0_stereo_rds", "stations_per_gpu": S, "blocks_per_step": B, "mode": 0, "profile": "intent", "paths": "mono+stereo+rds",
-                   "numerics": "audio path reference-exact (mul+add), RDS path fma",
+                   "numerics": args.numerics, "mono_only": sides.get("mono_only"), "numerics_fma": sides.get("numerics_fma"), "numerics_strict": sides.get("numerics_strict"),
+                   "numerics_reference": sides.get("numerics_reference"), "numerics_note": sides.get("numerics_note"), "strong_4096_total": strong,
                    "sm_partition": {"pll_sms": pll_sms, "filter_sms": filter_sms} if pll_sms else "none (phases share the device)", "realtime_streams": int(value / 2.4), "e2e_realtime_streams": int(e2e_value / 2.4),
                    "l2": "input per step %.2f GB >> 126 MB L2, no flush needed" % (S * B * BLOCK_BYTES / 1e9), "input_reuse": "same synthesised block replayed each step, state carried",
-                   "synth_seconds": round(t_synth, 2), "parity_spot_check": parity, "rank0_numa_node": numa,
+                   "synth_seconds": round(t_synth, 2), "parity_spot_check": parity, "rank0_numa_node": numa, "gpu_map": gpu_map,
                    "e2e_timer": "host clock around K fmrx_batch_submit calls with fmrx_batch_wait on the previous step (two steps in flight), barrier + synchronize on both sides, max over ranks",
                    "e2e_sync_call_msps": round(e2e_sync_value, 1), "e2e_link": link, "single_stream": single, "mode1": mode1, "mode2_44k1": mode2},
         "e2e": {"value": round(e2e_value, 1), "unit": "Msps", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world},  # whole job, like `value`
@@ -625,6 +836,7 @@ def run_fmrx_arm(args, rank, world, local_rank):
         "cpu_baseline": {"value": round(cpu_msps, 3), "unit": "Msps", "cores": cores, "kind": cpu_kind,
                          "sample": f"{cores} concurrent processes x {args.cpu_blocks} blocks of the same mode-0 workload ({cpu_dt:.1f} s wall)",
                          "single_process": {"value": round(cpu1_msps, 3), "unit": "Msps", "sample": f"1 process x {args.cpu_blocks} blocks ({cpu1_dt:.1f} s)"},
+                         "python_models": py_models,
                          "stages_ms_per_block_one_core": cpu_stages, "stages_kind": cpu_stage_kind,
                          "stages_note": "the reference's functions on one host core, one mode-0 block per call (SURVEY 8d ii); hold against "
                                         "roofline.stages[*].ms_per_step / stations_per_gpu for the GPU's time per station-block"},

@@ -55,7 +55,18 @@ int fmrx_design_lpf(float Fs, float Fc, unsigned short ntaps, float *h); /* impu
 int fmrx_design_bpf(float Fb, float Fe, float Fs, int ntaps, float *h);  /* impulseResponseBPF, src/filter.cpp:41-60 */
 int fmrx_design_rrc(float Fs, int ntaps, float *h);                      /* impulseResponseRRC, src/filter.cpp:63-93 */
 
+/* quality-profile design helpers (host, double): response of a real FIR at f; impulseResponseBPF scaled to unit gain at its band
+ * centre; the NCO phase adjust that lines the regenerated RDS carrier up with the RDS band (-arg H_sq(f2) / 2); the bilinear
+ * de-emphasis coefficients of y[n] = b (x[n] + x[n-1]) - a1 y[n-1] */
+int fmrx_fir_response(const float *h, int ntaps, float Fs, float f, double *mag, double *phase);
+int fmrx_design_bpf_unity(float Fb, float Fe, float Fs, int ntaps, float *h);
+int fmrx_rds_auto_phase(const float *h_sq, int ntaps, float Fs, float f2, float *phase_adj);
+int fmrx_deemphasis_coeffs(float tau_us, float Fs, double *b, double *a1);
+
 /* ---- function-level operators (GPU; host buffers) ------------------------------------------------------------ */
+/* de-emphasis + the reference's quantiser (src/fm_radio.cpp:290-298) on interleaved L,R float audio: audio_f:[S][B][2n] filtered in
+ * place, audio:[S][B][2n] int16 (may be NULL), state:[S][4] = x[-1], y[-1] of L, then of R (zero before the first block) */
+int fmrx_deemphasis(float *audio_f, int16_t *audio, int n_streams, int n_blocks, int n, float tau_us, float Fs, int mult, float *state);
 /* readStdInBlock's conversion, src/iofunc.cpp:61-69: out[k] = (raw[k]-128)/128 */
 int fmrx_unpack_iq(const uint8_t *raw, size_t n, float *out);
 /* convolveWithDecim / convolveWithDecimPointer, src/filter.cpp:126-185.  x:[S][B][n] y:[S][B][n/decim] zi:[S][nzi];
@@ -128,6 +139,19 @@ enum { FMRX_PATH_AUDIO = 1, FMRX_PATH_RDS = 2, FMRX_PATH_RDS_STAGES = 4 };
  *   ahead of a PLL decides the fp32 rounding of the oscillator argument, src/helper.cpp:41). */
 enum { FMRX_NUMERICS_REFERENCE = 0, FMRX_NUMERICS_FMA = 1, FMRX_NUMERICS_STRICT = 2 };
 
+/* `quality` profile: what the reference's own report proposes and the program never got -- NEVER the default,
+ * because with any of these set the output is no longer the reference's:
+ *  FMRX_QUALITY_DEEMPH_75 / _50: de-emphasis 1 / (1 + s tau), tau = 75 us (Americas, Korea) or 50 us, bilinear transform at the
+ *    audio rate, on L and R ahead of the quantiser (the reference quantises the low-pass output as is, src/fm_radio.cpp:277-299);
+ *  FMRX_QUALITY_UNITY_BPF: the four band-pass filters scaled to unit gain at their band centre (impulseResponseBPF has 0.308 at
+ *    19 kHz, src/filter.cpp:41-60), the stereo mixer with the x2 a product of two cosines needs (the reference mixes x1,
+ *    src/fm_radio.cpp:271; its Python model x2, model/fmMonoBlock.py:155-156), and the L+R branch delayed by the 75 IF samples
+ *    (15 at 48 kHz) the L-R branch spends in its extra band-pass -- together: L-R at the gain and timing of L+R, i.e. stereo
+ *    separation instead of the reference's level-and-delay mismatch;
+ *  FMRX_QUALITY_AUTO_RDS_PHASE: the 114 kHz NCO's phase adjust computed from the response of pllCombine's filter at 114 kHz
+ *    (fmrx_rds_auto_phase) instead of the hand-tuned constant of src/fm_radio.cpp:342,400 (14 degrees off on the reference's taps). */
+enum { FMRX_QUALITY_DEEMPH_75 = 1, FMRX_QUALITY_DEEMPH_50 = 2, FMRX_QUALITY_UNITY_BPF = 4, FMRX_QUALITY_AUTO_RDS_PHASE = 8 };
+
 typedef struct {
     int32_t mode;       /* 0: 2.4 Msps, /10, /5, +RDS ; 1: 2.5 Msps, /10, x24 /125, no RDS (src/fm_radio.cpp:36-37,174-180);
                          * 2 (extension, not in the reference's main()): mode 0's front end and RDS path with the audio
@@ -138,7 +162,7 @@ typedef struct {
     int32_t device;     /* CUDA device ordinal */
     int32_t paths;      /* FMRX_PATH_* mask; 0 = all the mode has */
     int32_t numerics;   /* FMRX_NUMERICS_* */
-    int32_t reserved;
+    int32_t quality;    /* FMRX_QUALITY_* mask; 0 = the reference's receiver */
 } fmrx_config;
 
 typedef struct fmrx_batch fmrx_batch;
@@ -183,6 +207,10 @@ int fmrx_batch_partition(const fmrx_batch *, int *pll_sms, int *filter_sms);
 long long fmrx_batch_launch_count(const fmrx_batch *); /* kernels launched by this handle so far */
 /* per-stream initial_offset of the RDS decoder (host int32[S]) */
 int fmrx_batch_rds_offsets(fmrx_batch *, int32_t *offsets);
+/* the 114 kHz NCO's phase adjust in use (the reference's constant, or the computed one under FMRX_QUALITY_AUTO_RDS_PHASE); the
+ * setter is for experiments (phase sweeps): it takes effect from the next process call */
+float fmrx_batch_rds_phase(const fmrx_batch *);
+int fmrx_batch_set_rds_phase(fmrx_batch *, float phase_adj);
 
 /* intermediate signals of the most recent process call, for per-stage parity tests: copies [S][n_blocks][len] floats */
 enum {

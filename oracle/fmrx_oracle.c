@@ -441,6 +441,10 @@ struct orc_chain {
     float rds_pll_st[6], rds_phase;
     float *rbpf, *rsq, *rnco, *rlpf, *rres, *rrrc;
     int n_rds;
+    /* quality profile (not in the reference: SURVEY 8f row 4; restated from include/fmrx.h FMRX_QUALITY_*) */
+    int quality, mono_delay;
+    float mono_tail[16];
+    double de_b, de_a1, de_state[4]; /* x[-1], y[-1] of L, then of R */
     /* frame_thread (:444-729) */
     orc_rds_decoder *dec;
     uint8_t bits[128];
@@ -510,6 +514,45 @@ void orc_chain_destroy(orc_chain *c) {
     free(c);
 }
 
+/* response of a real FIR at f: the double sums the product's host code forms (csrc/fmrx_design.cpp fmrx_fir_response) */
+static void fir_response(const float *h, int n, double Fs, double f, double *mag, double *phase) {
+    double re = 0.0, im = 0.0, w = 2.0 * ORC_PI * f / Fs;
+    for (int k = 0; k < n; k++) { re += (double)h[k] * cos(w * k); im -= (double)h[k] * sin(w * k); }
+    if (mag) *mag = hypot(re, im);
+    if (phase) *phase = atan2(im, re);
+}
+static void unity(float *h, int n, float Fb, float Fe, float Fs) {
+    double mag;
+    fir_response(h, n, (double)Fs, (double)((Fb + Fe) / 2.0f), &mag, NULL);
+    for (int k = 0; k < n; k++) h[k] = (float)((double)h[k] / mag);
+}
+
+/* flags as FMRX_QUALITY_*: 1 / 2 de-emphasis 75 / 50 us, 4 unity-gain band-pass filters + x2 stereo mixer + delayed mono, 8 computed
+ * RDS phase adjust.  Call right after orc_chain_create. */
+void orc_chain_set_quality(orc_chain *c, int flags) {
+    c->quality = flags;
+    float bpf_Fs = c->mode == 1 ? 6000000.0f : 240000.0f;
+    if (flags & 4) {
+        unity(c->h_pilot, NT, 18.5e3f, 19.5e3f, bpf_Fs);
+        unity(c->h_sbpf, NT, 22e3f, 54e3f, bpf_Fs);
+        unity(c->h_rbpf, NT, 54000.0f, 60000.0f, 240000.0f);
+        unity(c->h_sq, NT, 113500.0f, 114500.0f, 240000.0f);
+        for (int k = 0; k < c->audio_taps; k++) c->h_stereo[k] *= 2.0f;
+        c->mono_delay = (int)((75L * c->audio_up + c->audio_decim / 2) / c->audio_decim);
+    }
+    if (flags & 8) {
+        double ph;
+        fir_response(c->h_sq, NT, 240000.0, 114000.0, NULL, &ph);
+        c->rds_phase = (float)(-0.5 * ph);
+    }
+    if (flags & 3) {
+        float rate = (float)((double)(c->mode == 1 ? 250000.0 : 240000.0) * c->audio_up / c->audio_decim);
+        double k = 2.0 * (double)rate * (double)((flags & 1) ? 75.0f : 50.0f) * 1e-6;
+        c->de_b = 1.0 / (1.0 + k);
+        c->de_a1 = (1.0 - k) / (1.0 + k);
+    }
+}
+
 int orc_chain_audio_per_block(const orc_chain *c) { return c->n_audio; }
 void orc_chain_set_paths(orc_chain *c, int mask) { c->paths = mask; }
 
@@ -547,10 +590,24 @@ int orc_chain_block(orc_chain *c, const uint8_t *raw, int16_t *audio) {
             for (int i = 0; i < na; i++) c->stereo[i] = 0.0f;
         }
         for (int i = 0; i < na; i++) { /* :247-252/:277-282 */
-            float l = (c->mono[i] + c->stereo[i]) / 2.0f, r = (c->mono[i] - c->stereo[i]) / 2.0f;
+            float m = c->mono[i];
+            if (c->mono_delay) m = i >= c->mono_delay ? c->mono[i - c->mono_delay] : c->mono_tail[i]; /* quality: L+R as late as L-R */
+            float l = (m + c->stereo[i]) / 2.0f, r = (m - c->stereo[i]) / 2.0f;
+            if (c->de_b != 0.0) { /* quality: 1/(1 + s tau), bilinear, in double (scipy.signal.lfilter's recurrence); a NaN sample counts as 0 */
+                float in[2] = {isnan(l) ? 0.0f : l, isnan(r) ? 0.0f : r};
+                float out[2];
+                for (int ch = 0; ch < 2; ch++) {
+                    double y = c->de_b * ((double)in[ch] + c->de_state[2 * ch]) - c->de_a1 * c->de_state[2 * ch + 1];
+                    c->de_state[2 * ch] = (double)in[ch];
+                    c->de_state[2 * ch + 1] = y;
+                    out[ch] = (float)y;
+                }
+                l = out[0]; r = out[1];
+            }
             c->audio_f[2 * i] = l; c->audio_f[2 * i + 1] = r;
             if (audio) { audio[2 * i] = quantise(l, c->mult); audio[2 * i + 1] = quantise(r, c->mult); }
         }
+        for (int j = 0; j < c->mono_delay; j++) c->mono_tail[j] = c->mono[na - c->mono_delay + j];
     }
 
     /* ---- rds_thread (:395-411) + frame_thread: not in mode 1 (:324, :446); mode 2 has mode 0's 240 kHz IF, so it runs ---- */

@@ -88,6 +88,8 @@ int orc_chain_rds_events(const orc_chain *, orc_rds_event *ev, int cap);
 int orc_chain_rds_offset(const orc_chain *);
 /* stage switches for timing: bit0 mono/stereo, bit1 rds (default 3) */
 void orc_chain_set_paths(orc_chain *, int mask);
+/* FMRX_QUALITY_* of include/fmrx.h: the quality profile is NOT in the reference; call right after create */
+void orc_chain_set_quality(orc_chain *, int flags);
 
 #ifdef __cplusplus
 }

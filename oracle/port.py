@@ -176,10 +176,12 @@ class RdsDecoder:
 class Chain:
     """Sequential composition of the four thread bodies of src/fm_radio.cpp (profile 0 = binary, 1 = intent)."""
 
-    def __init__(self, mode=0, profile=0, paths=3):
+    def __init__(self, mode=0, profile=0, paths=3, quality=0):
         self.lib = load_port()
         self.h = C.c_void_p(self.lib.orc_chain_create(mode, profile))
         self.lib.orc_chain_set_paths(self.h, paths)
+        if quality:
+            self.lib.orc_chain_set_quality(self.h, quality)
         self.mode = mode
         self.n_audio = self.lib.orc_chain_audio_per_block(self.h)
         self.block_id = 0

@@ -219,6 +219,20 @@ int fmrx_frontend(float *demod, float *yi, float *yq, const uint8_t *raw, int n_
     return FMRX_OK;
 }
 
+int fmrx_deemphasis(float *audio_f, int16_t *audio, int n_streams, int n_blocks, int n, float tau_us, float Fs, int mult, float *state) {
+    if (!audio_f || !state || n_streams <= 0 || n_blocks <= 0 || n <= 0 || n > 24000) return fail(FMRX_ERR_ARG, "fmrx_deemphasis: bad argument");
+    double bb, a1;
+    if (int e = fmrx_deemphasis_coeffs(tau_us, Fs, &bb, &a1)) return e;
+    const size_t nx = (size_t)n_streams * n_blocks * 2 * n;
+    Dev<float> df, ds; Dev<int16_t> da;
+    CU(df.up(audio_f, nx)); CU(ds.up(state, (size_t)n_streams * 4));
+    if (audio) CU(da.alloc(nx));
+    LAUNCH(launch_deemphasis(df.p, audio ? da.p : nullptr, (long long)n_blocks * 2 * n, n, n_blocks, n_streams, bb, a1, mult, ds.p, 1, nullptr));
+    CU(df.down(audio_f, nx)); CU(ds.down(state, (size_t)n_streams * 4));
+    if (audio) CU(da.down(audio, nx));
+    return FMRX_OK;
+}
+
 int fmrx_rds_decode(const float *rrc, int n_streams, int n_blocks, int n, uint8_t *bits, int32_t *n_bits, fmrx_rds_event *events,
                     int32_t *n_events, int32_t *state) {
     if (!rrc || !state || n_streams <= 0 || n_blocks <= 0 || n < 24 * 8 || n / 24 / 2 + 1 > FMRX_MAX_BITS) return fail(FMRX_ERR_ARG, "fmrx_rds_decode: bad argument");
@@ -293,6 +307,10 @@ struct fmrx_batch {
     float h_rf[kTaps], h_pilot[kTaps], h_sbpf[kTaps], h_rbpf[kTaps], h_sq[kTaps], h_lpf3k[kTaps], h_rrc[kTaps];
     std::vector<float> h_mono, h_stereo, h_anti;
     float rds_phase = 0.f;
+    // quality profile (FMRX_QUALITY_*): de-emphasis coefficients (b == 0: off), mono delay in audio samples (0: off) and their states
+    double de_b = 0.0, de_a1 = 0.0;
+    int mono_delay = 0;
+    float *mono_tail = nullptr, *deemph_st = nullptr;
     // device
     float *d_h_mono = nullptr, *d_h_stereo = nullptr, *d_h_anti = nullptr, *d_hp_mono = nullptr, *d_hp_stereo = nullptr;
     char *d_state = nullptr;  // one blob: every carried state
@@ -501,7 +519,13 @@ int enqueue_chain(fmrx_batch *b, const uint8_t *iq, long long ld_iq, int s0, int
         CombineJob c{};
         c.mono = AU2(b->mono); c.stereo = stereo; c.audio = b->audio + (long long)s0 * lda * 2; c.audio_f = b->want_audio_f ? b->audio_f + (long long)s0 * lda * 2 : nullptr;  // the float copy is 2/3 of this kernel's writes: only when asked for
         c.ld = lda; c.n_total = nblk * b->n_audio; c.n_streams = ns; c.mult = b->mult;
+        c.mono_delay = b->mono_delay; c.mono_tail = b->mono_delay ? b->mono_tail + (long long)s0 * 16 : nullptr;
+        const bool deemph = b->de_b != 0.0;
+        if (deemph) { c.audio = nullptr; c.audio_f = b->audio_f + (long long)s0 * lda * 2; }  // the quantiser moves behind the de-emphasis
         LAUNCH(launch_combine(c, st));
+        if (deemph)
+            LAUNCH(launch_deemphasis(b->audio_f + (long long)s0 * lda * 2, b->audio + (long long)s0 * lda * 2, lda * 2, b->n_audio, nblk, ns, b->de_b, b->de_a1, b->mult,
+                                     b->deemph_st + (long long)s0 * 4, b->want_audio_f ? 1 : 0, st));
     }
     // ---- rds_thread after the PLL (:404-411) and frame_thread
     if (b->rds_on) {
@@ -604,6 +628,24 @@ int fmrx_batch_create(const fmrx_config *cfg, fmrx_batch **out) {
     fmrx_design_rrc(57000.0f, kTaps, b->h_rrc);                                         // :370
     const float phase_adj = (float)(kPi / 3.3 - kPi / 1.5);                             // :342
     b->rds_phase = (float)((double)phase_adj - kPi / 1.4);                              // :400
+    // ---- quality profile: never the default (the output is no longer the reference's)
+    if (cfg->quality & ~(FMRX_QUALITY_DEEMPH_75 | FMRX_QUALITY_DEEMPH_50 | FMRX_QUALITY_UNITY_BPF | FMRX_QUALITY_AUTO_RDS_PHASE))
+        return fail(FMRX_ERR_ARG, "fmrx_batch_create: unknown quality flag in %d", cfg->quality);
+    if ((cfg->quality & FMRX_QUALITY_DEEMPH_75) && (cfg->quality & FMRX_QUALITY_DEEMPH_50)) return fail(FMRX_ERR_ARG, "fmrx_batch_create: one de-emphasis time constant, not two");
+    if (cfg->quality & FMRX_QUALITY_UNITY_BPF) {
+        fmrx_design_bpf_unity(18.5e3f, 19.5e3f, bpf_Fs, kTaps, b->h_pilot);
+        fmrx_design_bpf_unity(22e3f, 54e3f, bpf_Fs, kTaps, b->h_sbpf);
+        fmrx_design_bpf_unity(54000.0f, 60000.0f, 240000.0f, kTaps, b->h_rbpf);
+        fmrx_design_bpf_unity(113500.0f, 114500.0f, 240000.0f, kTaps, b->h_sq);
+        for (float &v : b->h_stereo) v *= 2.0f;  // the x2 of the stereo mixer, folded into the (linear) low-pass behind it: exact
+        // the L-R branch spends 75 IF samples more in filters than L+R: in audio samples 75 * U / D (15 in mode 0, rounded otherwise)
+        b->mono_delay = (int)((75LL * b->up + b->decim_a / 2) / b->decim_a);
+    }
+    if (cfg->quality & FMRX_QUALITY_AUTO_RDS_PHASE) fmrx_rds_auto_phase(b->h_sq, kTaps, 240000.0f, 114000.0f, &b->rds_phase);
+    if (cfg->quality & (FMRX_QUALITY_DEEMPH_75 | FMRX_QUALITY_DEEMPH_50)) {
+        const float audio_rate = (float)((double)(cfg->mode == 1 ? 250000.0 : 240000.0) * b->up / b->decim_a);
+        fmrx_deemphasis_coeffs((cfg->quality & FMRX_QUALITY_DEEMPH_75) ? 75.0f : 50.0f, audio_rate, &b->de_b, &b->de_a1);
+    }
 
     const size_t S = b->S, NB = b->NB;
     b->set_if = S * NB * NIF; b->set_au = S * NB * b->n_audio;
@@ -614,7 +656,7 @@ int fmrx_batch_create(const fmrx_config *cfg, fmrx_batch **out) {
         {(void **)&b->zi_mono, S * b->nzi_a * 4}, {(void **)&b->zi_pilot, S * b->nzi_b * 4}, {(void **)&b->zi_sbpf, S * b->nzi_b * 4}, {(void **)&b->zi_stereo, S * b->nzi_a * 4},
         {(void **)&b->pll_st, S * 6 * 4}, {(void **)&b->zi_rbpf, S * kHist * 4}, {(void **)&b->zi_sq, S * kHist * 4}, {(void **)&b->zi_lpf, S * kHist * 4},
         {(void **)&b->zi_rrc, S * kHist * 4}, {(void **)&b->zi_anti, S * (kTaps * 19 - 1) * 4}, {(void **)&b->rds_pll_st, S * 6 * 4},
-        {(void **)&b->dec_st, S * FMRX_RDS_STATE_WORDS * 4}};
+        {(void **)&b->dec_st, S * FMRX_RDS_STATE_WORDS * 4}, {(void **)&b->mono_tail, S * 16 * 4}, {(void **)&b->deemph_st, S * 4 * 4}};
     size_t total = 0;
     for (auto &sg : segs) total += (sg.bytes + 255) & ~(size_t)255;
     b->state_bytes = total;
@@ -864,6 +906,13 @@ int fmrx_batch_rds_offsets(fmrx_batch *b, int32_t *offsets) {
     return FMRX_OK;
 }
 
+float fmrx_batch_rds_phase(const fmrx_batch *b) { return b ? b->rds_phase : 0.0f; }
+int fmrx_batch_set_rds_phase(fmrx_batch *b, float phase_adj) {
+    if (!b || !(phase_adj == phase_adj)) return fail(FMRX_ERR_ARG, "fmrx_batch_set_rds_phase: bad argument");
+    b->rds_phase = phase_adj;
+    return FMRX_OK;
+}
+
 int fmrx_batch_tap_len(const fmrx_batch *b, int which) {
     if (!b) return 0;
     switch (which) {
@@ -896,7 +945,7 @@ struct StateHeader {
     uint64_t state_bytes;
     long long block_id;
 };
-constexpr uint32_t kStateMagic = 0x58524D46u, kStateLayout = 2;  // bump kStateLayout when a segment or the decoder words (fmrx_rds.cu W_*) change
+constexpr uint32_t kStateMagic = 0x58524D46u, kStateLayout = 3;  // bump kStateLayout when a segment or the decoder words (fmrx_rds.cu W_*) change
 StateHeader make_header(const fmrx_batch *b) {
     StateHeader h{};
     h.magic = kStateMagic; h.version = kStateLayout; h.mode = b->cfg.mode; h.profile = b->cfg.profile; h.n_streams = b->S;

@@ -79,3 +79,54 @@ extern "C" int fmrx_design_rrc(float Fs, int ntaps, float *h) {
     }
     return FMRX_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// `quality` profile: what the reference's report proposes and never built.  None of this is in the
+// reference's signal path, so there is nothing to be bit-identical with; the arithmetic is double on the host.
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" int fmrx_fir_response(const float *h, int ntaps, float Fs, float f, double *mag, double *phase) {
+    if (!h || ntaps <= 0 || !(Fs > 0.0f)) return fmrx::fail(FMRX_ERR_ARG, "fmrx_fir_response: bad argument");
+    double re = 0.0, im = 0.0;
+    const double w = 2.0 * kPi * static_cast<double>(f) / static_cast<double>(Fs);
+    for (int k = 0; k < ntaps; ++k) {
+        re += static_cast<double>(h[k]) * std::cos(w * k);
+        im -= static_cast<double>(h[k]) * std::sin(w * k);
+    }
+    if (mag) *mag = std::hypot(re, im);
+    if (phase) *phase = std::atan2(im, re);
+    return FMRX_OK;
+}
+
+// impulseResponseBPF scaled to unit gain at the centre of its pass band (the reference's has 0.308 at 19 kHz, src/filter.cpp:41-60:
+// the cosine modulation halves a low-pass prototype whose own gain the sin^2 window already lowered)
+extern "C" int fmrx_design_bpf_unity(float Fb, float Fe, float Fs, int ntaps, float *h) {
+    if (int e = fmrx_design_bpf(Fb, Fe, Fs, ntaps, h)) return e;
+    double mag = 0.0;
+    fmrx_fir_response(h, ntaps, Fs, (Fb + Fe) / 2.0f, &mag, nullptr);
+    if (!(mag > 0.0)) return fmrx::fail(FMRX_ERR_ARG, "fmrx_design_bpf_unity: the filter has no gain at its band centre");
+    for (int k = 0; k < ntaps; ++k) h[k] = static_cast<float>(static_cast<double>(h[k]) / mag);
+    return FMRX_OK;
+}
+
+// The phase the 114 kHz NCO has to be turned by so that the regenerated 57 kHz carrier lines up with the RDS band it is mixed with
+// -- what the reference tunes by hand (phaseAdjust = pi/3.3 - pi/1.5, then "- PI/1.4", src/fm_radio.cpp:342,400).  The RDS band
+// r = m cos(w n + p) is squared and band-passed (pllCombine's filter, response H at 2w): the loop locks to 2 w n + 2 p + arg H(2w),
+// the NCO halves that (ncoScale 0.5), and its output for sample n is the one computed for it (the one-sample delay of ncoOut and the
+// "+1" of trigArg cancel): cos(w n + p + arg H(2w) / 2 + adj).  Mixing with r is coherent for adj = -arg H(2w) / 2 (mod pi; the
+// polarity is irrelevant behind a differential decoder).
+extern "C" int fmrx_rds_auto_phase(const float *h_sq, int ntaps, float Fs, float f2, float *phase_adj) {
+    if (!phase_adj) return fmrx::fail(FMRX_ERR_ARG, "fmrx_rds_auto_phase: null pointer");
+    double ph = 0.0;
+    if (int e = fmrx_fir_response(h_sq, ntaps, Fs, f2, nullptr, &ph)) return e;
+    *phase_adj = static_cast<float>(-0.5 * ph);
+    return FMRX_OK;
+}
+
+// 1 / (1 + s tau) through the bilinear transform at Fs: y[n] = b (x[n] + x[n-1]) - a1 y[n-1]
+extern "C" int fmrx_deemphasis_coeffs(float tau_us, float Fs, double *b, double *a1) {
+    if (!b || !a1 || !(tau_us > 0.0f) || !(Fs > 0.0f)) return fmrx::fail(FMRX_ERR_ARG, "fmrx_deemphasis_coeffs: bad argument");
+    const double k = 2.0 * static_cast<double>(Fs) * static_cast<double>(tau_us) * 1e-6;
+    *b = 1.0 / (1.0 + k);
+    *a1 = (1.0 - k) / (1.0 + k);
+    return FMRX_OK;
+}

@@ -103,8 +103,13 @@ struct CombineJob {  // L/R combine + quantise, src/fm_radio.cpp:277-299
     float *audio_f;              // [S][2*ld] or null
     long long ld;
     int n_total, n_streams, mult;
+    int mono_delay;              // quality profile: mono taken this many samples late (<= 16) ...
+    float *mono_tail;            // ... with the previous call's last samples here, [S][16]; null = no delay
 };
 int launch_combine(const CombineJob &j, fmrx_stream_t st);
+// de-emphasis + quantiser on [S][n_blocks][2n] float audio (in place when write_float), state [S][4] = x[-1], y[-1] of L then R
+int launch_deemphasis(float *audio_f, int16_t *audio, long long ld2, int n, int n_blocks, int n_streams, double b, double a1, int mult, float *state, int write_float,
+                      fmrx_stream_t st);
 
 // rrc [S][ld] with n_blocks*n; outputs as in fmrx_rds_decode; state [S][FMRX_RDS_STATE_WORDS]
 int launch_rds_decode(const float *rrc, long long ld, int n_streams, int n_blocks, int n, uint8_t *bits, int32_t *n_bits,

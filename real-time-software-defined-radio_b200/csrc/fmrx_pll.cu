@@ -139,16 +139,87 @@ __device__ __forceinline__ int16_t quantise(float v, float mult) {
     return (int16_t)(unsigned short)(w & 0xFFFF);
 }
 
-__global__ void combine_kernel(const float *mono, const float *stereo, int16_t *audio, float *audio_f, long long ld, int n_total, float mult) {
+// mono_delay > 0 (quality profile): the mono sum is taken `mono_delay` samples late, from the previous samples of this call or,
+// at the start of the call, from the carried tail of the previous one -- the L-R branch passes one more 151-tap filter (the 22-54 kHz
+// band-pass, 75 samples at 240 kHz = 15 at 48 kHz) than the L+R branch, which the reference does not compensate
+__global__ void combine_kernel(const float *mono, const float *stereo, int16_t *audio, float *audio_f, long long ld, int n_total, float mult, int mono_delay,
+                               const float *mono_tail) {
     const int s = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_total) return;
-    const float m = mono[(long long)s * ld + i];
+    const float m = mono_delay == 0 ? mono[(long long)s * ld + i] : (i >= mono_delay ? mono[(long long)s * ld + i - mono_delay] : mono_tail[s * 16 + i]);
     const float t = stereo ? stereo[(long long)s * ld + i] : 0.0f;
     const float l = __fdiv_rn(__fadd_rn(m, t), 2.0f), r = __fdiv_rn(__fsub_rn(m, t), 2.0f);
     const long long o = ((long long)s * ld + i) * 2;
     if (audio_f) *reinterpret_cast<float2 *>(audio_f + o) = make_float2(l, r);
     if (audio) *reinterpret_cast<short2 *>(audio + o) = make_short2(quantise(l, mult), quantise(r, mult));
+}
+
+// after the combiner has read the old tail: the last `mono_delay` mono samples of this call become the next call's tail
+__global__ void mono_tail_kernel(const float *mono, float *mono_tail, long long ld, int n_total, int mono_delay, int n_streams) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = g / 16, j = g % 16;
+    if (s >= n_streams || j >= mono_delay) return;
+    const int i = n_total - mono_delay + j;
+    mono_tail[s * 16 + j] = i >= 0 ? mono[(long long)s * ld + i] : mono_tail[s * 16 + j + n_total];  // a call shorter than the delay shifts the tail (never in the chain)
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// De-emphasis (quality profile; the reference sends the low-pass output straight to the quantiser, src/fm_radio.cpp:277-299):
+// 1 / (1 + s tau) through the bilinear transform, y[n] = b (x[n] + x[n-1]) - a1 y[n-1], on L and R, then the quantiser.
+// A first-order recursion is an affine map per sample, y -> c y + u, and affine maps compose: one CTA per station, one warp
+// per channel, a lane owns a run of consecutive samples, runs it once from y = 0 to get its map (c^len, end value), the 32 maps
+// are combined by a warp scan, and the run is redone from the right starting value.  The block is staged in shared memory so that
+// global loads and stores stay coalesced.  State per station: x[-1], y[-1] of L and of R.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) deemphasis_kernel(float *audio_f, int16_t *audio, long long ld2, int n, int n_blocks, float b, float c, float mult,
+                                                         float *state, int write_float) {
+    extern __shared__ float blk[];  // 2n floats: L,R interleaved
+    const int s = blockIdx.x, lane = threadIdx.x & 31, ch = threadIdx.x >> 5;
+    float xprev = state[s * 4 + 2 * ch], yprev = state[s * 4 + 2 * ch + 1];
+    const int len = (n + 31) / 32, lo = min(n, lane * len), hi = min(n, lo + len);
+    for (int bk = 0; bk < n_blocks; ++bk) {
+        float *g = audio_f + (long long)s * ld2 + (long long)bk * 2 * n;
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * n; i += 64) { const float v = g[i]; blk[i] = isnan(v) ? 0.0f : v; }  // the quantiser writes 0 for a NaN (mode 1, Q5)
+        __syncthreads();
+        const float x0 = lo > 0 ? blk[2 * (lo - 1) + ch] : xprev;
+        float y = 0.0f, a = 1.0f, xp = x0;
+        for (int i = lo; i < hi; ++i) {
+            const float x = blk[2 * i + ch];
+            y = fmaf(c, y, __fmul_rn(b, __fadd_rn(x, xp)));
+            a *= c;
+            xp = x;
+        }
+        // inclusive scan of the maps (A, B): applying lane j's map after the maps of the lanes below it
+        float A = a, B = y;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const float Ad = __shfl_up_sync(0xffffffffu, A, d), Bd = __shfl_up_sync(0xffffffffu, B, d);
+            if (lane >= d) { B = fmaf(A, Bd, B); A *= Ad; }
+        }
+        float Ain = __shfl_up_sync(0xffffffffu, A, 1), Bin = __shfl_up_sync(0xffffffffu, B, 1);
+        if (lane == 0) { Ain = 1.0f; Bin = 0.0f; }
+        y = fmaf(Ain, yprev, Bin);  // the value just before this lane's run
+        xp = x0;
+        const float x_last = blk[2 * (n - 1) + ch];
+        __syncwarp();
+        for (int i = lo; i < hi; ++i) {
+            const float x = blk[2 * i + ch];
+            y = fmaf(c, y, __fmul_rn(b, __fadd_rn(x, xp)));
+            xp = x;
+            blk[2 * i + ch] = y;
+        }
+        yprev = __shfl_sync(0xffffffffu, fmaf(A, yprev, B), 31);  // the whole block's map applied to the carried value = y[n-1]
+        xprev = x_last;
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * n; i += 64) {
+            const float v = blk[i];
+            if (write_float) g[i] = v;
+            if (audio) audio[(long long)s * ld2 + (long long)bk * 2 * n + i] = quantise(v, mult);
+        }
+    }
+    if (lane == 0) { state[s * 4 + 2 * ch] = xprev; state[s * 4 + 2 * ch + 1] = yprev; }
 }
 
 __global__ void multiply_kernel(const float *a, const float *b, float *y, long long ld, int n_total) {
@@ -192,7 +263,23 @@ int launch_multiply(const float *a, const float *b, float *y, long long ld, int 
 
 int launch_combine(const CombineJob &j, fmrx_stream_t st) {
     dim3 grid((j.n_total + 255) / 256, j.n_streams);
-    combine_kernel<<<grid, 256, 0, st>>>(j.mono, j.stereo, j.audio, j.audio_f, j.ld, j.n_total, (float)j.mult);
+    const int dly = j.mono_tail ? j.mono_delay : 0;
+    combine_kernel<<<grid, 256, 0, st>>>(j.mono, j.stereo, j.audio, j.audio_f, j.ld, j.n_total, (float)j.mult, dly, j.mono_tail);
+    launch_counter() += 1;
+    if (dly > 0) {
+        mono_tail_kernel<<<(j.n_streams * 16 + 255) / 256, 256, 0, st>>>(j.mono, j.mono_tail, j.ld, j.n_total, dly, j.n_streams);
+        launch_counter() += 1;
+    }
+    return (int)cudaGetLastError();
+}
+
+int launch_deemphasis(float *audio_f, int16_t *audio, long long ld2, int n, int n_blocks, int n_streams, double b, double a1, int mult, float *state, int write_float,
+                      fmrx_stream_t st) {
+    const size_t smem = (size_t)2 * n * sizeof(float);
+    if (smem > 48 * 1024) {
+        if (cudaError_t e = cudaFuncSetAttribute(deemphasis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) return (int)e;
+    }
+    deemphasis_kernel<<<n_streams, 64, smem, st>>>(audio_f, audio, ld2, n, n_blocks, (float)b, (float)(-a1), (float)mult, state, write_float);
     launch_counter() += 1;
     return (int)cudaGetLastError();
 }

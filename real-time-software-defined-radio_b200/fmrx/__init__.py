@@ -30,6 +30,7 @@ RDS_STATE_WORDS = 160
 PROFILE_BINARY, PROFILE_INTENT = 0, 1
 PATH_AUDIO, PATH_RDS, PATH_RDS_STAGES = 1, 2, 4
 NUMERICS_REFERENCE, NUMERICS_FMA, NUMERICS_STRICT = 0, 1, 2
+QUALITY_DEEMPH_75, QUALITY_DEEMPH_50, QUALITY_UNITY_BPF, QUALITY_AUTO_RDS_PHASE = 1, 2, 4, 8
 TAPS = dict(demod=0, mono=1, pilot=2, nco=3, stereo_bpf=4, stereo=5, rds_bpf=6, rds_sq=7, rds_nco=8, rds_lpf=9, rds_res=10, rds_rrc=11)
 
 STAGES = ("frontend", "mono", "pilot_bpf", "stereo_bpf", "rds_bpf", "rds_sq_bpf", "pll", "stereo_lpf", "combine", "rds_mix_lpf",
@@ -66,7 +67,7 @@ evp = C.POINTER(RdsEvent)
 
 
 class Config(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in ("mode", "profile", "n_streams", "max_blocks", "device", "paths", "numerics", "reserved")]
+    _fields_ = [(n, C.c_int32) for n in ("mode", "profile", "n_streams", "max_blocks", "device", "paths", "numerics", "quality")]
 
 
 class Outputs(C.Structure):
@@ -81,6 +82,13 @@ SIGNATURES = {
     "fmrx_design_lpf": (C.c_int, [C.c_float, C.c_float, C.c_ushort, fp]),
     "fmrx_design_bpf": (C.c_int, [C.c_float, C.c_float, C.c_float, C.c_int, fp]),
     "fmrx_design_rrc": (C.c_int, [C.c_float, C.c_int, fp]),
+    "fmrx_fir_response": (C.c_int, [fp, C.c_int, C.c_float, C.c_float, dp, dp]),
+    "fmrx_design_bpf_unity": (C.c_int, [C.c_float, C.c_float, C.c_float, C.c_int, fp]),
+    "fmrx_rds_auto_phase": (C.c_int, [fp, C.c_int, C.c_float, C.c_float, fp]),
+    "fmrx_deemphasis_coeffs": (C.c_int, [C.c_float, C.c_float, dp, dp]),
+    "fmrx_deemphasis": (C.c_int, [fp, i16p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, fp]),
+    "fmrx_batch_rds_phase": (C.c_float, [C.c_void_p]),
+    "fmrx_batch_set_rds_phase": (C.c_int, [C.c_void_p, C.c_float]),
     "fmrx_unpack_iq": (C.c_int, [u8p, C.c_size_t, fp]),
     "fmrx_fir_decim": (C.c_int, [fp, fp, C.c_int, C.c_int, C.c_int, fp, C.c_int, fp, C.c_int, C.c_int, C.c_int]),
     "fmrx_fir_decim_iq": (C.c_int, [fp, fp, fp, fp, C.c_int, C.c_int, C.c_int, fp, C.c_int, fp, fp, C.c_int, C.c_int]),
@@ -202,6 +210,44 @@ def design_rrc(Fs, ntaps):
     h = np.zeros(ntaps, F)
     check(lib().fmrx_design_rrc(Fs, ntaps, _p(h)))
     return h
+
+
+def fir_response(h, Fs, f):
+    """(|H(f)|, arg H(f)) of the real FIR `h` at sampling rate Fs"""
+    h = f32(h)
+    m, ph = C.c_double(0), C.c_double(0)
+    check(lib().fmrx_fir_response(_p(h), h.size, Fs, f, C.byref(m), C.byref(ph)))
+    return m.value, ph.value
+
+
+def design_bpf_unity(Fb, Fe, Fs, ntaps):
+    h = np.zeros(ntaps, F)
+    check(lib().fmrx_design_bpf_unity(Fb, Fe, Fs, ntaps, _p(h)))
+    return h
+
+
+def rds_auto_phase(h_sq, Fs=240000.0, f2=114000.0):
+    h = f32(h_sq)
+    v = C.c_float(0)
+    check(lib().fmrx_rds_auto_phase(_p(h), h.size, Fs, f2, C.byref(v)))
+    return v.value
+
+
+def deemphasis_coeffs(tau_us, Fs):
+    b, a1 = C.c_double(0), C.c_double(0)
+    check(lib().fmrx_deemphasis_coeffs(tau_us, Fs, C.byref(b), C.byref(a1)))
+    return b.value, a1.value
+
+
+def deemphasis(audio_f, tau_us, Fs, state, mult=1, want_int16=False):
+    """audio_f: [2n] | [B][2n] | [S][B][2n] interleaved L,R; state: float32 [S][4] (x[-1], y[-1] of L then R), updated in place.
+    Returns the filtered float audio (and the quantised int16 when asked)."""
+    a3 = _as3(audio_f).copy()
+    S, B, n2 = a3.shape
+    q = np.zeros((S, B, n2), np.int16) if want_int16 else None
+    check(lib().fmrx_deemphasis(_p(a3), _p(q, i16p) if want_int16 else None, S, B, n2 // 2, tau_us, Fs, mult, _p(state)))
+    out = a3.reshape(np.shape(audio_f))
+    return (out, q.reshape(np.shape(audio_f))) if want_int16 else out
 
 
 def unpack_iq(raw):
@@ -424,8 +470,8 @@ class RdsApp:
 class Batch:
     """n_streams independent stations processed in lock step, max_blocks blocks per call."""
 
-    def __init__(self, n_streams=1, mode=0, profile=PROFILE_BINARY, max_blocks=1, device=0, paths=0, numerics=NUMERICS_REFERENCE):
-        self.cfg = Config(mode, profile, n_streams, max_blocks, device, paths, numerics, 0)
+    def __init__(self, n_streams=1, mode=0, profile=PROFILE_BINARY, max_blocks=1, device=0, paths=0, numerics=NUMERICS_REFERENCE, quality=0):
+        self.cfg = Config(mode, profile, n_streams, max_blocks, device, paths, numerics, quality)
         self.h = C.c_void_p()
         check(lib().fmrx_batch_create(C.byref(self.cfg), C.byref(self.h)))
         self.S, self.mode, self.max_blocks = n_streams, mode, max_blocks
@@ -499,6 +545,14 @@ class Batch:
         out = np.zeros(self.S, np.int32)
         check(lib().fmrx_batch_rds_offsets(self.h, _p(out, i32p)))
         return out
+
+    @property
+    def rds_phase(self):
+        return lib().fmrx_batch_rds_phase(self.h)
+
+    @rds_phase.setter
+    def rds_phase(self, v):
+        check(lib().fmrx_batch_set_rds_phase(self.h, float(v)))
 
     def rds_text(self, res, stream=0):
         """The stderr lines the reference's frame_thread prints for the blocks of `res` (src/fm_radio.cpp:516,619-701)."""

@@ -1,4 +1,4 @@
-"""Small device-resident run of the chain for ncu: python tools/prof_chain.py [stations] [steps]"""
+"""Small device-resident run of the chain for ncu: python tools/prof_chain.py [stations] [steps] [reference|strict|fma]"""
 import os
 import sys
 
@@ -13,7 +13,8 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 dev = torch.device("cuda", 0)
 iq = torch.randint(0, 256, (S, fmrx.BLOCK_BYTES), dtype=torch.uint8, device=dev)
 torch.cuda.synchronize()
-rx = fmrx.Batch(S, mode=0, profile=fmrx.PROFILE_INTENT, max_blocks=1)
+num = {"reference": fmrx.NUMERICS_REFERENCE, "strict": fmrx.NUMERICS_STRICT, "fma": fmrx.NUMERICS_FMA}[sys.argv[3] if len(sys.argv) > 3 else "reference"]
+rx = fmrx.Batch(S, mode=0, profile=fmrx.PROFILE_INTENT, max_blocks=1, numerics=num)
 for _ in range(steps):
     rx.process_device(iq.data_ptr(), 1, None)
 rx.sync()
