@@ -715,8 +715,10 @@ int fmrx_batch_create(const fmrx_config *cfg, fmrx_batch **out) {
         // per 64 ms block at 1 / 2 / 3 / 4 warps per scheduler (one warp = 32 loops), the filters of 4096 stations take
         // f ms on the whole device and scale with the SMs they are left with.  4096 stations, stereo + RDS: 32 / 116.
         int pll_sms = 0;
-        if (b->S >= 1024 && (b->audio_on || b->rds_on)) {
-            const int loops = b->S * ((b->audio_on ? 1 : 0) + (b->rds_on ? 1 : 0)), warps = (loops + 31) / 32;
+        // binary profile: the stereo loop runs in block 0 only (Q7) -- without the RDS loop there is nothing to give a partition to
+        const bool pilot_loop = b->audio_on && cfg->profile == FMRX_PROFILE_INTENT;
+        if (b->S >= 1024 && (pilot_loop || b->rds_on)) {
+            const int loops = b->S * ((pilot_loop ? 1 : 0) + (b->rds_on ? 1 : 0)), warps = (loops + 31) / 32;
             const double f_audio = cfg->mode == 0 ? 1.52 : cfg->mode == 1 ? 2.35 : 2.97;
             const double f_ms = (1.43 + (b->audio_on ? f_audio : 0.0) + (b->rds_on ? 1.09 : 0.0)) * b->S / 4096.0;
             int sms = 148;

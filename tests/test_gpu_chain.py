@@ -12,13 +12,13 @@ from util import LONG_STRIDE, assert_bits, rel_rms, sha
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
-# RDS stages downstream of the 114 kHz PLL.  The reference rounds the oscillator argument to fp32 (src/helper.cpp:156),
-# whose ulp is 4e-3 rad at the end of block 0 and 3e-2 rad after 8 blocks; its filter in front of the loop accumulates a
-# DOUBLE product (src/helper.cpp:139), which the GPU path replaces by one FFMA per tap.  The loop input therefore
-# differs in the last bit, the two loops round trigArg differently now and then, and the NCO phases differ by about one
-# ulp(trigArg)/2 on those samples.  That is the reference's own quantisation noise floor, not an error budget the
-# north_star states (its 1e-5 is for float AUDIO, which is bit-exact here); the RDS criterion is bit-exact bits and sync.
-TOL_AFTER_RDS_PLL = 2e-3
+# RDS stages downstream of the 114 kHz PLL under REFERENCE numerics.  The reference rounds the oscillator argument to fp32
+# (src/helper.cpp:156) and its filter in front of the loop accumulates a DOUBLE product (src/helper.cpp:139), which REFERENCE
+# numerics replaces by one FFMA per tap: the loop input differs in the last bit, the two loops round trigArg differently now
+# and then while the loop pulls in (blocks 1-4 of the fixture: 1e-5 .. 3e-5), and agree to 1e-7 once it has.  STRICT numerics
+# runs that filter with the reference's arithmetic and is held to bit-exactness (stage by stage) / 2e-6 (symbol-rate path).
+# (With the 54-60 kHz band-pass in FFMA too -- round 1 -- this figure was 2e-3.)
+TOL_AFTER_RDS_PLL = 1e-4
 NAMES = {0: "binary", 1: "intent"}
 
 
