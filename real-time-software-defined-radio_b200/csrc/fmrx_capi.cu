@@ -298,7 +298,7 @@ struct fmrx_batch {
     bool audio_on = false, rds_on = false, exact = true;
     bool strict = false;    // FMRX_NUMERICS_STRICT: the squared-input filter in front of the 114 kHz PLL with the reference's double products, staged RDS back end exact
     bool rds_fast = false;  // RDS back end at symbol rate (fmrx_rdsfast.cu) instead of stage by stage
-    float *d_W = nullptr, *d_G = nullptr, *d_h2p = nullptr;
+    float *d_W = nullptr, *d_E = nullptr;
     int32_t *d_off = nullptr;
     long long block_id = 0;  // blocks consumed per stream so far
     int last_blocks = 0;
@@ -531,10 +531,11 @@ int enqueue_chain(fmrx_batch *b, const uint8_t *iq, long long ld_iq, int s0, int
     if (b->rds_on) {
         if (b->rds_fast) {
             RdsFastJob q{};
-            q.p = IF2(b->rmixed); q.rrc = RD(b->rrrc); q.zi_lpf = b->zi_lpf + (long long)s0 * kHist; q.zi_anti = b->zi_anti + (long long)s0 * (kTaps * 19 - 1);
-            q.zi_rrc = b->zi_rrc + (long long)s0 * kHist; q.h1 = b->h_lpf3k; q.hr = b->h_rrc; q.h2p = b->d_h2p; q.W = b->d_W; q.G = b->d_G;
+            // the symbol-rate path keeps ONE state, the edge products of the last block, in the segment the staged path uses for the
+            // resampler history (2868 floats per station; the mixer and RRC history segments stay unused)
+            q.p = IF2(b->rmixed); q.rrc = RD(b->rrrc); q.edge = b->zi_anti + (long long)s0 * (kTaps * 19 - 1); q.edge_stride = kTaps * 19 - 1; q.W = b->d_W; q.E = b->d_E;
             q.off_state = b->dec_st + (long long)s0 * FMRX_RDS_STATE_WORDS + 1; q.off_state_stride = FMRX_RDS_STATE_WORDS; q.off_scratch = b->d_off + s0;
-            q.ld = ldif; q.ldr = ldr; q.n_streams = ns; q.n_blocks = nblk; q.first_block_is_zero = b->block_id == 0; q.nzi_anti = kTaps * 19 - 1;
+            q.ld = ldif; q.ldr = ldr; q.n_streams = ns; q.n_blocks = nblk; q.first_block_is_zero = b->block_id == 0;
             STAGE(FMRX_STAGE_RDS_SYMBOLS);
             LAUNCH(launch_rds_fast(q, st));
         } else {
@@ -693,8 +694,8 @@ int fmrx_batch_create(const fmrx_config *cfg, fmrx_batch **out) {
         CU(b->dalloc(b->rres, S * NB * NRDS)); CU(b->dalloc(b->rrrc, S * NB * NRDS));
         CU(b->dalloc(b->bits, S * NB * FMRX_MAX_BITS)); CU(b->dalloc(b->nbits, S * NB)); CU(b->dalloc(b->nev, S * NB)); CU(b->dalloc(b->ev, S * NB * FMRX_MAX_EVENTS));
         if (b->rds_fast) {
-            CU((cudaError_t)fmrx::rds_fast_tables(b->h_lpf3k, b->h_anti.data(), b->h_rrc, &b->d_W, &b->d_G, &b->d_h2p));
-            b->allocs.push_back(b->d_W); b->allocs.push_back(b->d_G); b->allocs.push_back(b->d_h2p);
+            CU((cudaError_t)fmrx::rds_fast_tables(b->h_lpf3k, b->h_anti.data(), b->h_rrc, &b->d_W, &b->d_E));
+            b->allocs.push_back(b->d_W); b->allocs.push_back(b->d_E);
             CU(b->dalloc(b->d_off, S));
             CU(cudaMemset(b->rrrc, 0, S * NB * NRDS * sizeof(float)));  // only the decoder's positions are ever written
         }
@@ -947,7 +948,7 @@ struct StateHeader {
     uint64_t state_bytes;
     long long block_id;
 };
-constexpr uint32_t kStateMagic = 0x58524D46u, kStateLayout = 3;  // bump kStateLayout when a segment or the decoder words (fmrx_rds.cu W_*) change
+constexpr uint32_t kStateMagic = 0x58524D46u, kStateLayout = 4;  // bump kStateLayout when a segment or the decoder words (fmrx_rds.cu W_*) change
 StateHeader make_header(const fmrx_batch *b) {
     StateHeader h{};
     h.magic = kStateMagic; h.version = kStateLayout; h.mode = b->cfg.mode; h.profile = b->cfg.profile; h.n_streams = b->S;
@@ -977,9 +978,9 @@ int fmrx_batch_set_state(fmrx_batch *b, const void *blob, size_t bytes) {
     std::memcpy(&h, blob, sizeof(h));
     const StateHeader want = make_header(b);
     if (h.magic != kStateMagic || h.version != kStateLayout) return fail(FMRX_ERR_ARG, "not a state blob of this library version (magic %08x, layout %u; expected layout %u)", h.magic, h.version, kStateLayout);
-    if (h.mode != want.mode || h.profile != want.profile || h.n_streams != want.n_streams || h.paths != want.paths || h.state_bytes != want.state_bytes)  // rds_fast is informational: both back ends keep the same state
-        return fail(FMRX_ERR_ARG, "state blob is from a handle of another shape (mode %d profile %d streams %d paths %d, %llu bytes; this handle: %d %d %d %d, %llu)",
-                    h.mode, h.profile, h.n_streams, h.paths, (unsigned long long)h.state_bytes, want.mode, want.profile, want.n_streams, want.paths, (unsigned long long)want.state_bytes);
+    if (h.mode != want.mode || h.profile != want.profile || h.n_streams != want.n_streams || h.paths != want.paths || h.rds_fast != want.rds_fast || h.state_bytes != want.state_bytes)  // the two RDS back ends keep different states
+        return fail(FMRX_ERR_ARG, "state blob is from a handle of another shape (mode %d profile %d streams %d paths %d staged-RDS %d, %llu bytes; this handle: %d %d %d %d %d, %llu)",
+                    h.mode, h.profile, h.n_streams, h.paths, !h.rds_fast, (unsigned long long)h.state_bytes, want.mode, want.profile, want.n_streams, want.paths, !want.rds_fast, (unsigned long long)want.state_bytes);
     if (bytes < sizeof(h) + b->state_bytes) return fail(FMRX_ERR_ARG, "state blob truncated: %zu bytes, %zu needed", bytes, sizeof(h) + b->state_bytes);
     if (h.block_id < 0) return fail(FMRX_ERR_ARG, "state blob carries a negative block counter");
     CU(cudaSetDevice(b->cfg.device));

@@ -116,20 +116,19 @@ int launch_rds_decode(const float *rrc, long long ld, int n_streams, int n_block
                       fmrx_rds_event *events, int32_t *n_events, int32_t *state, fmrx_stream_t st);
 
 // RDS back end at symbol rate (fmrx_rdsfast.cu): mixer LPF, 19/80 resampler and RRC as one composite polyphase filter
-// evaluated only at the 152 samples per block the decoder reads; block-edge semantics restated exactly on the head
+// evaluated only at the 152 samples per block the decoder reads; the reference's block-edge semantics enter through a second
+// table over two windows of the previous block's products
 struct RdsFastJob {
     const float *p;                 // [S][ld] mixer product NCO x RDS band (no x2), n_blocks * 15360 per station
     float *rrc;                     // [S][ldr] RRC buffer: written at 24k + off (and 0..23 in the very first block)
-    float *zi_lpf, *zi_anti, *zi_rrc;  // carried state [S][150], [S][nzi_anti], [S][150]
-    const float *h1, *hr;           // HOST: 3 kHz LPF taps, RRC taps (151 each)
-    const float *h2p;               // DEVICE: anti-image taps, phase-major [19][152] (rds_fast_tables)
-    const float *W, *G;             // DEVICE: composite tables from rds_fast_tables
+    float *edge;                    // carried state [S][edge_stride]: the 1094 edge products of the last block processed
+    const float *W, *E;             // DEVICE: composite tables from rds_fast_tables
     const int32_t *off_state;       // DEVICE: sampling phase of station s at off_state[s * off_state_stride] (decoder state), valid when !first_block_is_zero
     int32_t *off_scratch;           // DEVICE [S]: receives the phase derived from block 0 when first_block_is_zero
     long long ld, ldr;
-    int off_state_stride, n_streams, n_blocks, first_block_is_zero, nzi_anti;
+    int off_state_stride, n_streams, n_blocks, first_block_is_zero, edge_stride;
 };
-int rds_fast_tables(const float *h1, const float *h2, const float *hr, float **dW, float **dG, float **dH2p);
+int rds_fast_tables(const float *h1, const float *h2, const float *hr, float **dW, float **dE);
 int launch_rds_fast(const RdsFastJob &j, fmrx_stream_t st);
 
 int measure_fp32_peak(int device, int kind, int reps, double *tera);

@@ -4,22 +4,29 @@
 // Behind the 114 kHz PLL the reference runs three full-rate filters per block -- mixer + 3 kHz LPF (15360 outputs x 151
 // taps, src/filter.cpp:373-401), the 19/80 polyphase resampler (3648 x 151, :301-339) and the RRC matched filter
 // (3648 x 151, :126-154) -- and then frame_thread looks at ONE RRC sample in 24 (152 per block, src/fm_radio.cpp:
-// 519-526).  All three are linear and time-invariant inside a block, so the sample the decoder reads,
-// rrc[24k + off], is a single 933-tap polyphase filter applied to the mixer product p = NCO x RDS band that the PLL kernel
-// already writes:  rrc[i] = sum_j W[i mod 19][j] * p[floor(80 i / 19) - j],  W = hr * (19 h2) * (2 h1) laid out per phase.
-// 142 of a block's 152 symbols are such interior samples: 0.13 M MACs per block instead of 3.4 M.
+// 519-526).  All three are linear, so the sample the decoder reads is one dot product with the mixer product p = NCO x RDS
+// band that the PLL kernel already writes:
 //
-// What is NOT time-invariant are the reference's block-edge semantics -- the mixer's half-weight history (Q8), the
-// resampler's history indexed by tap count (Q6), the RRC's one-late history (Q1) -- and they reach the first ten symbols
-// of a block.  Those (and, in the very first block, the 24 samples frame_thread picks its sampling phase from, Q11) are
-// computed by a head kernel that restates the three stages exactly as the staged kernels do, on the 1008 + 240 samples
-// they need.  The carried state keeps its meaning: the last 150 mixer products, the eight entries of the resampler's
-// state its history map can reach, and the last 150 resampler outputs (one late), the latter two evaluated directly from
-// p with the composite taps.
+//   interior samples   rrc[i] = sum_j W[i mod 19][j] * p[floor(80 i / 19) - j],  W = hr * (19 h2) * (2 h1) per phase, 933 taps.
 //
-//   rds_head_kernel    one CTA per (station, block): X window -> rlpf[0..1008) -> rres[0..240) -> rrc at the head symbols
-//   rds_symbol_kernel  one CTA per (station, block), one warp per filter phase: the 142 interior symbols; for the last
-//                      block of a call also the new carried state, from the same staged samples
+//   block edge         What is NOT time-invariant are the reference's block-edge semantics -- the mixer's half-weight history
+//                      (Q8), the resampler's history indexed by tap count (Q6), the RRC's one-late history (Q1).  They reach
+//                      rrc[0..239] (the first ten symbols of a block), and they are still LINEAR: every history value is
+//                      itself a fixed combination of the previous block's products (the mixer history IS the last 150 of
+//                      them; the eight resampler-state entries the history map can reach are mixer-filter outputs at
+//                      12635..12642; the RRC history is the resampler's outputs 3497..3646).  So
+//                          rrc[i] = sum_j W[i mod 19][j] * p_ze[q(i) - j]  +  sum_m E[i][m] * p_prev[window(m)],   i < 240,
+//                      with p_ze = this block's products preceded by zeros (the causal cascade of a zero-extended input) and
+//                      E a 240 x 1094 table over two windows of the previous block, p_prev[12485..12642] and
+//                      p_prev[14424..15359], built once on the host in double (make_tables).  Checked against the staged
+//                      kernels and the oracle by tests/test_gpu_chain.py::test_rds_symbol_rate_path_equals_staged.
+//
+// One kernel, one CTA per (station, block): the block's products staged in shared memory behind 960 zeros, the two windows of
+// the previous block (read from the previous block of the same call, or from the carried state at the start of a call) next
+// to them; a warp takes a filter phase, keeps its 960 taps in registers and walks the 8 symbols of that phase.  The first
+// version restated the three stages on the head of the block (1008 + 240 + 10 filter outputs per block, barrier-separated,
+// 8.6 M shared-memory bank conflicts per launch: 0.20 ms) and recomputed the three filter states at every block end
+// (150 x 301 + 8 x 151 MACs); this one does 152 x 933 + 10 x 1094 MACs per block and keeps 1094 products as its state.
 // The decoder kernel is unchanged: the symbols are written at their positions 24k + off of the (otherwise untouched) RRC
 // buffer.  FMRX_PATH_RDS_STAGES selects the staged kernels instead (every stage materialised, debug taps available).
 #include <cuda_runtime.h>
@@ -33,232 +40,124 @@ namespace {
 
 constexpr int NIF = FMRX_IF_PER_BLOCK, NRDS = FMRX_RDS_PER_BLOCK, SPS = 24, NSYM = NRDS / SPS;
 constexpr int U = 19, D = 80, TPP = kTaps;
-constexpr int HEAD_SYMS = 10;                 // symbols 0..9 (rrc index < 240) feel the block edge
-constexpr int NRH = HEAD_SYMS * SPS;          // 240 resampler outputs restated by the head kernel
-constexpr int NLH = 1008;                     // mixer-LPF outputs they need: floor(80*239/19) = 1006
-constexpr int WLEN = 960;                     // composite taps per phase, zero padded (support 933)
-constexpr int GLEN = 320;                     // mixer-LPF x resampler composite per phase (support 301), zero padded to 10 x 32
-constexpr int ZA_LO = 143, ZA_N = 8;          // entries of the resampler state its history map can reach: (2867 - c)/19, c <= 150
+constexpr int HEAD = 240;                     // rrc positions 0..239 (symbols 0..9) feel the block edge
+constexpr int WLEN = 960;                     // composite taps per phase, zero padded (support 933): 30 per lane
+constexpr int GLEN = 301;                     // mixer-LPF x resampler composite per phase
+constexpr int A0 = 12485, AN = 158;           // window A of the previous block: feeds the 8 reachable resampler-state entries
+constexpr int B0 = 14424, BN = NIF - B0;      // window B: feeds the RRC history (resampler outputs 3497..3646) and the mixer history
+constexpr int EN = AN + BN;                   // 1094 edge products
+constexpr int ELEN = 1120;                    // padded to 35 per lane
+constexpr int ZPAD = WLEN;                    // zeros staged ahead of the block
+static_assert(BN == 936 && EN == 1094 && ELEN % 32 == 0 && ELEN >= EN, "edge window geometry");
 
 __host__ __device__ constexpr int qof(int o) { return (D * o) / U; }
 __host__ __device__ constexpr int phof(int o) { return (D * o) % U; }
 
-struct Taps151 {
-    float h[kTaps + 1];
-};
-
 struct FastDev {
     const float *p;        // [S][ld] mixer product, n_blocks * NIF per station
     float *rrc;            // [S][ldr] sparse RRC buffer, n_blocks * NRDS per station
-    float *zi_lpf, *zi_anti, *zi_rrc;
-    const float *h2p;      // device: anti-image taps, phase-major [19][152]: h2p[ph][c] = h2[ph + 19c]
-    const float *W, *G;    // device: [19][WLEN], [19][GLEN]
+    float *edge;           // [S][edge_stride] carried state: the EN edge products of the last block processed
+    const float *W, *E;    // device: [19][WLEN], [HEAD][ELEN]
     const int32_t *off;    // sampling phase per station: off[s * off_stride]
-    int32_t *off_out;      // where the first block's phase is written (phase_only pass)
+    int32_t *off_out;      // where the first block's phase is written (phase-only pass)
     long long ld, ldr;
-    int off_stride, n_blocks, first_block_is_zero, nzi_anti;
+    int off_stride, n_blocks, first_block_is_zero, edge_stride;
 };
 
-// rres[o] for an interior o of block `pb` (every tap in-block): composite of mixer LPF and resampler, straight from p.
-// Warp-cooperative: the 301 taps are split over the lanes (coalesced loads of taps and samples), then reduced.
-__device__ __forceinline__ float rres_interior_warp(const float *pb, const float *G, int o, int lane) {
-    const float *g = G + phof(o) * GLEN + lane;
-    const float *x = pb + qof(o) - lane;
-    float acc = 0.0f;
-#pragma unroll
-    for (int it = 0; it < GLEN / 32; ++it) acc = fmaf(__ldg(g + 32 * it), __ldg(x - 32 * it), acc);  // G is zero beyond its 301 taps
-#pragma unroll
-    for (int sh = 16; sh > 0; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
-    return acc;
-}
-
-// phase_only: grid (1, S), computes the 24 first RRC samples of block 0 and the sampling phase frame_thread derives from
-// them (src/fm_radio.cpp:503-517); otherwise grid (n_blocks, S): head symbols (and those 24 samples again, for the decoder)
-template <bool PHASE_ONLY>
-__global__ void __launch_bounds__(256) rds_head_kernel(const FastDev a, const __grid_constant__ Taps151 h1, const __grid_constant__ Taps151 hr) {
-    __shared__ __align__(16) float xw[kHist + NLH + 10];  // X(j), j = -150 .. NLH-1: history as stored, in-block doubled (+ pad for the last quad)
-    __shared__ float rl[NLH];               // rlpf head
-    __shared__ float rh[kHist + NRH];       // R(j), j = -150 .. 239: one-late history then rres head
-    __shared__ float a8[ZA_N];
+// the very first block of a station: frame_thread picks its sampling phase from |rrc[0..23]| (src/fm_radio.cpp:503-517), so
+// those 24 samples come first: one CTA per station, a warp per position
+__global__ void __launch_bounds__(256) rds_phase_kernel(const FastDev a) {
     __shared__ float dense[SPS];
-    const int b = blockIdx.x, s = blockIdx.y, t = threadIdx.x;
-    const float *pb = a.p + (long long)s * a.ld + (long long)b * NIF;
-    // ---- X window (Q8: the history holds the product without its x2) and the reachable resampler / RRC history
-    for (int i = t; i < kHist + NLH + 10; i += 256) {
-        const int j = i - kHist;
-        xw[i] = j >= NLH ? 0.0f : j >= 0 ? __fmul_rn(pb[j], 2.0f) : (b > 0 ? pb[j] : a.zi_lpf[(long long)s * kHist + kHist + j]);
-    }
-    if (b == 0) {
-        if (t < ZA_N) a8[t] = a.zi_anti[(long long)s * a.nzi_anti + ZA_LO + t];
-    } else {  // rlpf of the previous block at 12492 + 143 + e: interior, straight from p; one warp per entry
-        const int e = t >> 5, lane_ = t & 31;
-        const float *x = pb - NIF + (NIF + 1 - a.nzi_anti - 1) + ZA_LO + e;
+    const int s = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float *pb = a.p + (long long)s * a.ld;
+    const float *ed = a.edge + (long long)s * a.edge_stride;
+    for (int i = warp; i < SPS; i += 8) {
+        const float *w = a.W + (i % U) * WLEN;
+        const int q = qof(i);
         float acc = 0.0f;
-        for (int k = lane_; k < kTaps; k += 32) acc = fmaf(__fmul_rn(x[-k], 2.0f), h1.h[k], acc);
+        for (int j = lane; j <= q; j += 32) acc = fmaf(__ldg(w + j), pb[q - j], acc);
+        const float *e = a.E + (long long)i * ELEN;
+        for (int m = lane; m < EN; m += 32) acc = fmaf(__ldg(e + m), ed[m], acc);
 #pragma unroll
         for (int sh = 16; sh > 0; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
-        if (lane_ == 0) a8[e] = acc;
-    }
-    // R(-j') = rres_prev[NRDS - 1 - j'] (Q1): entry i = 150 - j' holds rres_prev[NRDS - 151 + i]
-    if (b == 0) {
-        if (t < kHist) rh[t] = a.zi_rrc[(long long)s * kHist + t];
-    } else {
-        for (int i = t >> 5; i < kHist; i += 8) {
-            const float v = rres_interior_warp(pb - NIF, a.G, NRDS - kHist - 1 + i, t & 31);
-            if ((t & 31) == 0) rh[i] = v;
-        }
+        if (lane == 0) dense[i] = acc;
     }
     __syncthreads();
-    // ---- mixer LPF on the head (src/filter.cpp:381-396), taps ascending.  Eight consecutive outputs per thread, the
-    // loop over the thread's samples newest first (one 128-bit LDS per four, each applied to every output it feeds)
-    constexpr int NL = PHASE_ONLY ? (qof(SPS - 1) + 8) / 8 * 8 : NLH;
-    if (8 * t < NL) {
-        const float *wnd = xw + 8 * t;  // window offset c <-> X(8t - 150 + c); output r uses it with tap k = 150 + r - c
-        float acc[8];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) acc[r] = 0.0f;
-#pragma unroll
-        for (int q = (kHist + 7) / 4; q >= 0; --q) {
-            const float4 v = *reinterpret_cast<const float4 *>(wnd + 4 * q);
-            const float xv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int e = 3; e >= 0; --e) {
-                const int c = 4 * q + e;
-#pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    const int k = kHist + r - c;
-                    if (k >= 0 && k < kTaps) acc[r] = fmaf(xv[e], h1.h[k], acc[r]);
-                }
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < 8; ++r) rl[8 * t + r] = acc[r];
-    }
-    __syncthreads();
-    // ---- resampler on the head (src/filter.cpp:317-334): in-block taps read rlpf, the others the state at (Z-1-c)/U (Q6)
-    constexpr int NR = PHASE_ONLY ? SPS : NRH;
-    if (t < NR) {
-        const int q0 = qof(t);
-        const float4 *hp = reinterpret_cast<const float4 *>(a.h2p + phof(t) * 152);  // phase-major copy: hp[c] = h2[ph + 19c]
-        float acc = 0.0f;
-        if (q0 >= TPP - 1) {  // every tap in-block (all but the first 36 outputs): no case analysis in the loop
-            const float *r = rl + q0;
-#pragma unroll 2
-            for (int c4 = 0; c4 < 152 / 4; ++c4) {
-                const float4 h = __ldg(hp + c4);
-                acc = fmaf(r[-4 * c4], h.x, acc);
-                acc = fmaf(r[-4 * c4 - 1], h.y, acc);
-                acc = fmaf(r[-4 * c4 - 2], h.z, acc);
-                if (c4 < 37) acc = fmaf(r[-4 * c4 - 3], h.w, acc);  // tap 151 does not exist
-            }
-        } else {
-            const float *hs = reinterpret_cast<const float *>(hp);
-            for (int c = 0; c < TPP; ++c) {
-                const float v = c <= q0 ? rl[q0 - c] : a8[(a.nzi_anti - 1 - c) / U - ZA_LO];
-                acc = fmaf(v, __ldg(hs + c), acc);
-            }
-        }
-        rh[kHist + t] = __fmul_rn(acc, (float)U);
-    }
-    __syncthreads();
-    // ---- RRC at the positions the decoder reads
-    const bool want_dense = PHASE_ONLY || (a.first_block_is_zero && b == 0);
-    const int off = PHASE_ONLY ? 0 : a.off[(long long)s * a.off_stride];
-    const int n_out = (PHASE_ONLY ? 0 : HEAD_SYMS) + (want_dense ? SPS : 0);
-    if (t < n_out) {
-        const int i = t < (PHASE_ONLY ? 0 : HEAD_SYMS) ? SPS * t + off : t - (PHASE_ONLY ? 0 : HEAD_SYMS);
-        const float *r = rh + kHist + i;
-        float acc = 0.0f;
-#pragma unroll
-        for (int k = 0; k < kTaps; ++k) acc = fmaf(r[-k], hr.h[k], acc);
-        if (PHASE_ONLY) dense[i] = acc;
-        else a.rrc[(long long)s * a.ldr + (long long)b * NRDS + i] = acc;
-    }
-    if (PHASE_ONLY) {
-        __syncthreads();
-        if (t == 0) {  // frame_thread's pick: the first strict maximum of |rrc[0..23]|
-            float best = fabsf(dense[0]);
-            int o = 0;
-            for (int i = 1; i < SPS; ++i)
-                if (fabsf(dense[i]) > best) { best = fabsf(dense[i]); o = i; }
-            a.off_out[s] = o;
-        }
+    if (threadIdx.x == 0) {  // the first strict maximum of |rrc[0..23]|
+        float best = fabsf(dense[0]);
+        int o = 0;
+        for (int i = 1; i < SPS; ++i)
+            if (fabsf(dense[i]) > best) { best = fabsf(dense[i]); o = i; }
+        a.off_out[s] = o;
     }
 }
 
-// interior symbols: the block's p is staged once in shared memory (asynchronous 16-byte copies); warp w handles filter
-// phases w, w+8, w+16, a phase's taps staying in registers (30 per lane) for its 7-8 symbols; each symbol is 30 conflict-free
-// LDS + FFMA per lane and a warp reduction
-__global__ void __launch_bounds__(256) rds_symbol_kernel(const FastDev a, const __grid_constant__ Taps151 h1) {
-    extern __shared__ __align__(16) float ps[];  // NIF floats
+__global__ void __launch_bounds__(256) rds_symbol_kernel(const FastDev a) {
+    extern __shared__ __align__(16) float ps[];  // ZPAD zeros | NIF products of this block | ELEN edge products of the previous one
+    float *pz = ps + ZPAD, *pw = ps + ZPAD + NIF;
     const int b = blockIdx.x, s = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float *pb = a.p + (long long)s * a.ld + (long long)b * NIF;
     float *out = a.rrc + (long long)s * a.ldr + (long long)b * NRDS;
+    float *ed = a.edge + (long long)s * a.edge_stride;
     const int off = a.off[(long long)s * a.off_stride];
-    if (((uintptr_t)pb & 15) == 0) {
-        const unsigned sbase = (unsigned)__cvta_generic_to_shared(ps);
+    const bool aligned = ((uintptr_t)pb & 15) == 0;
+    if (aligned) {
+        const unsigned sbase = (unsigned)__cvta_generic_to_shared(pz);
         for (int i = threadIdx.x; i < NIF / 4; i += 256) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + 16u * i), "l"(pb + 4 * i) : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
     } else {
-        for (int i = threadIdx.x; i < NIF; i += 256) ps[i] = pb[i];
+        for (int i = threadIdx.x; i < NIF; i += 256) pz[i] = pb[i];
     }
+    for (int i = threadIdx.x; i < ZPAD; i += 256) ps[i] = 0.0f;
+    for (int m = threadIdx.x; m < ELEN; m += 256) {
+        float v = 0.0f;
+        if (m < EN) {
+            const int src = m < AN ? A0 + m : B0 + (m - AN);
+            v = b > 0 ? pb[src - NIF] : ed[m];
+        }
+        pw[m] = v;
+    }
+    if (aligned) asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
+    const bool dense = a.first_block_is_zero && b == 0;  // the decoder re-derives the sampling phase from rrc[0..23] of block 0
     for (int phi = warp; phi < U; phi += 8) {
         float w[WLEN / 32];
 #pragma unroll
         for (int i = 0; i < WLEN / 32; ++i) w[i] = __ldg(a.W + phi * WLEN + 32 * i + lane);
-        // symbols k with (24k + off) mod 19 == phi: 5k = phi - off (mod 19), 5^-1 = 4
-        int k = (4 * (((phi - off) % U + U) % U)) % U;
-        while (k < HEAD_SYMS) k += U;
-        for (; k < NSYM; k += U) {
-            const int i = SPS * k + off;
-            const float *x = ps + qof(i) - lane;
+        auto sample = [&](int i) {
+            const float *x = pz + qof(i) - lane;
             float acc = 0.0f;
 #pragma unroll
             for (int it = 0; it < WLEN / 32; ++it) acc = fmaf(w[it], x[-32 * it], acc);
+            if (i < HEAD) {  // warp-uniform
+                const float *e = a.E + (long long)i * ELEN + lane;
+#pragma unroll 5
+                for (int t = 0; t < ELEN / 32; ++t) acc = fmaf(__ldg(e + 32 * t), pw[32 * t + lane], acc);
+            }
 #pragma unroll
             for (int sh = 16; sh > 0; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
             if (lane == 0) out[i] = acc;
-        }
+        };
+        // symbols k with (24k + off) mod 19 == phi: 5k = phi - off (mod 19), 5^-1 = 4
+        for (int k = (4 * (((phi - off) % U + U) % U)) % U; k < NSYM; k += U) sample(SPS * k + off);
+        if (dense)
+            for (int i = phi; i < SPS; i += U)
+                if (i != off) sample(i);
     }
-    if (b != a.n_blocks - 1) return;
-    // ---- the last block of the call also leaves the carried state, from the same staged samples
-    if (threadIdx.x < kHist) a.zi_lpf[(long long)s * kHist + threadIdx.x] = ps[NIF - kHist + threadIdx.x];  // src/filter.cpp:398-400 at its call site (Q8)
-    {   // the eight reachable entries of the resampler state: rlpf[12492 + 143 + e], one warp each
-        const float *x = ps + (NIF + 1 - a.nzi_anti - 1) + ZA_LO + warp;
-        float acc = 0.0f;
-        for (int k = lane; k < kTaps; k += 32) acc = fmaf(__fmul_rn(x[-k], 2.0f), h1.h[k], acc);
-#pragma unroll
-        for (int sh = 16; sh > 0; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
-        if (lane == 0) a.zi_anti[(long long)s * a.nzi_anti + ZA_LO + warp] = acc;
-    }
-    // the last 150 resampler outputs, one late (Q1): rres[3497 + i] = sum_d G[ph][d] p[q - d]; a warp takes a phase, keeps its
-    // composite taps in registers and walks the 7-8 outputs of that phase (ph(o) = 4o mod 19, so o = 5 ph mod 19)
-    for (int ph = warp; ph < U; ph += 8) {
-        float g[GLEN / 32];
-#pragma unroll
-        for (int it = 0; it < GLEN / 32; ++it) g[it] = __ldg(a.G + ph * GLEN + 32 * it + lane);
-        constexpr int O0 = NRDS - kHist - 1;
-        int o = O0 + (((5 * ph) % U - O0 % U) % U + U) % U;
-        for (; o < O0 + kHist; o += U) {
-            const float *x = ps + qof(o) - lane;
-            float acc = 0.0f;
-#pragma unroll
-            for (int it = 0; it < GLEN / 32; ++it) acc = fmaf(g[it], x[-32 * it], acc);
-#pragma unroll
-            for (int sh = 16; sh > 0; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
-            if (lane == 0) a.zi_rrc[(long long)s * kHist + (o - O0)] = acc;
-        }
-    }
+    if (b != 0) return;
+    // the carried state for the next call: the edge products of the LAST block of this one.  Written by the CTA that read the old
+    // state (block 0's, after the barrier above), so no other CTA of this launch races with it.
+    const float *pl = a.p + (long long)s * a.ld + (long long)(a.n_blocks - 1) * NIF;
+    for (int m = threadIdx.x; m < EN; m += 256) ed[m] = pl[m < AN ? A0 + m : B0 + (m - AN)];
 }
 
-struct Composite {
-    std::vector<float> W, G;
+struct Tables {
+    std::vector<float> W, E;
 };
 
-// W[phi][j]: rrc[i] = sum_j W[i%19][j] p[q(i) - j];  G[ph][d]: rres[o] = sum_d G[ph(o)][d] p[q(o) - d]  (double, then fp32)
-Composite make_composite(const float *h1, const float *h2, const float *hr) {
+// W[phi][j]: rrc[i] = sum_j W[i%19][j] p[q(i) - j] away from the block edge.
+// E[i][m], i < 240: what the previous block's edge products add to rrc[i] through the three histories (see the header).
+Tables make_tables(const float *h1, const float *h2, const float *hr) {
     std::vector<double> G((size_t)U * GLEN, 0.0), W((size_t)U * WLEN, 0.0);
     for (int ph = 0; ph < U; ++ph)
         for (int c = 0; c < TPP; ++c)
@@ -268,58 +167,78 @@ Composite make_composite(const float *h1, const float *h2, const float *hr) {
         for (int aa = 0; aa < kTaps; ++aa) {
             const int o = i - aa, base = M - qof(o);
             const double *g = &G[(size_t)phof(o) * GLEN];
-            for (int d = 0; d <= 2 * (kTaps - 1); ++d) W[(size_t)phi * WLEN + base + d] += (double)hr[aa] * g[d];
+            for (int d = 0; d < GLEN; ++d) W[(size_t)phi * WLEN + base + d] += (double)hr[aa] * g[d];
         }
     }
-    Composite c;
-    c.W.assign(W.begin(), W.end());
-    c.G.assign(G.begin(), G.end());
-    return c;
-}
-
-Taps151 pack(const float *h) {
-    Taps151 t;
-    for (int k = 0; k < kTaps; ++k) t.h[k] = h[k];
-    t.h[kTaps] = 0.0f;
+    // R[j], j = -150 .. 239: coefficients over the edge products of the resampler output the RRC reads at position j
+    //   j < 0: the RRC's one-late history (Q1), R(j) = rres_prev[3647 + j], an interior output of the previous block: G over window B
+    //   j >= 0: rres[j] of this block, its history part only -- tap c reads the mixer filter at q(j) - c, whose taps k > q(j) - c reach
+    //           into the mixer history (the previous block's last products at weight 1 instead of 2, Q8), or, for c > q(j), the
+    //           resampler state entry (2867 - c) / 19 (Q6) = the previous block's mixer filter output at 12492 + that index
+    std::vector<double> R((size_t)(kHist + HEAD) * EN, 0.0);
+    auto row = [&](int j) { return &R[(size_t)(j + kHist) * EN]; };
+    for (int j = -kHist; j < 0; ++j) {
+        const int o = NRDS - 1 + j, q = qof(o);
+        const double *g = &G[(size_t)phof(o) * GLEN];
+        for (int d = 0; d < GLEN; ++d) row(j)[AN + (q - d - B0)] += g[d];
+    }
+    for (int j = 0; j < HEAD; ++j) {
+        const int q = qof(j), f = phof(j);
+        for (int c = 0; c < TPP; ++c) {
+            const double w = (double)U * (double)h2[f + U * c];
+            if (c <= q) {
+                const int n = q - c;
+                for (int k = n + 1; k < kTaps; ++k) row(j)[AN + (NIF + n - k - B0)] += w * (double)h1[k];
+            } else {
+                const int n = (NIF + 1 - (kTaps * U - 1) - 1) + (kTaps * U - 2 - c) / U;  // 12492 + (2867 - c) / 19
+                for (int k = 0; k < kTaps; ++k) row(j)[n - k - A0] += w * 2.0 * (double)h1[k];
+            }
+        }
+    }
+    std::vector<double> E((size_t)HEAD * ELEN, 0.0);
+    for (int i = 0; i < HEAD; ++i)
+        for (int aa = 0; aa < kTaps; ++aa) {
+            const double *r = row(i - aa);
+            double *e = &E[(size_t)i * ELEN];
+            for (int m = 0; m < EN; ++m) e[m] += (double)hr[aa] * r[m];
+        }
+    Tables t;
+    t.W.assign(W.begin(), W.end());
+    t.E.assign(E.begin(), E.end());
     return t;
 }
 
 }  // namespace
 
-int rds_fast_tables(const float *h1, const float *h2, const float *hr, float **dW, float **dG, float **dH2p) {
-    const Composite c = make_composite(h1, h2, hr);
-    std::vector<float> h2p((size_t)U * 152, 0.0f);
-    for (int ph = 0; ph < U; ++ph)
-        for (int cc = 0; cc < TPP; ++cc) h2p[(size_t)ph * 152 + cc] = h2[ph + U * cc];
-    if (cudaError_t e0 = cudaMalloc(dH2p, h2p.size() * sizeof(float))) return (int)e0;
-    if (cudaError_t e0 = cudaMemcpy(*dH2p, h2p.data(), h2p.size() * sizeof(float), cudaMemcpyHostToDevice)) return (int)e0;
-    cudaError_t e = cudaMalloc(dW, c.W.size() * sizeof(float));
+int rds_fast_tables(const float *h1, const float *h2, const float *hr, float **dW, float **dE) {
+    const Tables t = make_tables(h1, h2, hr);
+    cudaError_t e = cudaMalloc(dW, t.W.size() * sizeof(float));
     if (e) return (int)e;
-    e = cudaMalloc(dG, c.G.size() * sizeof(float));
+    e = cudaMalloc(dE, t.E.size() * sizeof(float));
     if (e) return (int)e;
-    e = cudaMemcpy(*dW, c.W.data(), c.W.size() * sizeof(float), cudaMemcpyHostToDevice);
+    e = cudaMemcpy(*dW, t.W.data(), t.W.size() * sizeof(float), cudaMemcpyHostToDevice);
     if (e) return (int)e;
-    return (int)cudaMemcpy(*dG, c.G.data(), c.G.size() * sizeof(float), cudaMemcpyHostToDevice);
+    return (int)cudaMemcpy(*dE, t.E.data(), t.E.size() * sizeof(float), cudaMemcpyHostToDevice);
 }
 
 int launch_rds_fast(const RdsFastJob &j, fmrx_stream_t st) {
+    if (j.edge_stride < EN) return (int)cudaErrorInvalidValue;
     FastDev d{};
-    d.p = j.p; d.rrc = j.rrc; d.zi_lpf = j.zi_lpf; d.zi_anti = j.zi_anti; d.zi_rrc = j.zi_rrc; d.h2p = j.h2p; d.W = j.W; d.G = j.G;
-    d.ld = j.ld; d.ldr = j.ldr; d.n_blocks = j.n_blocks; d.first_block_is_zero = j.first_block_is_zero; d.nzi_anti = j.nzi_anti;
-    const Taps151 h1 = pack(j.h1), hr = pack(j.hr);
+    d.p = j.p; d.rrc = j.rrc; d.edge = j.edge; d.W = j.W; d.E = j.E;
+    d.ld = j.ld; d.ldr = j.ldr; d.n_blocks = j.n_blocks; d.first_block_is_zero = j.first_block_is_zero; d.edge_stride = j.edge_stride;
     if (j.first_block_is_zero) {  // the sampling phase does not exist yet: derive it from block 0 first
         d.off_out = j.off_scratch;
-        rds_head_kernel<true><<<dim3(1, j.n_streams), 256, 0, st>>>(d, h1, hr);
+        rds_phase_kernel<<<j.n_streams, 256, 0, st>>>(d);
         d.off = j.off_scratch; d.off_stride = 1;
         launch_counter() += 1;
     } else {
         d.off = j.off_state; d.off_stride = j.off_state_stride;
     }
-    rds_head_kernel<false><<<dim3(j.n_blocks, j.n_streams), 256, 0, st>>>(d, h1, hr);
+    const int smem = (ZPAD + NIF + ELEN) * (int)sizeof(float);
     // per device (per context), so set on every launch: a process may hold handles on several GPUs (fmrx_config.device)
-    if (cudaError_t e0 = cudaFuncSetAttribute(rds_symbol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NIF * (int)sizeof(float))) return (int)e0;
-    rds_symbol_kernel<<<dim3(j.n_blocks, j.n_streams), 256, NIF * sizeof(float), st>>>(d, h1);
-    launch_counter() += 2;
+    if (cudaError_t e0 = cudaFuncSetAttribute(rds_symbol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) return (int)e0;
+    rds_symbol_kernel<<<dim3(j.n_blocks, j.n_streams), 256, smem, st>>>(d);
+    launch_counter() += 1;
     return (int)cudaGetLastError();
 }
 
