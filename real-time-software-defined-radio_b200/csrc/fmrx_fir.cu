@@ -107,8 +107,10 @@ struct FirDev {
     const float *x, *x2;
     float *y;
     const float *zi;  // points at the 150 live entries of this launch's state: zi_live[s*nzi + (nzi-150) ...]
+    float *zi_out;    // the whole state [S][nzi]: rewritten from the last block's input by the one CTA per stream that reads it
     long long ldx, ldy;
     int nzi, n, ny, n_blocks;
+    int zi_first;     // first state entry to rewrite (nzi - 150 when only the live entries matter, else 0)
 };
 
 template <int KIND>
@@ -137,6 +139,23 @@ __device__ __forceinline__ float source(const FirDev &a, const float *xs, const 
     float v = xs[q];
     float w = (KIND == SRC_MIX_LATE || KIND == SRC_MIX_HALF) ? x2s[q] : 0.0f;
     return form<KIND>(v, w, in_block);
+}
+
+// The state after the launch, zi[i] = formed(x[N - nzi - 1 + i]) of the LAST block (mixer kinds: N - nzi + i, the plain product):
+// written by the CTA that read the old state -- tile 0 of block 0 is the only one whose window reaches into it -- after the barrier
+// that ends its staging.  The input is never written by the launch, so no other CTA races with this (a separate 8 us state kernel
+// behind each of the seven filters of a step was 1 % of the step).
+template <int KIND>
+__device__ __forceinline__ void update_state(const FirDev &a, int s, int nthreads) {
+    const float *xs = a.x + (long long)s * a.ldx + (long long)(a.n_blocks - 1) * a.n;
+    const float *x2s = a.x2 ? a.x2 + (long long)s * a.ldx + (long long)(a.n_blocks - 1) * a.n : nullptr;
+    for (int i = a.zi_first + threadIdx.x; i < a.nzi; i += nthreads) {
+        const int p = a.n - a.nzi + i - ((KIND == SRC_MIX_HALF || KIND == SRC_PROD_HALF) ? 0 : 1);
+        if (p < 0) continue;  // block shorter than the state: the entry keeps its old value (never live for a 151-tap filter)
+        const float v = xs[p];
+        const float w = (KIND == SRC_MIX_LATE || KIND == SRC_MIX_HALF) ? x2s[p] : 0.0f;
+        a.zi_out[(long long)s * a.nzi + i] = KIND == SRC_PROD_HALF ? v : form<KIND>(v, w, false);  // the state keeps the plain product
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -203,6 +222,7 @@ __global__ void __launch_bounds__(NT) fir151_kernel(const FirDev a, const __grid
         }
     }
     __syncthreads();
+    if (blockIdx.x == 0 && b == 0 && a.zi_out) update_state<KIND>(a, s, NT);
 
     // row t's window starts at entry ROW*t = float PITCHF*t; c = p + OFF is the index inside the window of the sample p
     // positions after the row's first output's newest one, and output r uses it with tap k = D*r - p
@@ -302,6 +322,7 @@ __global__ void __launch_bounds__(SQ_NT) fir151_sq_exact_kernel(const FirDev a, 
     }
     for (int i = threadIdx.x; i <= kTaps; i += SQ_NT) hd[i] = tapsd.h[i];
     const bool tile_finite = __syncthreads_and(finite);
+    if (blockIdx.x == 0 && b == 0 && a.zi_out) update_state<SRC_SQUARE>(a, s, SQ_NT);
 
     const int t = threadIdx.x, o0 = n0 + SQ_RO * t;   // first output of this thread
     float out[SQ_RO];
@@ -368,20 +389,6 @@ __global__ void __launch_bounds__(SQ_NT) fir151_sq_exact_kernel(const FirDev a, 
         for (int r = 0; r < SQ_RO; ++r)
             if (o0 + r < a.ny) ys[r] = out[r];
     }
-}
-
-// state after the launch: zi[i] = formed(x[N - nzi - 1 + i]) of the LAST block (mixer: N - nzi + i, no x2)
-template <int KIND>
-__global__ void fir_state_kernel(const float *x, const float *x2, float *zi, long long ldx, int nzi, int n, int n_blocks, int i0) {
-    const int s = blockIdx.y;
-    const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nzi) return;
-    const int p = n - nzi + i - ((KIND == SRC_MIX_HALF || KIND == SRC_PROD_HALF) ? 0 : 1);
-    if (p < 0) return;  // block shorter than the state: entry keeps its old value (never live for a 151-tap filter)
-    const long long q = (long long)s * ldx + (long long)(n_blocks - 1) * n + p;
-    const float v = x[q];
-    const float w = (KIND == SRC_MIX_LATE || KIND == SRC_MIX_HALF) ? x2[q] : 0.0f;
-    zi[(long long)s * nzi + i] = KIND == SRC_PROD_HALF ? v : form<KIND>(v, w, false);  // the state keeps the plain product
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -847,19 +854,16 @@ int launch_fir_k(const FirJob &j, const FirDev &d, dim3 grid, fmrx_stream_t st) 
     else if (j.decim == 5 && (KIND == SRC_PLAIN || KIND == SRC_MIX_LATE)) e = launch_fir_dk<5, (KIND == SRC_PLAIN || KIND == SRC_MIX_LATE) ? KIND : SRC_PLAIN>(j, d, grid, st);
     else if (j.decim == 10 && KIND == SRC_PLAIN) e = launch_fir_dk<10, SRC_PLAIN>(j, d, grid, st);
     else return (int)cudaErrorInvalidValue;
-    if (e) return e;
-    const int i0 = j.live_state_only && j.nzi > kHist ? j.nzi - kHist : 0;
-    dim3 sg((j.nzi - i0 + 127) / 128, j.n_streams);
-    fir_state_kernel<KIND><<<sg, 128, 0, st>>>(j.x, j.x2, j.zi, j.ldx, j.nzi, j.n, j.n_blocks, i0);
-    launch_counter() += 2;
-    return (int)cudaGetLastError();
+    launch_counter() += 1;
+    return e;
 }
 
 }  // namespace
 
 int launch_fir(const FirJob &j, fmrx_stream_t st) {
     FirDev d;
-    d.x = j.x; d.x2 = j.x2; d.y = j.y; d.zi = j.zi + (j.nzi - kHist);
+    d.x = j.x; d.x2 = j.x2; d.y = j.y; d.zi = j.zi + (j.nzi - kHist); d.zi_out = j.zi;
+    d.zi_first = j.live_state_only && j.nzi > kHist ? j.nzi - kHist : 0;
     d.ldx = j.ldx; d.ldy = j.ldy; d.nzi = j.nzi; d.n = j.n; d.ny = j.n / j.decim; d.n_blocks = j.n_blocks;
     constexpr int TO = R * CT;
     dim3 grid((d.ny + TO - 1) / TO, j.n_blocks, j.n_streams);

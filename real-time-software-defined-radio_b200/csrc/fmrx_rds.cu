@@ -243,6 +243,9 @@ constexpr int SPS = 24;  // samples per chip at 57 kHz
 __constant__ uint16_t kH[26] = {0x200, 0x100, 0x080, 0x040, 0x020, 0x010, 0x008, 0x004, 0x002, 0x001, 0x2DC, 0x16E, 0x0B7,
                                 0x287, 0x39F, 0x313, 0x355, 0x376, 0x1BB, 0x201, 0x3DC, 0x1EE, 0x0F7, 0x2A7, 0x38F, 0x31B};
 __constant__ uint16_t kSyn[4] = {0x3D8, 0x3D4, 0x25C, 0x258};
+// the same matrix by columns: bit j of kHcol[b] = bit b of kH[j], so that bit b of the syndrome of a 26-bit window w (bit j = the
+// window's j-th bit) is the parity of w & kHcol[b] -- ten AND + POPC on registers instead of 26 loads from a byte array per position
+__constant__ uint32_t kHcol[10] = {0x3cdf200, 0x3e6f900, 0x1f37c80, 0x3344c40, 0x257d420, 0xe61810, 0x730c08, 0x1f47404, 0x337c802, 0x39be401};
 
 enum { W_BLOCK = 0, W_OFFSET, W_START, W_LONELY, W_FRONT, W_PREBIT, W_NBITS, W_PRINTPOS, W_LASTPOS1, W_BAD, W_CARRY = 10, W_BITS = 40 };
 
@@ -320,10 +323,18 @@ __global__ void rds_decode_kernel(const float *rrc, long long ld, int n_streams,
         fmrx_rds_event *ev = events ? events + ((long long)s * n_blocks + b) * FMRX_MAX_EVENTS : nullptr;
         int nev = 0;
         unsigned pos = 0;
+        // the (at most 27 + 77) bits packed into two words; the window at `pos` is bits pos .. pos + 25
+        unsigned long long lo = 0ull, hi = 0ull;
+        for (int g = 0; g < total; ++g) {
+            if (g < 64) lo |= (unsigned long long)(diff[g] & 1u) << g;
+            else hi |= (unsigned long long)(diff[g] & 1u) << (g - 64);
+        }
         for (;;) {  // :631-713
+            const unsigned long long sh = pos == 0 ? lo : pos < 64 ? ((lo >> pos) | (hi << (64 - pos))) : (hi >> (pos - 64));
+            const unsigned w = (unsigned)sh & 0x3FFFFFFu;
             unsigned syn = 0;
-            for (int j = 0; j < 26; ++j)
-                if (diff[pos + j]) syn ^= kH[j];
+#pragma unroll
+            for (int bb = 0; bb < 10; ++bb) syn |= (unsigned)(__popc(w & kHcol[bb]) & 1) << bb;
             for (int L = 0; L < 4; ++L) {
                 if (syn != kSyn[L]) continue;
                 const bool good = last_pos == -1 || printpos - (unsigned)last_pos == 26u;
