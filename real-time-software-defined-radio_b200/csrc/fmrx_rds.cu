@@ -251,116 +251,158 @@ enum { W_BLOCK = 0, W_OFFSET, W_START, W_LONELY, W_FRONT, W_PREBIT, W_NBITS, W_P
 
 __device__ __forceinline__ bool same_sign(float a, float b) { return (a > 0 && b > 0) || (a < 0 && b < 0); }
 
-__global__ void rds_decode_kernel(const float *rrc, long long ld, int n_streams, int n_blocks, int n, uint8_t *bits_out, int32_t *n_bits_out,
-                                  fmrx_rds_event *events, int32_t *n_events_out, int32_t *state) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_streams) return;
-    int32_t *st = state + (long long)s * FMRX_RDS_STATE_WORDS;
-    int block_id = st[W_BLOCK];
-    unsigned offset = (unsigned)st[W_OFFSET], start_pos = (unsigned)st[W_START];
+// One station per lane, 32 stations per (single-warp) CTA.  Every global access is made by the warp TOGETHER -- a station's 160
+// state words, its 152 symbols (stride 24 in the RRC buffer), its 24 first samples in block 0, its decoded bits -- and staged in
+// shared memory with an odd row stride, so the lanes then walk their own rows without bank conflicts.  (First version: each lane
+// loaded its own state and symbols, ~300 dependent global loads of one sector each per block: 0.10 ms at 1.7 % warps active.)
+constexpr int DEC_ROW = FMRX_RDS_STATE_WORDS + 1;  // 161: odd stride
+constexpr int DEC_BITS_ROW = 21;                   // 80 bytes of bits + one pad word
+
+__device__ __forceinline__ unsigned window_bit(unsigned long long lo, unsigned long long hi, int g) {
+    return (unsigned)(((g < 64) ? (lo >> g) : (hi >> (g - 64))) & 1ull);
+}
+
+__global__ void __launch_bounds__(32) rds_decode_kernel(const float *rrc, long long ld, int n_streams, int n_blocks, int n, uint8_t *bits_out, int32_t *n_bits_out,
+                                                        fmrx_rds_event *events, int32_t *n_events_out, int32_t *state) {
+    __shared__ int32_t sst[32 * DEC_ROW];
+    __shared__ float ssym[32 * DEC_ROW];
+    __shared__ float sdense[32 * (SPS + 1)];
+    __shared__ uint32_t sbits[32 * DEC_BITS_ROW];
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x, s0 = blockIdx.x * 32, s = s0 + lane;
+    const int live = min(32, n_streams - s0);
+    const bool mine = lane < live;
+    for (int t = 0; t < live; ++t)
+        for (int w = lane; w < FMRX_RDS_STATE_WORDS; w += 32) sst[t * DEC_ROW + w] = state[(long long)(s0 + t) * FMRX_RDS_STATE_WORDS + w];
+    __syncwarp();
+    int32_t *st = sst + lane * DEC_ROW;            // bits[i] = st[W_BITS + i]: `bit_stream`, persistent (Q12)
+    uint8_t *mybits = reinterpret_cast<uint8_t *>(sbits + lane * DEC_BITS_ROW);
+    int block_id = mine ? st[W_BLOCK] : 1;
+    unsigned offset = mine ? (unsigned)st[W_OFFSET] : 0u, start_pos = mine ? (unsigned)st[W_START] : 0u;
     float lonely = __int_as_float(st[W_LONELY]);
     int front_bit = st[W_FRONT], prebit = st[W_PREBIT], nbits = st[W_NBITS];
     unsigned printpos = (unsigned)st[W_PRINTPOS];
     int last_pos = st[W_LASTPOS1] - 1, bad = st[W_BAD];
-    uint8_t bits[FMRX_MAX_BITS + 1], diff[27 + FMRX_MAX_BITS + 1];
-    for (int i = 0; i < FMRX_MAX_BITS; ++i) bits[i] = (uint8_t)st[W_BITS + i];
     const int nsym = n / SPS;
 
     for (int b = 0; b < n_blocks; ++b, ++block_id) {
-        const float *r = rrc + (long long)s * ld + (long long)b * n;
-        if (block_id == 0) {  // :503-517
-            float best = fabsf(r[0]);
-            for (unsigned i = 1; i < SPS; ++i)
-                if (fabsf(r[i]) > best) { best = fabsf(r[i]); offset = i; }
-        }
-        const float *sym = r + offset;  // sym[k] = r[24k + offset]
-        if (block_id == 0) {  // :542-558 (loop index starts at 0, Q10)
-            int c0 = 0, c1 = 0;
-            for (int j = 0; j < nsym / 4; ++j) {
-                const float a0 = sym[SPS * 2 * j], a1 = sym[SPS * (2 * j + 1)], a2 = sym[SPS * (2 * j + 2)];
-                if (same_sign(a0, a1)) ++c0;
-                else if (same_sign(a1, a2)) ++c1;
+        const float *r0 = rrc + (long long)s0 * ld + (long long)b * n;  // station t of this CTA: r0 + t * ld
+        if (__any_sync(FULL, mine && block_id == 0)) {  // :503-517, the sampling phase from |rrc[0..23]| of a station's first block
+            for (int t = 0; t < live; ++t)
+                if (lane < SPS) sdense[t * (SPS + 1) + lane] = r0[(long long)t * ld + lane];
+            __syncwarp();
+            if (mine && block_id == 0) {
+                const float *d = sdense + lane * (SPS + 1);
+                float best = fabsf(d[0]);
+                for (unsigned i = 1; i < SPS; ++i)
+                    if (fabsf(d[i]) > best) { best = fabsf(d[i]); offset = i; }
             }
-            if (c0 > c1) start_pos = 1;
-            else if (c1 > c0) start_pos = 0;
         }
-        const int want = nsym / 2 - (int)start_pos;  // :560
-        for (int i = nbits; i < want; ++i) bits[i] = 0;
-        nbits = want;
-        if (start_pos == 1 && block_id != 0) {  // :565-572
-            const float s0 = sym[0];
-            if (lonely > s0) front_bit = 1;
-            else if (s0 > lonely) front_bit = 0;
+        for (int t = 0; t < live; ++t) {  // sym[k] = r[24k + offset] of every station of the CTA
+            const unsigned off_t = __shfl_sync(FULL, offset, t);
+            for (int k = lane; k < nsym; k += 32) ssym[t * DEC_ROW + k] = r0[(long long)t * ld + SPS * k + off_t];
         }
-        for (int k = 0; k < nbits; ++k) {  // :574-585
-            const unsigned a = 2u * k + start_pos;
-            if (a + 1 > (unsigned)nsym - 1) break;
-            const float u = sym[SPS * a], v = sym[SPS * (a + 1)];
-            if (u > v) bits[k] = 1;
-            else if (u < v) bits[k] = 0;
-        }
-        if (start_pos == 1) {  // :587-592
-            for (int i = nbits; i > 0; --i) bits[i] = bits[i - 1];
-            bits[0] = (uint8_t)front_bit;
-            ++nbits;
-            lonely = sym[SPS * (nsym - 1)];
-        }
-        int off = 0;  // :596-616
-        if (block_id == 0) { prebit = bits[0]; off = 1; }
-        const int ncarry = block_id != 0 ? 27 : 0;
-        for (int g = 0; g < ncarry; ++g) diff[g] = (uint8_t)st[W_CARRY + g];
-        const int nd = nbits - off;
-        uint8_t *bo = bits_out ? bits_out + ((long long)s * n_blocks + b) * FMRX_MAX_BITS : nullptr;
-        for (int t = 0; t < nd; ++t) {
-            const int v = prebit ^ bits[t + off];
-            diff[ncarry + t] = (uint8_t)v;
-            prebit = bits[t + off];
-            if (bo) bo[t] = (uint8_t)v;
-        }
-        prebit = bits[nbits - 1];
-        if (n_bits_out) n_bits_out[(long long)s * n_blocks + b] = nd;
-        const int total = ncarry + nd;
-        fmrx_rds_event *ev = events ? events + ((long long)s * n_blocks + b) * FMRX_MAX_EVENTS : nullptr;
-        int nev = 0;
-        unsigned pos = 0;
-        // the (at most 27 + 77) bits packed into two words; the window at `pos` is bits pos .. pos + 25
-        unsigned long long lo = 0ull, hi = 0ull;
-        for (int g = 0; g < total; ++g) {
-            if (g < 64) lo |= (unsigned long long)(diff[g] & 1u) << g;
-            else hi |= (unsigned long long)(diff[g] & 1u) << (g - 64);
-        }
-        for (;;) {  // :631-713
-            const unsigned long long sh = pos == 0 ? lo : pos < 64 ? ((lo >> pos) | (hi << (64 - pos))) : (hi >> (pos - 64));
-            const unsigned w = (unsigned)sh & 0x3FFFFFFu;
-            unsigned syn = 0;
+        __syncwarp();
+        int nd = 0, nev = 0;
+        if (mine) {
+            const float *sym = ssym + lane * DEC_ROW;
+            if (block_id == 0) {  // :542-558 (loop index starts at 0, Q10)
+                int c0 = 0, c1 = 0;
+                for (int j = 0; j < nsym / 4; ++j) {
+                    const float a0 = sym[2 * j], a1 = sym[2 * j + 1], a2 = sym[2 * j + 2];
+                    if (same_sign(a0, a1)) ++c0;
+                    else if (same_sign(a1, a2)) ++c1;
+                }
+                if (c0 > c1) start_pos = 1;
+                else if (c1 > c0) start_pos = 0;
+            }
+            const int want = nsym / 2 - (int)start_pos;  // :560
+            for (int i = nbits; i < want; ++i) st[W_BITS + i] = 0;
+            nbits = want;
+            if (start_pos == 1 && block_id != 0) {  // :565-572
+                const float f0 = sym[0];
+                if (lonely > f0) front_bit = 1;
+                else if (f0 > lonely) front_bit = 0;
+            }
+            for (int k = 0; k < nbits; ++k) {  // :574-585
+                const unsigned a = 2u * k + start_pos;
+                if (a + 1 > (unsigned)nsym - 1) break;
+                const float u = sym[a], v = sym[a + 1];
+                if (u > v) st[W_BITS + k] = 1;
+                else if (u < v) st[W_BITS + k] = 0;
+            }
+            if (start_pos == 1) {  // :587-592
+                for (int i = nbits; i > 0; --i) st[W_BITS + i] = st[W_BITS + i - 1];
+                st[W_BITS] = front_bit;
+                ++nbits;
+                lonely = sym[nsym - 1];
+            }
+            int off = 0;  // :596-616
+            if (block_id == 0) { prebit = st[W_BITS]; off = 1; }
+            const int ncarry = block_id != 0 ? 27 : 0;
+            // the (at most 27 carried + 77 new) differentially decoded bits packed into two words; the window at `pos` is bits pos .. pos + 25
+            unsigned long long lo = 0ull, hi = 0ull;
+            for (int g = 0; g < ncarry; ++g) lo |= (unsigned long long)(st[W_CARRY + g] & 1) << g;
+            nd = nbits - off;
+            for (int t = 0; t < nd; ++t) {
+                const unsigned v = (unsigned)(prebit ^ st[W_BITS + t + off]) & 1u;
+                const int g = ncarry + t;
+                if (g < 64) lo |= (unsigned long long)v << g;
+                else hi |= (unsigned long long)v << (g - 64);
+                prebit = st[W_BITS + t + off];
+                mybits[t] = (uint8_t)v;
+            }
+            prebit = st[W_BITS + nbits - 1];
+            const int total = ncarry + nd;
+            fmrx_rds_event *ev = events ? events + ((long long)s * n_blocks + b) * FMRX_MAX_EVENTS : nullptr;
+            unsigned pos = 0;
+            for (;;) {  // :631-713
+                const unsigned long long sh = pos == 0 ? lo : pos < 64 ? ((lo >> pos) | (hi << (64 - pos))) : (hi >> (pos - 64));
+                const unsigned w = (unsigned)sh & 0x3FFFFFFu;
+                unsigned syn = 0;
 #pragma unroll
-            for (int bb = 0; bb < 10; ++bb) syn |= (unsigned)(__popc(w & kHcol[bb]) & 1) << bb;
-            for (int L = 0; L < 4; ++L) {
-                if (syn != kSyn[L]) continue;
-                const bool good = last_pos == -1 || printpos - (unsigned)last_pos == 26u;
-                if (ev && nev < FMRX_MAX_EVENTS) { ev[nev].block = block_id; ev[nev].kind = good ? FMRX_EV_GOOD : FMRX_EV_FALSE; ev[nev].letter = L; ev[nev].position = printpos; }
-                ++nev;
-                if (good) { last_pos = (int)printpos; bad = 0; }
-                else ++bad;
-                break;
+                for (int bb = 0; bb < 10; ++bb) syn |= (unsigned)(__popc(w & kHcol[bb]) & 1) << bb;
+                for (int L = 0; L < 4; ++L) {
+                    if (syn != kSyn[L]) continue;
+                    const bool good = last_pos == -1 || printpos - (unsigned)last_pos == 26u;
+                    if (ev && nev < FMRX_MAX_EVENTS) { ev[nev].block = block_id; ev[nev].kind = good ? FMRX_EV_GOOD : FMRX_EV_FALSE; ev[nev].letter = L; ev[nev].position = printpos; }
+                    ++nev;
+                    if (good) { last_pos = (int)printpos; bad = 0; }
+                    else ++bad;
+                    break;
+                }
+                if (bad > 10) {
+                    if (ev && nev < FMRX_MAX_EVENTS) { ev[nev].block = block_id; ev[nev].kind = FMRX_EV_RESYNC; ev[nev].letter = -1; ev[nev].position = printpos; }
+                    ++nev;
+                    bad = 0;
+                    last_pos = -1;
+                }
+                pos += 1;
+                if (pos + 26 > (unsigned)total - 1) break;
+                printpos += 1;
             }
-            if (bad > 10) {
-                if (ev && nev < FMRX_MAX_EVENTS) { ev[nev].block = block_id; ev[nev].kind = FMRX_EV_RESYNC; ev[nev].letter = -1; ev[nev].position = printpos; }
-                ++nev;
-                bad = 0;
-                last_pos = -1;
-            }
-            pos += 1;
-            if (pos + 26 > (unsigned)total - 1) break;
-            printpos += 1;
+            for (int g = 0; g < 27; ++g) st[W_CARRY + g] = (int)window_bit(lo, hi, (int)pos - 1 + g);  // :715-718
+            if (n_bits_out) n_bits_out[(long long)s * n_blocks + b] = nd;
+            if (n_events_out) n_events_out[(long long)s * n_blocks + b] = nev < FMRX_MAX_EVENTS ? nev : FMRX_MAX_EVENTS;
         }
-        for (int g = 0; g < 27; ++g) st[W_CARRY + g] = diff[pos - 1 + g];  // :715-718
-        if (n_events_out) n_events_out[(long long)s * n_blocks + b] = nev < FMRX_MAX_EVENTS ? nev : FMRX_MAX_EVENTS;
+        __syncwarp();
+        if (bits_out)
+            for (int t = 0; t < live; ++t) {
+                const int nd_t = __shfl_sync(FULL, nd, t);
+                const uint8_t *src = reinterpret_cast<const uint8_t *>(sbits + t * DEC_BITS_ROW);
+                uint8_t *bo = bits_out + ((long long)(s0 + t) * n_blocks + b) * FMRX_MAX_BITS;
+                for (int i = lane; i < nd_t; i += 32) bo[i] = src[i];
+            }
+        __syncwarp();
     }
-    st[W_BLOCK] = block_id; st[W_OFFSET] = (int)offset; st[W_START] = (int)start_pos; st[W_LONELY] = __float_as_int(lonely);
-    st[W_FRONT] = front_bit; st[W_PREBIT] = prebit; st[W_NBITS] = nbits; st[W_PRINTPOS] = (int)printpos;
-    st[W_LASTPOS1] = last_pos + 1; st[W_BAD] = bad;
-    for (int i = 0; i < FMRX_MAX_BITS; ++i) st[W_BITS + i] = bits[i];
+    if (mine) {
+        st[W_BLOCK] = block_id; st[W_OFFSET] = (int)offset; st[W_START] = (int)start_pos; st[W_LONELY] = __float_as_int(lonely);
+        st[W_FRONT] = front_bit; st[W_PREBIT] = prebit; st[W_NBITS] = nbits; st[W_PRINTPOS] = (int)printpos;
+        st[W_LASTPOS1] = last_pos + 1; st[W_BAD] = bad;
+    }
+    __syncwarp();
+    for (int t = 0; t < live; ++t)
+        for (int w = lane; w < FMRX_RDS_STATE_WORDS; w += 32) state[(long long)(s0 + t) * FMRX_RDS_STATE_WORDS + w] = sst[t * DEC_ROW + w];
 }
 
 }  // namespace
