@@ -58,7 +58,7 @@ PROFILE_TAG = "r4"  # profiles/<tag>_ncu_kernels.csv (tools/ncu_trim.py) and pro
 STAGE_KERNELS = {
     "frontend": ("frontend_stream4_kernel<1>", "frontend_edge_kernel<1>", "iq_state_kernel<1>"),
     "pll": ("pll_kernel",), "combine": ("combine_kernel",), "rds_decode": ("rds_decode_kernel",),
-    "rds_symbols": ("rds_head_kernel<1>", "rds_head_kernel<0>", "rds_symbol_kernel"),
+    "rds_symbols": ("rds_symbol_kernel",), "bpf_fused": ("fir151_multi_kernel",),
 }
 
 
@@ -80,10 +80,10 @@ def stage_traffic(prof, stage, fir_order):
         return sum(float(r["dram_read_bytes"]) + float(r["dram_write_bytes"]) for r in rows)
 
     if stage in STAGE_KERNELS:
-        rows = [r for k in STAGE_KERNELS[stage] for r in prof.get(k, [])]
+        rows = [r for k, v in prof.items() if any(k.startswith(p) for p in STAGE_KERNELS[stage]) for r in v]
         return tot(rows) if rows else None
-    if stage in fir_order:  # the FIR stages share one kernel template: identify the launch by its position among the fir151 launches
-        firs = sorted((r for k, v in prof.items() if k.startswith("fir151") for r in v), key=lambda r: int(r["launch"]))
+    if stage in fir_order:  # the FIR stages share one kernel template: identify the launch by its position among the fir151_kernel launches
+        firs = sorted((r for k, v in prof.items() if k.startswith("fir151_kernel") for r in v), key=lambda r: int(r["launch"]))
         i = fir_order.index(stage)
         return tot([firs[i]]) if i < len(firs) else None
     return None
@@ -717,6 +717,11 @@ def run_fmrx_arm(args, rank, world, local_rank):
     mixes, mix_path = sass_mix()
     fir_order = [n for n in ("mono", "pilot_bpf", "stereo_bpf", "rds_bpf", "rds_sq_bpf", "stereo_lpf") if stage.get(n, (0, 0))[1]]
     exact_now = {"rds_bpf": numerics != fmrx.NUMERICS_FMA, "rds_sq_bpf": False, "stereo_bpf": numerics != fmrx.NUMERICS_FMA}
+    # the band-pass filters of the discriminator output share one launch: all three (exact) under REFERENCE / STRICT, the stereo and RDS
+    # band (fma) under FMA numerics, where the pilot filter stays exact and on its own
+    n_fused = 2 if numerics == fmrx.NUMERICS_FMA else 3
+    STAGE_MACS["bpf_fused"] = (n_fused * NIF * NT, numerics != fmrx.NUMERICS_FMA)
+    STAGE_BYTES["bpf_fused"] = 4 * NIF + n_fused * 4 * NIF
     per = {}
     for name, (ms, cnt) in stage.items():
         if cnt == 0:
@@ -742,7 +747,7 @@ def run_fmrx_arm(args, rank, world, local_rank):
                         "note": "tflops / frac_fp32 count the MACs this formulation executes (composite filter at the decoder's sampling instants); "
                                 "the *_survey_algorithmic pair counts the MACs of the three full-rate stages it replaces"})
         gbs = STAGE_BYTES[name] * S * B * args.steps / (ms * 1e-3) / 1e9
-        tr = stage_traffic(prof, name, fir_order)
+        tr = stage_traffic(prof, name, fir_order) if args.numerics == "reference" else None  # the committed capture is of the default numerics
         ent.update({"hbm_gbs": round(gbs, 1), "frac_hbm": round(gbs / hbm_peak, 4), "algorithmic_bytes": STAGE_BYTES[name] * S * B,
                     "traffic": None if tr is None else round(tr * S * B / 4096.0), "traffic_over_algorithmic": None if tr is None else round(tr / (STAGE_BYTES[name] * 4096.0), 3)})
         per[name] = ent

@@ -228,7 +228,9 @@ int fmrx_batch_tap(fmrx_batch *, int which, float *dst);
 enum {
     FMRX_STAGE_FRONTEND = 0, FMRX_STAGE_MONO, FMRX_STAGE_PILOT_BPF, FMRX_STAGE_STEREO_BPF, FMRX_STAGE_RDS_BPF,
     FMRX_STAGE_RDS_SQ_BPF, FMRX_STAGE_PLL, FMRX_STAGE_STEREO_LPF, FMRX_STAGE_COMBINE, FMRX_STAGE_RDS_MIX_LPF,
-    FMRX_STAGE_RDS_RESAMPLE, FMRX_STAGE_RDS_RRC, FMRX_STAGE_RDS_DECODE, FMRX_STAGE_RDS_SYMBOLS, FMRX_STAGE_COUNT
+    FMRX_STAGE_RDS_RESAMPLE, FMRX_STAGE_RDS_RRC, FMRX_STAGE_RDS_DECODE, FMRX_STAGE_RDS_SYMBOLS,
+    FMRX_STAGE_BPF_FUSED, /* the band-pass filters of the discriminator output that share one launch (csrc/fmrx_fir.cu fir151_multi_kernel) */
+    FMRX_STAGE_COUNT
 };
 int fmrx_batch_profile(fmrx_batch *, int enable); /* 0 off, 1 serialised per-stage timing, 2 timeline: keep the pipeline */
 /* start / end of every bracket recorded since profiling was enabled, in ms after the first bracket's start; returns the

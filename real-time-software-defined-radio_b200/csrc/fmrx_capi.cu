@@ -458,21 +458,38 @@ int enqueue_chain(fmrx_batch *b, const uint8_t *iq, long long ld_iq, int s0, int
             LAUNCH(fir(IF(b->demod), nullptr, AU2(b->mono), b->zi_mono + (long long)s0 * b->nzi_a, b->nzi_a, b->h_mono.data(), ldif, lda, NIF, 5, SRC_PLAIN, ex, nblk));
         }
     }
-    if (b->audio_on) {
-        if (stereo_live) {
-            STAGE(FMRX_STAGE_PILOT_BPF);
-            LAUNCH(fir(IF(b->demod), nullptr, IF2(b->pilot), b->zi_pilot + (long long)s0 * b->nzi_b, b->nzi_b, b->h_pilot, ldif, ldif, NIF, 1, SRC_PLAIN, 1, st_blocks));
-        }
-        if (stereo_live) {
+    // the three band-pass filters of the discriminator output -- pilot 18.5-19.5 kHz (:232/:261), stereo band 22-54 kHz (:236/:265),
+    // RDS band 54-60 kHz (:395) -- in ONE launch when they run over the same blocks with the same rounding (intent profile: every
+    // block; their states are then updated together and hold the same input tail): the tile is staged once instead of three times.
+    // Under FMA numerics the pilot filter stays exact and on its own; the other two share a launch.
+    const bool same_blocks = b->audio_on && stereo_live && st_blocks == nblk && NIF % 1024 == 0;
+    const bool fuse3 = same_blocks && b->rds_on && b->exact && b->nzi_b == kHist;
+    const bool fuse2_audio = same_blocks && b->exact && !b->rds_on;                     // pilot + stereo band, both exact
+    const bool fuse2_fma = same_blocks && !b->exact && b->rds_on && b->nzi_b == kHist;  // stereo band + RDS band, both FMA
+    if (fuse3 || fuse2_audio || fuse2_fma) {
+        FirMultiJob m{};
+        m.x = IF(b->demod); m.ldx = ldif; m.ldy = ldif; m.n = NIF; m.n_blocks = nblk; m.n_streams = ns; m.nzi = b->nzi_b; m.exact = fuse2_fma ? 0 : 1;
+        int nf = 0;
+        auto add = [&](float *y, float *zi, const float *h) { m.y[nf] = y; m.zi[nf] = zi; m.h[nf] = h; ++nf; };
+        if (!fuse2_fma) add(IF2(b->pilot), b->zi_pilot + (long long)s0 * b->nzi_b, b->h_pilot);
+        add(IF2(b->sbpf), b->zi_sbpf + (long long)s0 * b->nzi_b, b->h_sbpf);
+        if (fuse3 || fuse2_fma) add(IF2(b->rbpf), b->zi_rbpf + (long long)s0 * kHist, b->h_rbpf);
+        m.nf = nf;
+        if (fuse2_fma) { STAGE(FMRX_STAGE_PILOT_BPF); LAUNCH(fir(IF(b->demod), nullptr, IF2(b->pilot), b->zi_pilot + (long long)s0 * b->nzi_b, b->nzi_b, b->h_pilot, ldif, ldif, NIF, 1, SRC_PLAIN, 1, st_blocks)); }
+        STAGE(FMRX_STAGE_BPF_FUSED);
+        LAUNCH(launch_fir_multi(m, st));
+    } else {
+        if (b->audio_on && stereo_live) {
+            { STAGE(FMRX_STAGE_PILOT_BPF); LAUNCH(fir(IF(b->demod), nullptr, IF2(b->pilot), b->zi_pilot + (long long)s0 * b->nzi_b, b->nzi_b, b->h_pilot, ldif, ldif, NIF, 1, SRC_PLAIN, 1, st_blocks)); }
             STAGE(FMRX_STAGE_STEREO_BPF);
             LAUNCH(fir(IF(b->demod), nullptr, IF2(b->sbpf), b->zi_sbpf + (long long)s0 * b->nzi_b, b->nzi_b, b->h_sbpf, ldif, ldif, NIF, 1, SRC_PLAIN, ex, st_blocks));
         }
+        // REFERENCE / STRICT: the 54-60 kHz band-pass with the reference's two roundings per tap (src/filter.cpp:126-154)
+        if (b->rds_on) { STAGE(FMRX_STAGE_RDS_BPF); LAUNCH(fir(IF(b->demod), nullptr, IF2(b->rbpf), b->zi_rbpf + (long long)s0 * kHist, kHist, b->h_rbpf, ldif, ldif, NIF, 1, SRC_PLAIN, ex, nblk)); }
     }
-    // ---- rds_thread, filters before the PLL (:395, :400's BPF)
+    // ---- rds_thread, pllCombine's filter (:400).  STRICT: with its double products (src/helper.cpp:139), so that the 114 kHz loop sees
+    // the reference's input bit for bit
     if (b->rds_on) {
-        // REFERENCE: the 54-60 kHz band-pass with the reference's two roundings per tap (src/filter.cpp:126-154); STRICT: also the
-        // squared-input filter with its double products (src/helper.cpp:139), so that the 114 kHz loop sees the reference's input bit for bit
-        { STAGE(FMRX_STAGE_RDS_BPF); LAUNCH(fir(IF(b->demod), nullptr, IF2(b->rbpf), b->zi_rbpf + (long long)s0 * kHist, kHist, b->h_rbpf, ldif, ldif, NIF, 1, SRC_PLAIN, ex, nblk)); }
         STAGE(FMRX_STAGE_RDS_SQ_BPF);
         LAUNCH(fir(IF2(b->rbpf), nullptr, IF2(b->rsq), b->zi_sq + (long long)s0 * kHist, kHist, b->h_sq, ldif, ldif, NIF, 1, SRC_SQUARE, b->strict ? 1 : 0, nblk));
     }

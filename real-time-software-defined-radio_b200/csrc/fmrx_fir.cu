@@ -266,6 +266,101 @@ __global__ void __launch_bounds__(NT) fir151_kernel(const FirDev a, const __grid
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Several D = 1 filters of ONE input in one launch (the pilot, 22-54 kHz and 54-60 kHz band-pass filters all read the
+// discriminator output): the tile is staged once and the tap loop runs once per filter, the taps of filter f coming from the
+// parameter block at a warp-uniform offset, so the loop body exists once in the instruction stream.  Same arithmetic and
+// summation order as fir151_kernel<1, SRC_PLAIN, EXACT, NT> -- bit-identical outputs -- minus two of the three stagings.
+// All filters carry the same history (the input's tail), so it is staged from filter 0's state; every filter's state is rewritten.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int MAXF = 3;
+struct TapsF {
+    float h[MAXF][kTaps + 1];
+};
+struct MultiDev {
+    const float *x;
+    float *y[MAXF];
+    float *zi[MAXF];   // [S][nzi] each; the last 150 entries are live
+    long long ldx, ldy;
+    int nzi, n, ny, n_blocks, nf, zi_first;
+};
+
+template <bool EXACT, int NT>
+__global__ void __launch_bounds__(NT) fir151_multi_kernel(const MultiDev a, const __grid_constant__ TapsF taps, const Exact2 ex) {
+    constexpr int RO = EXACT ? 4 : 8, D = 1;
+    using G = GeomP<D, NT, RO>;
+    __shared__ __align__(16) float sm[G::WORDS];
+    const int s = blockIdx.z, b = blockIdx.y, n0 = blockIdx.x * G::TO;
+    FirDev one{};
+    one.x = a.x; one.x2 = nullptr; one.zi = a.zi[0] + (a.nzi - kHist); one.ldx = a.ldx; one.nzi = a.nzi; one.n = a.n; one.ny = a.ny; one.n_blocks = a.n_blocks;
+    const float *xs = a.x + (long long)s * a.ldx;
+    const float *zs = one.zi + (long long)s * a.nzi;
+    const int P0 = D * n0 - OFF;
+    const float *xt = xs + (long long)b * a.n + P0;
+    const bool vec_ok = (a.n & 3) == 0 && ((uintptr_t)xt & 15) == 0;
+    {
+        constexpr int ITERS = (G::NPQ + NT - 1) / NT;
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) {
+            const int j = threadIdx.x + it * NT;
+            if (j >= G::NPQ) break;
+            const float4 lo = stage_quad<SRC_PLAIN>(one, xs, nullptr, zs, xt, xt, b, P0, 4 * j, vec_ok);
+            const float4 hi = stage_quad<SRC_PLAIN>(one, xs, nullptr, zs, xt, xt, b, P0, 4 * j + G::HALF, vec_ok);
+            float4 *dst = reinterpret_cast<float4 *>(sm + G::physf(4 * j));
+            dst[0] = make_float4(lo.x, hi.x, lo.y, hi.y);
+            dst[1] = make_float4(lo.z, hi.z, lo.w, hi.w);
+        }
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && b == 0) {
+        const float *xl = xs + (long long)(a.n_blocks - 1) * a.n;
+        for (int i = a.zi_first + threadIdx.x; i < a.nzi; i += NT) {
+            const int p = a.n - a.nzi + i - 1;
+            if (p < 0) continue;
+            const float v = xl[p];
+            for (int f = 0; f < a.nf; ++f) a.zi[f][(long long)s * a.nzi + i] = v;
+        }
+    }
+    const float *w = sm + G::PITCHF * threadIdx.x;
+#pragma unroll 1
+    for (int f = 0; f < a.nf; ++f) {
+        const float *h = taps.h[f];
+        float2 acc[RO];
+#pragma unroll
+        for (int r = 0; r < RO; ++r) acc[r] = make_float2(0.0f, 0.0f);
+#pragma unroll
+        for (int pq = G::PQHI; pq >= G::PQLO; --pq) {
+            const float4 v = *reinterpret_cast<const float4 *>(w + G::physf(2 * pq));
+#pragma unroll
+            for (int e = 1; e >= 0; --e) {
+                const float2 x2 = e ? make_float2(v.z, v.w) : make_float2(v.x, v.y);
+                const int p_ = 2 * pq + e - OFF;
+#pragma unroll
+                for (int r = 0; r < RO; ++r) {
+                    const int k = D * r - p_;
+                    if (k >= 0 && k < kTaps) acc[r] = mac2<EXACT>(acc[r], x2, h[k], ex);
+                }
+            }
+        }
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int o = n0 + RO * (threadIdx.x + hh * NT);
+            float *ys = a.y[f] + (long long)s * a.ldy + (long long)b * a.ny + o;
+            float out[RO];
+#pragma unroll
+            for (int r = 0; r < RO; ++r) out[r] = hh ? acc[r].y : acc[r].x;
+            if (o + RO <= a.ny && ((reinterpret_cast<uintptr_t>(ys) & 15) == 0)) {
+#pragma unroll
+                for (int r = 0; r < RO; r += 4) reinterpret_cast<float4 *>(ys)[r / 4] = make_float4(out[r], out[r + 1], out[r + 2], out[r + 3]);
+            } else {
+#pragma unroll
+                for (int r = 0; r < RO; ++r)
+                    if (o + r < a.ny) ys[r] = out[r];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // pllCombine's filter with the reference's own arithmetic (src/helper.cpp:139): an in-block tap is
 //     y[n] += pow(x[p], 2) * h[k]     -- the square and the product are DOUBLE, y[n] is a float,
 // i.e. acc <- (float)((double)acc + ((double)x * (double)x) * (double)h[k]); a history tap (:144) is the plain
@@ -859,6 +954,24 @@ int launch_fir_k(const FirJob &j, const FirDev &d, dim3 grid, fmrx_stream_t st) 
 }
 
 }  // namespace
+
+int launch_fir_multi(const FirMultiJob &j, fmrx_stream_t st) {
+    if (j.nf < 2 || j.nf > MAXF || j.n % (j.exact ? 1024 : 1024) != 0 || j.nzi < kHist) return (int)cudaErrorInvalidValue;
+    MultiDev d{};
+    TapsF t{};
+    d.x = j.x; d.ldx = j.ldx; d.ldy = j.ldy; d.nzi = j.nzi; d.n = j.n; d.ny = j.n; d.n_blocks = j.n_blocks; d.nf = j.nf;
+    d.zi_first = j.nzi > kHist ? j.nzi - kHist : 0;
+    for (int f = 0; f < j.nf; ++f) {
+        d.y[f] = j.y[f]; d.zi[f] = j.zi[f];
+        for (int k = 0; k < kTaps; ++k) t.h[f][k] = j.h[f][k];
+    }
+    const Exact2 ex{-0.0f, 1.0f};
+    dim3 grid(j.n / 1024, j.n_blocks, j.n_streams);
+    if (j.exact) fir151_multi_kernel<true, 128><<<grid, 128, 0, st>>>(d, t, ex);
+    else fir151_multi_kernel<false, 64><<<grid, 64, 0, st>>>(d, t, ex);
+    launch_counter() += 1;
+    return (int)cudaGetLastError();
+}
 
 int launch_fir(const FirJob &j, fmrx_stream_t st) {
     FirDev d;

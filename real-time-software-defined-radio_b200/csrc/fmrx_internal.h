@@ -42,6 +42,16 @@ struct FirJob {
 };
 int launch_fir(const FirJob &j, fmrx_stream_t st);
 
+struct FirMultiJob {  // 2 or 3 plain D = 1 filters of ONE input in one launch (same results as separate launch_fir calls, one staging)
+    const float *x;       // [S][ldx]
+    float *y[3];          // [S][ldy] each
+    float *zi[3];         // [S][nzi] each; all carry the input's tail (they are updated together)
+    const float *h[3];    // HOST taps
+    long long ldx, ldy;
+    int nzi, n, n_blocks, n_streams, nf, exact;  // n must be a multiple of 1024
+};
+int launch_fir_multi(const FirMultiJob &j, fmrx_stream_t st);
+
 struct FirIqJob {  // two channels sharing taps (convolveWithDecimIQ)
     const float *xi, *xq;
     float *yi, *yq, *zii, *ziq;

@@ -272,8 +272,21 @@ __global__ void __launch_bounds__(32) rds_decode_kernel(const float *rrc, long l
     const int lane = threadIdx.x, s0 = blockIdx.x * 32, s = s0 + lane;
     const int live = min(32, n_streams - s0);
     const bool mine = lane < live;
-    for (int t = 0; t < live; ++t)
-        for (int w = lane; w < FMRX_RDS_STATE_WORDS; w += 32) sst[t * DEC_ROW + w] = state[(long long)(s0 + t) * FMRX_RDS_STATE_WORDS + w];
+    // eight stations' loads are issued before the first of them is stored: a single warp per SM has nothing else to hide a DRAM
+    // round trip behind (one station at a time -- load, store, next -- took longer than the per-lane loads it replaced)
+    static_assert(FMRX_RDS_STATE_WORDS == 5 * 32, "five state words per lane per station");
+#pragma unroll 1
+    for (int t0 = 0; t0 < 32; t0 += 8) {
+        int32_t v[8][5];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int m = 0; m < 5; ++m) v[u][m] = t0 + u < live ? state[(long long)(s0 + t0 + u) * FMRX_RDS_STATE_WORDS + lane + 32 * m] : 0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int m = 0; m < 5; ++m) sst[(t0 + u) * DEC_ROW + lane + 32 * m] = v[u][m];
+    }
     __syncwarp();
     int32_t *st = sst + lane * DEC_ROW;            // bits[i] = st[W_BITS + i]: `bit_stream`, persistent (Q12)
     uint8_t *mybits = reinterpret_cast<uint8_t *>(sbits + lane * DEC_BITS_ROW);
@@ -298,9 +311,22 @@ __global__ void __launch_bounds__(32) rds_decode_kernel(const float *rrc, long l
                     if (fabsf(d[i]) > best) { best = fabsf(d[i]); offset = i; }
             }
         }
-        for (int t = 0; t < live; ++t) {  // sym[k] = r[24k + offset] of every station of the CTA
-            const unsigned off_t = __shfl_sync(FULL, offset, t);
-            for (int k = lane; k < nsym; k += 32) ssym[t * DEC_ROW + k] = r0[(long long)t * ld + SPS * k + off_t];
+#pragma unroll 1
+        for (int t0 = 0; t0 < 32; t0 += 8) {  // sym[k] = r[24k + offset] of every station of the CTA, eight stations in flight
+            float v[8][5];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const unsigned off_t = __shfl_sync(FULL, offset, t0 + u);
+#pragma unroll
+                for (int m = 0; m < 5; ++m) {
+                    const int k = lane + 32 * m;
+                    v[u][m] = (t0 + u < live && k < nsym) ? r0[(long long)(t0 + u) * ld + SPS * k + off_t] : 0.0f;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int m = 0; m < 5; ++m) ssym[(t0 + u) * DEC_ROW + lane + 32 * m] = v[u][m];
         }
         __syncwarp();
         int nd = 0, nev = 0;

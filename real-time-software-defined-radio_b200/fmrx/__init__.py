@@ -34,7 +34,7 @@ QUALITY_DEEMPH_75, QUALITY_DEEMPH_50, QUALITY_UNITY_BPF, QUALITY_AUTO_RDS_PHASE 
 TAPS = dict(demod=0, mono=1, pilot=2, nco=3, stereo_bpf=4, stereo=5, rds_bpf=6, rds_sq=7, rds_nco=8, rds_lpf=9, rds_res=10, rds_rrc=11)
 
 STAGES = ("frontend", "mono", "pilot_bpf", "stereo_bpf", "rds_bpf", "rds_sq_bpf", "pll", "stereo_lpf", "combine", "rds_mix_lpf",
-          "rds_resample", "rds_rrc", "rds_decode", "rds_symbols")
+          "rds_resample", "rds_rrc", "rds_decode", "rds_symbols", "bpf_fused")
 
 F = np.float32
 fp = C.POINTER(C.c_float)
