@@ -717,8 +717,8 @@ def run_fmrx_arm(args, rank, world, local_rank):
     mixes, mix_path = sass_mix()
     fir_order = [n for n in ("mono", "pilot_bpf", "stereo_bpf", "rds_bpf", "rds_sq_bpf", "stereo_lpf") if stage.get(n, (0, 0))[1]]
     exact_now = {"rds_bpf": numerics != fmrx.NUMERICS_FMA, "rds_sq_bpf": False, "stereo_bpf": numerics != fmrx.NUMERICS_FMA}
-    # the band-pass filters of the discriminator output share one launch: all three (exact) under REFERENCE / STRICT, the stereo and RDS
-    # band (fma) under FMA numerics, where the pilot filter stays exact and on its own
+    # band-pass filters of the discriminator output that share one launch: the stereo and RDS band under FMA numerics (the pilot filter
+    # stays exact and on its own); under REFERENCE / STRICT the three exact filters only with FMRX_BPF_FUSED=1 (measured slower)
     n_fused = 2 if numerics == fmrx.NUMERICS_FMA else 3
     STAGE_MACS["bpf_fused"] = (n_fused * NIF * NT, numerics != fmrx.NUMERICS_FMA)
     STAGE_BYTES["bpf_fused"] = 4 * NIF + n_fused * 4 * NIF

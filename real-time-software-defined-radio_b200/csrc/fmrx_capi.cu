@@ -459,12 +459,16 @@ int enqueue_chain(fmrx_batch *b, const uint8_t *iq, long long ld_iq, int s0, int
         }
     }
     // the three band-pass filters of the discriminator output -- pilot 18.5-19.5 kHz (:232/:261), stereo band 22-54 kHz (:236/:265),
-    // RDS band 54-60 kHz (:395) -- in ONE launch when they run over the same blocks with the same rounding (intent profile: every
-    // block; their states are then updated together and hold the same input tail): the tile is staged once instead of three times.
-    // Under FMA numerics the pilot filter stays exact and on its own; the other two share a launch.
+    // RDS band 54-60 kHz (:395) -- can share ONE launch when they run over the same blocks with the same rounding (intent profile:
+    // every block; their states are then updated together and hold the same input tail): the tile is staged once instead of three
+    // times (fir151_multi_kernel).  Measured (4096 stations): the fused-multiply-add pair 0.566 ms against 2 x 0.292 separately --
+    // adopted; the three exact filters 1.818 ms against 3 x 0.575 -- NOT adopted: with a run-time filter index the 151 taps reach the
+    // uniform registers as 158 scalar LDCU instead of the 50 wide ones of the single-filter kernel, +6 % instructions in a kernel at
+    // 90 % of its issue roof, more than the two stagings it saves.  FMRX_BPF_FUSED=1 forces the fused form for the exact filters too.
+    static const bool force_fused = [] { const char *v = getenv("FMRX_BPF_FUSED"); return v && atoi(v) == 1; }();
     const bool same_blocks = b->audio_on && stereo_live && st_blocks == nblk && NIF % 1024 == 0;
-    const bool fuse3 = same_blocks && b->rds_on && b->exact && b->nzi_b == kHist;
-    const bool fuse2_audio = same_blocks && b->exact && !b->rds_on;                     // pilot + stereo band, both exact
+    const bool fuse3 = force_fused && same_blocks && b->rds_on && b->exact && b->nzi_b == kHist;
+    const bool fuse2_audio = force_fused && same_blocks && b->exact && !b->rds_on;      // pilot + stereo band, both exact
     const bool fuse2_fma = same_blocks && !b->exact && b->rds_on && b->nzi_b == kHist;  // stereo band + RDS band, both FMA
     if (fuse3 || fuse2_audio || fuse2_fma) {
         FirMultiJob m{};
