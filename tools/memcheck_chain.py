@@ -1,7 +1,9 @@
-"""Small runs of every kernel family for compute-sanitizer (memcheck / racecheck / initcheck):
-    compute-sanitizer --tool memcheck python tools/memcheck_chain.py
-Ragged batch (33 stations), two calls of two blocks, every mode x numerics x back end, the quality profile, the ring, and the
-function-level operators with sizes that leave partial tiles."""
+"""Small runs of every kernel family in every configuration: ragged batch (33 stations), two calls of two blocks, every mode x
+numerics x RDS back end x quality profile with a checkpoint / resume in between, the ring, and the function-level operators with
+sizes that leave partial tiles.  Written as a driver for compute-sanitizer (`compute-sanitizer --tool memcheck python
+tools/memcheck_chain.py`); on pools where the sanitizer is not available it still runs as a configuration sweep
+(tests/test_gpu_configs.py) and checks what must hold across configurations: int16 audio is identical for REFERENCE and STRICT
+numerics and for both RDS back ends, and the RDS bits of both back ends agree."""
 import os
 import sys
 
@@ -14,19 +16,32 @@ import fmrx  # noqa: E402
 F = np.float32
 rng = np.random.default_rng(0)
 S, B = 33, 2
+sys.path.insert(0, ROOT)
+from fmrx import synth  # noqa: E402
+
 for mode in (0, 1, 2):
-    raw = rng.integers(0, 256, (S, 2 * B * fmrx.BLOCK_BYTES), dtype=np.uint8)
+    raw = np.stack([synth.synth_station(s % 4, 2 * B, mode) for s in range(S)])
+    seen = {}
     for numerics in (fmrx.NUMERICS_REFERENCE, fmrx.NUMERICS_STRICT, fmrx.NUMERICS_FMA):
         for extra in (0, fmrx.PATH_RDS_STAGES):
             for quality in (0, 13):
                 if mode == 1 and extra:
                     continue
                 with fmrx.Batch(S, mode=mode, profile=1, max_blocks=B, paths=fmrx.PATH_AUDIO | fmrx.PATH_RDS | extra, numerics=numerics, quality=quality) as rx:
-                    rx.process(raw[:, :B * fmrx.BLOCK_BYTES], want_float=True)
-                    rx.process(raw[:, B * fmrx.BLOCK_BYTES:])
+                    r1 = rx.process(raw[:, :B * fmrx.BLOCK_BYTES], want_float=True)
                     blob = rx.get_state()
                     rx.reset()
                     rx.set_state(blob)
+                    r2 = rx.process(raw[:, B * fmrx.BLOCK_BYTES:])
+                    audio = np.concatenate([r1["audio"], r2["audio"]], 1)
+                    assert np.isfinite(r1["audio_f"][~np.isnan(r1["audio_f"])]).all()
+                    if numerics != fmrx.NUMERICS_FMA:
+                        ref = seen.setdefault(("audio", quality), audio)
+                        assert np.array_equal(ref, audio), f"mode {mode} numerics {numerics} paths+{extra} quality {quality}: int16 audio differs between configurations"
+                    if mode != 1:
+                        bits = np.concatenate([r1["rds_bits"], r2["rds_bits"]], 1)
+                        refb = seen.setdefault(("bits", quality), bits)
+                        assert np.array_equal(refb, bits), f"mode {mode} numerics {numerics} paths+{extra} quality {quality}: RDS bits differ between configurations"
     print("mode", mode, "ok", flush=True)
 with fmrx.Batch(5, mode=0, profile=0, max_blocks=1) as rx, fmrx.Ring(rx, n_slots=2, n_blocks=1) as ring:
     for k in range(3):
