@@ -383,7 +383,9 @@ def run_reference_arm(args, rank):
         "impl": "reference", "metric": "IQ Msps (complex samples/s, whole job)", "value": round(value, 3), "unit": "Msps", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * t_total / args.steps, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "batch4096_mode0_stereo_rds", "reference_sample": sample, "realtime_streams": round(value / 2.4, 2)},
+        "config": {"workload": "batch4096_mode0_stereo_rds", "stations_per_gpu": args.stations, "blocks_per_step": args.blocks, "mode": 0, "paths": "mono+stereo+rds",
+                   "profile": "the shipped executable (= `binary` profile: its stereo branch is dead after block 0, SURVEY Q7)",
+                   "reference_sample": sample, "realtime_streams": round(value / 2.4, 2)},
         "cpu_baseline": {"value": round(value, 3), "unit": "Msps", "cores": procs, "kind": kind, "sample": sample},
         "e2e": {"value": round(value, 3), "unit": "Msps", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
