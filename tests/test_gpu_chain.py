@@ -526,3 +526,19 @@ def test_parity_sweep_256_stations(mode):
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "parity_sweep.py"), "256", "1", str(mode)], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "float audio samples that differ: 0   int16 samples that differ: 0   blocks with different RDS bits: 0" in r.stdout, r.stdout
+
+
+def test_handles_on_two_devices_in_one_process():
+    """fmrx_config.device: one process may hold handles on several GPUs (kernel attributes such as the symbol kernel's dynamic
+    shared-memory opt-in are per device).  Same bytes through a handle on device 0 and one on device 1: identical results."""
+    if fmrx.lib().fmrx_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    S, B = 5, 2
+    raw = np.stack([synth.synth_station(s, B, 0) for s in range(S)])
+    with fmrx.Batch(S, mode=0, profile=1, max_blocks=B, device=0) as a, fmrx.Batch(S, mode=0, profile=1, max_blocks=B, device=1) as b:
+        ra, rb = a.process(raw), b.process(raw)
+        rb2, ra2 = b.process(raw), a.process(raw)  # interleaved calls: each entry point selects its own device
+    for k in ("audio", "rds_bits", "rds_n_bits", "rds_n_events"):
+        assert np.array_equal(ra[k], rb[k]) and np.array_equal(ra2[k], rb2[k]), k
+    audio, _, bits, _, _ = Chain(0, 1).run(raw[0])
+    assert_bits(rb["audio"][0].ravel(), audio, "device 1 audio vs oracle")

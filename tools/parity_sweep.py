@@ -3,7 +3,7 @@ and through the oracle (one process per host core); counts the float audio sampl
 differ.  The PLL's double-precision kernels agree with glibc's after rounding to float in all but ~1e-9 of the calls
 (DESIGN 3.4), so at a few 1e8 calls a handful of last-bit differences in the float audio are expected, none in int16.
 
-    python tools/parity_sweep.py [stations] [blocks] [mode]
+    python tools/parity_sweep.py [stations] [blocks] [mode] [reference|strict|fma]
 """
 import os
 import sys
@@ -25,8 +25,8 @@ def oracle_station(args):
     s, blocks = args
     from oracle import Chain
 
-    audio, cap, bits, _, _ = Chain(MODE, 1).run(RAW[s], taps=("audio_f",))
-    return s, audio, np.stack(cap["audio_f"]), [b.copy() for b in bits]
+    audio, cap, bits, events, _ = Chain(MODE, 1).run(RAW[s], taps=("audio_f",))
+    return s, audio, np.stack(cap["audio_f"]), [b.copy() for b in bits], events
 
 
 def main():
@@ -34,6 +34,7 @@ def main():
     B = int(sys.argv[2]) if len(sys.argv) > 2 else 2
     global MODE
     MODE = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+    numerics_name = sys.argv[4] if len(sys.argv) > 4 else "reference"
     import fmrx
     from fmrx import synth
 
@@ -44,20 +45,24 @@ def main():
 
     t0 = time.time()
     raw = RAW = synth.synth_batch_torch(list(range(S)), B, mode, torch.device("cuda", 0), chunk=64).cpu().numpy()  # the bench's generator
-    with fmrx.Batch(S, mode=mode, profile=1, max_blocks=B) as rx:
+    numerics = {"reference": fmrx.NUMERICS_REFERENCE, "strict": fmrx.NUMERICS_STRICT, "fma": fmrx.NUMERICS_FMA}[numerics_name]
+    with fmrx.Batch(S, mode=mode, profile=1, max_blocks=B, numerics=numerics) as rx:
         na = rx.n_audio
         res = rx.process(raw, want_float=True)
     t1 = time.time()
-    nf = ni = nb = 0
+    nf = ni = nb = ne = 0
     bad_stations = []
     worst = 0.0
     with Pool(len(os.sched_getaffinity(0))) as pool:
-        for s, audio, audio_f, bits in pool.imap_unordered(oracle_station, [(s, B) for s in range(S)], chunksize=4):
+        for s, audio, audio_f, bits, events in pool.imap_unordered(oracle_station, [(s, B) for s in range(S)], chunksize=4):
             gf, gi = res["audio_f"][s], res["audio"][s].ravel()
             nan = np.isnan(gf) & np.isnan(audio_f)  # mode 1: every 24th sample is NaN on both sides (Q5)
             df = int(np.count_nonzero((gf.view(np.uint32) != audio_f.view(np.uint32)) & ~nan))
             di = int(np.count_nonzero(gi != audio))
             db = 0 if mode == 1 else sum(int(res["rds_n_bits"][s, b]) != bits[b].size or not np.array_equal(res["rds_bits"][s, b, :bits[b].size], bits[b]) for b in range(B))
+            if mode != 1:
+                got_ev = [tuple(int(v) for v in e) for b in range(B) for e in res["rds_events"][s, b, :res["rds_n_events"][s, b]]]
+                ne += got_ev != events
             if df or di or db:
                 bad_stations.append((s, df, di, db))
                 if df:
@@ -66,8 +71,9 @@ def main():
             nf += df; ni += di; nb += db
     t2 = time.time()
     n_float = S * B * 2 * na
-    print(f"mode {mode}: {S} stations x {B} blocks: {n_float} float audio samples, {S * B * 15360 * (1 if mode == 1 else 2) * 4} double-precision PLL calls")
+    print(f"mode {mode}, numerics {numerics_name}: {S} stations x {B} blocks: {n_float} float audio samples, {S * B * 15360 * (1 if mode == 1 else 2) * 4} double-precision PLL calls")
     print(f"  float audio samples that differ: {nf}   int16 samples that differ: {ni}   blocks with different RDS bits: {nb}")
+    print(f"  stations with different RDS sync events: {ne}")
     print(f"  stations with any difference: {len(bad_stations)} {bad_stations[:8]}   worst relative float difference: {worst:.3g}")
     print(f"  gpu + synth {t1 - t0:.1f} s, oracle {t2 - t1:.1f} s")
 
