@@ -408,8 +408,10 @@ def run_fmrx_arm(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None  # pinned buffers are first-touched on the GPU's own node
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        cpu_group = dist.new_group(backend="gloo")  # host-side barriers of the ingest arbitration (no GPU work, no stream sync)
 
     def barrier():
         if world > 1:
@@ -565,15 +567,57 @@ def run_fmrx_arm(args, rank, world, local_rank):
     c1.record()
     torch.cuda.synchronize()
     link_gbs = 5 * h2d / (c0.elapsed_time(c1) * 1e-3) / 1e9
+
     # the same with every rank copying at once, between barriers: the box's ceiling for this many GPUs ingesting together
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(5):
-        d_iq.copy_(h_iq[0], non_blocking=True)
-    torch.cuda.synchronize()
-    t_all = max_over_ranks(time.perf_counter() - t0)
-    barrier()
-    all_gbs = world * 5 * h2d / t_all / 1e9
+    def group_copy_seconds(active):
+        barrier()
+        t0 = time.perf_counter()
+        if active:
+            for _ in range(5):
+                d_iq.copy_(h_iq[0], non_blocking=True)
+            torch.cuda.synchronize()
+        t = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        return t
+
+    all_gbs = world * 5 * h2d / group_copy_seconds(True) / 1e9
+    # Ingest arbitration.  On this pool's 8-GPU boxes the host feeds four GPUs at once faster than eight (214 GB/s
+    # against 186), so when that is what the copies alone show, the two halves of the ranks (even / odd) take turns on the link:
+    # a host-side barrier, one half submits its step and waits for its host-to-device copy, barrier, the other half.  Kernels and
+    # result copies of either half run whenever they are ready; only the big input copies are serialised between the halves.
+    ingest = {"mode": "free-running", "free_running_msps": round(e2e_value, 1), "all_ranks_copying_gbs": round(all_gbs, 1)}
+    if world >= 4:
+        my_half = rank % 2
+        t_turns = group_copy_seconds(my_half == 0) + group_copy_seconds(my_half == 1)
+        turns_gbs = world * 5 * h2d / t_turns / 1e9
+        ingest["halves_taking_turns_gbs"] = round(turns_gbs, 1)
+        if turns_gbs > 1.05 * all_gbs:
+            def e2e_steps_arbitrated(n):
+                tickets = []
+                for k in range(n):
+                    for half in (0, 1):
+                        dist.barrier(group=cpu_group)
+                        if half == my_half:
+                            tickets.append(rx.submit(h_iq[k % 2].data_ptr(), B, hsets[k % 2]["out"]))
+                            rx.wait_ingest(tickets[-1])
+                            if k >= 1:
+                                rx.wait(tickets[k - 1])
+                rx.wait(tickets[-1])
+
+            rx.reset()
+            e2e_steps_arbitrated(max(2, args.warmup))
+            barrier()
+            t0 = time.perf_counter()
+            e2e_steps_arbitrated(args.steps)
+            torch.cuda.synchronize()
+            s_arb = max_over_ranks(time.perf_counter() - t0)
+            barrier()
+            arb_value = units / s_arb / 1e6
+            ingest["arbitrated_msps"] = round(arb_value, 1)
+            if arb_value > e2e_value:
+                ingest["mode"] = "arbitrated: the even and the odd ranks take turns on the host link (fmrx_batch_wait_ingest + a host barrier)"
+                e2e_value, s_e2e = arb_value, s_arb
+                all_gbs = max(all_gbs, turns_gbs)
     ach_gbs = world * S * B * BLOCK_BYTES * args.steps / s_e2e / 1e9
     link = {"h2d_copy_alone_gbs": round(link_gbs, 1), "all_ranks_copying_gbs": round(all_gbs, 1), "h2d_achieved_gbs": round(ach_gbs, 1),
             "frac_of_link": round(ach_gbs / all_gbs, 3), "e2e_ceiling_msps": round(all_gbs / 2.0 * 1e3, 1),
@@ -835,7 +879,7 @@ def run_fmrx_arm(args, rank, world, local_rank):
                    "l2": "input per step %.2f GB >> 126 MB L2, no flush needed" % (S * B * BLOCK_BYTES / 1e9), "input_reuse": "same synthesised block replayed each step, state carried",
                    "synth_seconds": round(t_synth, 2), "parity_spot_check": parity, "rank0_numa_node": numa, "gpu_map": gpu_map,
                    "e2e_timer": "host clock around K fmrx_batch_submit calls with fmrx_batch_wait on the previous step (two steps in flight), barrier + synchronize on both sides, max over ranks",
-                   "e2e_sync_call_msps": round(e2e_sync_value, 1), "e2e_link": link, "single_stream": single, "mode1": mode1, "mode2_44k1": mode2},
+                   "e2e_sync_call_msps": round(e2e_sync_value, 1), "e2e_link": link, "e2e_ingest": ingest, "single_stream": single, "mode1": mode1, "mode2_44k1": mode2},
         "e2e": {"value": round(e2e_value, 1), "unit": "Msps", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world},  # whole job, like `value`
         "gpu_launches": int(launches),
         "clocks": clocks,

@@ -191,6 +191,10 @@ int fmrx_batch_process(fmrx_batch *, const uint8_t *iq, int n_blocks, const fmrx
  * output buffers must be page-locked (fmrx_pinned_alloc) and stay untouched until fmrx_batch_wait(ticket) returns. */
 int fmrx_batch_submit(fmrx_batch *, const uint8_t *iq, int n_blocks, const fmrx_outputs *out, long long *ticket);
 int fmrx_batch_wait(fmrx_batch *, long long ticket);
+/* returns when the host -> device copy of that step has finished (its `iq` buffer may be refilled; the results are not there yet).
+ * For callers that arbitrate the host link between several handles / processes: on hosts that feed four GPUs at once faster than
+ * eight, letting two halves of the ranks take turns on the link moves more than letting all of them copy at once. */
+int fmrx_batch_wait_ingest(fmrx_batch *, long long ticket);
 /* device -> device, asynchronous on the handle's own (non-blocking) streams; fmrx_batch_sync() waits.  The handle's
  * streams do not synchronise with any stream of the caller: iq_device must be complete before the call (synchronise the
  * stream that produced it) and the outputs must not be read before fmrx_batch_sync() or a wait on fmrx_batch_cuda_stream(). */

@@ -121,6 +121,7 @@ SIGNATURES = {
     "fmrx_batch_partition": (C.c_int, [C.c_void_p, i32p, i32p]),
     "fmrx_batch_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Outputs), C.POINTER(C.c_longlong)]),
     "fmrx_batch_wait": (C.c_int, [C.c_void_p, C.c_longlong]),
+    "fmrx_batch_wait_ingest": (C.c_int, [C.c_void_p, C.c_longlong]),
     "fmrx_batch_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "fmrx_batch_stage_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "fmrx_batch_timeline": (C.c_int, [C.c_void_p, C.c_int, i32p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
@@ -608,6 +609,10 @@ class Batch:
 
     def wait(self, ticket):
         check(lib().fmrx_batch_wait(self.h, ticket))
+
+    def wait_ingest(self, ticket):
+        """returns when that step's host-to-device copy has finished (its input buffer may be refilled)"""
+        check(lib().fmrx_batch_wait_ingest(self.h, ticket))
 
     @property
     def launches(self):
