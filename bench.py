@@ -366,6 +366,59 @@ def pick_gpu(rank, world, local_rank):
     return chosen[local_rank % len(chosen)], info
 
 
+class ShmBarrier:
+    """Host barrier between the ranks of one node through a few words of POSIX shared memory: every rank owns one slot and writes its
+    epoch there, a barrier is over when every slot has reached the epoch.  One writer per slot, so no atomics; a spin of a few
+    microseconds -- the ingest arbitration crosses two of these per step and a gloo barrier (a TCP ring) cost it milliseconds."""
+
+    def __init__(self, rank, world):
+        from multiprocessing import shared_memory
+
+        self.rank, self.world, self.epoch = rank, world, 0
+        name = f"fmrx_bar_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}"
+        if rank == 0:
+            try:
+                shared_memory.SharedMemory(name=name).unlink()
+            except FileNotFoundError:
+                pass
+            self.shm = shared_memory.SharedMemory(name=name, create=True, size=8 * world)
+            self.shm.buf[:8 * world] = bytes(8 * world)
+        else:
+            t0 = time.time()
+            while True:
+                try:
+                    self.shm = shared_memory.SharedMemory(name=name)
+                    if self.shm.size >= 8 * world:
+                        break
+                except FileNotFoundError:
+                    pass
+                if time.time() - t0 > 120:
+                    raise RuntimeError("no shared-memory barrier from rank 0")
+                time.sleep(0.01)
+            try:  # the creator unlinks it; keep this process's resource tracker from doing (and announcing) the same at exit
+                from multiprocessing import resource_tracker
+
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
+        self.slots = np.ndarray((world,), dtype=np.int64, buffer=self.shm.buf)
+
+    def wait(self):
+        self.epoch += 1
+        self.slots[self.rank] = self.epoch
+        while int(self.slots.min()) < self.epoch:
+            pass
+
+    def close(self):
+        self.slots = None
+        self.shm.close()
+        if self.rank == 0:
+            try:
+                self.shm.unlink()
+            except FileNotFoundError:
+                pass
+
+
 def run_reference_arm(args, rank):
     if rank != 0:
         return
@@ -408,10 +461,8 @@ def run_fmrx_arm(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None  # pinned buffers are first-touched on the GPU's own node
-    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-        cpu_group = dist.new_group(backend="gloo")  # host-side barriers of the ingest arbitration (no GPU work, no stream sync)
 
     def barrier():
         if world > 1:
@@ -592,11 +643,14 @@ def run_fmrx_arm(args, rank, world, local_rank):
         turns_gbs = world * 5 * h2d / t_turns / 1e9
         ingest["halves_taking_turns_gbs"] = round(turns_gbs, 1)
         if turns_gbs > 1.05 * all_gbs:
+            dist.barrier()  # rank 0 creates the shared words before anybody attaches
+            host_bar = ShmBarrier(rank, world)
+
             def e2e_steps_arbitrated(n):
                 tickets = []
                 for k in range(n):
                     for half in (0, 1):
-                        dist.barrier(group=cpu_group)
+                        host_bar.wait()
                         if half == my_half:
                             tickets.append(rx.submit(h_iq[k % 2].data_ptr(), B, hsets[k % 2]["out"]))
                             rx.wait_ingest(tickets[-1])
@@ -612,10 +666,11 @@ def run_fmrx_arm(args, rank, world, local_rank):
             torch.cuda.synchronize()
             s_arb = max_over_ranks(time.perf_counter() - t0)
             barrier()
+            host_bar.close()
             arb_value = units / s_arb / 1e6
             ingest["arbitrated_msps"] = round(arb_value, 1)
             if arb_value > e2e_value:
-                ingest["mode"] = "arbitrated: the even and the odd ranks take turns on the host link (fmrx_batch_wait_ingest + a host barrier)"
+                ingest["mode"] = "arbitrated: the even and the odd ranks take turns on the host link (fmrx_batch_wait_ingest + a shared-memory host barrier)"
                 e2e_value, s_e2e = arb_value, s_arb
     ach_gbs = world * S * B * BLOCK_BYTES * args.steps / s_e2e / 1e9
     ceiling = max(all_gbs, ingest.get("halves_taking_turns_gbs", 0.0)) if ingest["mode"] != "free-running" else all_gbs
