@@ -463,6 +463,12 @@ def run_fmrx_arm(args, rank, world, local_rank):
     numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None  # pinned buffers are first-touched on the GPU's own node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()  # every rank has read the GPU map by now
+        if rank == 0:
+            try:
+                os.unlink(f"/dev/shm/fmrx_gpumap_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}.json")
+            except OSError:
+                pass
 
     def barrier():
         if world > 1:

@@ -88,3 +88,53 @@ def test_two_ranks_cover_the_batch_and_match_one_rank(tmp_path):
         audio, _, bits, _, _ = Chain(0, 1).run(synth.synth_station(s, 1, 0))
         assert np.array_equal(got[s][0], audio)
         assert np.array_equal(got[s][1], np.concatenate(bits) if len(bits) else np.zeros(0, np.uint8))
+
+
+def _bar_worker(rank, world, key, out):
+    import time
+
+    os.environ["MASTER_PORT"] = "45678"
+    sys.path.insert(0, ROOT)
+    import bench
+
+    bench.os.getppid = lambda: key          # the launcher's pid keys the segment: the same for every rank of one launch
+    if rank:
+        time.sleep(0.1 * rank)              # late attachers wait for rank 0's segment
+    bar = bench.ShmBarrier(rank, world)
+    order = []
+    for step in range(50):
+        if step % world == rank:
+            time.sleep(0.002)               # one straggler per step: nobody may pass the barrier before it arrives
+        bar.wait()
+        order.append(int(bar.slots.min()))
+    out.put((rank, order))
+    bar.wait()
+    bar.close()
+
+
+def test_shared_memory_barrier_between_ranks():
+    """bench.ShmBarrier (the host barrier of the ingest arbitration): after wait() number k every rank's slot has reached k."""
+    import multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    world = 3
+    ps = [ctx.Process(target=_bar_worker, args=(r, world, os.getpid(), q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(world))
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in range(world):
+        assert all(m >= k + 1 for k, m in enumerate(got[r])), f"rank {r} passed a barrier early"
+
+
+def test_gpu_map_is_identity_when_there_is_nothing_to_choose():
+    """bench.pick_gpu: one rank, or as many ranks as visible GPUs (none here): LOCAL_RANK, no probe, no file."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    for rank, world, local in ((0, 1, 0), (3, 8, 3)):
+        idx, info = bench.pick_gpu(rank, world, local)
+        assert idx == local and info["policy"] == "identity"
