@@ -926,9 +926,9 @@ int fmrx_batch_wait_ingest(fmrx_batch *b, long long ticket) {
     if (!b) return fail(FMRX_ERR_ARG, "null handle");
     const long long issued = b->submits.load();
     if (ticket < 0 || ticket >= issued) return fail(FMRX_ERR_ARG, "ticket %lld was never issued (next is %lld)", ticket, issued);
-    if (ticket < issued - 2) return FMRX_OK;  // its staging buffer has been handed to a later step since: that copy is long done
     CU(cudaSetDevice(b->cfg.device));
-    // the slot holds this ticket's copy event or, once reused, that of the submit two later on the same in-order stream
+    // the slot holds this ticket's copy event or, once reused, that of a later submit into the same staging buffer on the same
+    // in-order stream (then the wait is longer than necessary, never shorter)
     CU(cudaEventSynchronize(b->e_h2d[ticket & 1]));
     return FMRX_OK;
 }
