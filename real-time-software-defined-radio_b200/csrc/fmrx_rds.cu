@@ -8,8 +8,13 @@
 //                           zi[i] = x[N-Z-1+i] afterwards.  Only the retained phases are computed.
 //   src/fm_radio.cpp:444-729 frame_thread: one-shot sampling phase, Manchester alignment screening, biphase decode,
 //                           differential decode, sliding 26-bit syndrome against A/B/C/D with the false-positive
-//                           counter / resync, 27-bit carry.  Integer results are bit-exact by construction: the only
-//                           floating-point operations are comparisons of RRC samples.
+//                           counter / resync, 27-bit carry.  The decoder itself is integer logic on COMPARISONS of RRC samples:
+//                           given the reference's RRC samples its bits and events are the reference's.  Whether the samples
+//                           are the reference's is decided upstream: bit for bit under STRICT numerics with the staged back
+//                           end, to 2e-7 with the symbol-rate back end, to 1e-5 .. 1e-7 under REFERENCE numerics (FFMA in
+//                           pllCombine's filter) -- there a decision can differ only where two compared samples are closer than
+//                           that; measured under AWGN down to 2 dB CNR: 0 of 3036 bits differ in any setting
+//                           (tests/test_gpu_chain.py::test_rds_on_noisy_input_agreement).
 #include <cuda_runtime.h>
 
 #include <cstdint>
