@@ -178,10 +178,11 @@ def synth_station(s: int, n_blocks: int, mode: int = 0) -> np.ndarray:
     return synth_iq(n_blocks, mode=mode, **station_params(s))
 
 
-def synth_batch_torch(stations, n_blocks: int, mode: int, device, chunk: int = 64):
+def synth_batch_torch(stations, n_blocks: int, mode: int, device, chunk: int = 64, cnr_db=None, noise_seed: int = 0):
     """Same multiplex for many stations at once, synthesised on `device` with torch (float64).  Returns a uint8
     tensor [len(stations), n_blocks*307200].  Used by bench.py to fill HBM with thousands of distinct stations in
-    seconds; parity spot checks copy individual rows back and run the oracle on those exact bytes."""
+    seconds; parity spot checks copy individual rows back and run the oracle on those exact bytes.  `cnr_db`: white Gaussian
+    noise ahead of the quantiser as in synth_iq (torch's generator, seeded with noise_seed: not numpy's noise, the same statistics)."""
     import torch
 
     fs = rf_rate(mode)
@@ -214,6 +215,13 @@ def synth_batch_torch(stations, n_blocks: int, mode: int, device, chunk: int = 6
         m = m + 0.05 * bb * c3[None, :]
         phi = 2 * np.pi * 75e3 * torch.cumsum(m, dim=1) / fs
         row = out[lo:lo + len(ids)]
-        row[:, 0::2] = torch.clamp(torch.round(127.0 * torch.cos(phi) + 128.0), 0, 255).to(torch.uint8)
-        row[:, 1::2] = torch.clamp(torch.round(127.0 * torch.sin(phi) + 128.0), 0, 255).to(torch.uint8)
+        ci, cq = torch.cos(phi), torch.sin(phi)
+        if cnr_db is not None:
+            gen = torch.Generator(device=device)
+            gen.manual_seed(int(noise_seed) * 1000003 + lo)
+            sigma = float(np.sqrt(0.5 * 10.0 ** (-float(cnr_db) / 10.0)))
+            ci = ci + sigma * torch.randn(ci.shape, dtype=torch.float64, device=device, generator=gen)
+            cq = cq + sigma * torch.randn(cq.shape, dtype=torch.float64, device=device, generator=gen)
+        row[:, 0::2] = torch.clamp(torch.round(127.0 * ci + 128.0), 0, 255).to(torch.uint8)
+        row[:, 1::2] = torch.clamp(torch.round(127.0 * cq + 128.0), 0, 255).to(torch.uint8)
     return out
