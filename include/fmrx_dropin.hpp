@@ -90,7 +90,7 @@ inline void convolveWithDecimMode1RDS(std::vector<float> &y, const std::vector<f
                                       std::vector<float> &zi, const int &decim_num, const int &up_sample) {
     y.assign(x.size() * up_sample / decim_num, 0.0f);
     fmrx_dropin::check(fmrx_resample(y.data(), 0, x.data(), 1, 1, (int)x.size(), h.data(), (int)h.size(), zi.data(), (int)zi.size(),
-                                     decim_num, up_sample, 1, 0),
+                                     decim_num, up_sample, 1, 1),
                        "convolveWithDecimMode1RDS");
 }
 // ---- src/filter.cpp:373-401 at its call site src/fm_radio.cpp:404: x = the (n+1)-long NCO vector of pllCombine,

@@ -1,6 +1,7 @@
 """include/fmrx_dropin.hpp: the reference's own function names (src/filter.h, helper.h, rf_module.h) over the C-ABI.
 CPU: the header compiles and links against libfmrx.so.  GPU: a program written like the reference's thread bodies
-(tests/native/dropin_check.cpp) reproduces the oracle's demod / mono / pilot / NCO / stereo bit for bit."""
+(tests/native/dropin_check.cpp: rf_thread, mono_stero_thread and rds_thread) reproduces the oracle's demod / mono / pilot / NCO /
+stereo and the whole RDS branch (band, pllCombine's filter and NCO, mixer filter, 19/80 resampler, RRC) bit for bit."""
 import os
 import subprocess
 
@@ -35,11 +36,11 @@ def test_reference_style_program_matches_oracle(exe, tmp_path):
     raw.tofile(fin)
     subprocess.check_call([exe, fin, fout])
     got = np.fromfile(fout, np.float32).reshape(nblk, -1)
-    sizes = [15360, 3072, 15360, 15360, 3072]
+    sizes = [15360, 3072, 15360, 15360, 3072, 15360, 15360, 15360, 15360, 3648, 3648]
     chain = Chain(0, 1)  # intent profile: stereo computed in every block, outputs assigned
     for b in range(nblk):
         chain.block(raw[b * 307200:(b + 1) * 307200])
         off = 0
-        for name, n in zip(("demod", "mono", "pilot", "nco", "stereo"), sizes):
-            assert_bits(got[b, off:off + n], chain.tap(name), f"block {b} {name}")
+        for name, n in zip(("demod", "mono", "pilot", "nco", "stereo", "rds_bpf", "rds_sq", "rds_nco", "rds_lpf", "rds_res", "rds_rrc"), sizes):
+            assert_bits(got[b, off:off + n], chain.tap(name)[:n], f"block {b} {name}")
             off += n
