@@ -126,3 +126,19 @@ def test_binary_profile_stereo_dead_after_block0(golden):
     assert (a[1:, :, 0] == a[1:, :, 1]).all() and (a[0, :, 0] != a[0, :, 1]).any()
     a1 = golden["chain_mode1"]["binary_audio"].reshape(-1, 2949, 2)
     assert (a1[:, 12::24, :] == 0).all()  # Q5
+
+
+def test_oracle_chain_on_noisy_input_equals_the_reference():
+    """tests/golden/chain_mode0_noisy.npz (AWGN at 4 dB CNR: decisions without wide margins): audio = stdout of the unmodified
+    reference executable, frame_thread text = the reference's own functions in sequence (the executable's stderr is a race on such
+    input: the fixture records 4 different texts in 4 runs).  The oracle port reproduces both."""
+    import os
+
+    from fmrx import synth
+    from oracle import Chain
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "chain_mode0_noisy.npz"), allow_pickle=False)
+    raw = synth.synth_iq(int(g["nblk"]), 0, seed=int(g["seed"]), cnr_db=float(g["cnr_db"]), noise_seed=int(g["noise_seed"]))
+    audio, _, _, _, text = Chain(0, 0).run(raw)
+    assert np.array_equal(audio, g["binary_audio"]) and text == str(g["frame_text"])
+    assert int(g["executable_distinct_texts_in_4_runs"]) > 1, "if the executable ever becomes deterministic here, pin the fixture to it"
