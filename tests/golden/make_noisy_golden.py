@@ -6,9 +6,9 @@ byte for byte (tests/test_gpu_cli.py::test_cli_matches_reference_on_noisy_input)
   * stdout (int16 audio): from the reference EXECUTABLE (oracle/_ref/fm_radio), which is deterministic in its audio;
   * the frame_thread lines of stderr: from the reference's own FUNCTIONS driven in sequence (oracle/_ref/libfmref.so: the unmodified
     objects behind oracle/ref_shim.cpp: rds_thread's calls, then frame_thread's body).  The executable itself cannot serve here:
-    its RDS output is a race -- four runs on this input print four different sequences of syndromes (and on a CLEAN 12-block input
-    two of three runs differ); the hazards are the ones SURVEY App. A lists as Q16 (ring slot written before the lock is taken,
-    `if`-guarded condition waits), observed here for the first time.  Audio is unaffected (identical md5 over every run).  The
+    its RDS output is NOT DETERMINISTIC -- four runs on this input print four different sequences of syndromes (and on a CLEAN
+    12-block input two of three runs differ), consistent with the hazards SURVEY App. A lists as Q16 (ring slot written before the
+    lock is taken, `if`-guarded condition waits), observed here for the first time.  Audio is unaffected (identical md5 over every run).  The
     script prints how many distinct stderr texts a few runs of the executable give, for the record.
 
     make -C oracle && python tests/golden/make_noisy_golden.py

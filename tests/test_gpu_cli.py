@@ -37,7 +37,7 @@ def test_cli_matches_reference_binary(golden, mode, extra):
 def test_cli_matches_reference_on_noisy_input(extra):
     """The same contract on an input without wide decision margins: AWGN at 4 dB CNR.  Golden (tests/golden/make_noisy_golden.py):
     stdout of the unmodified reference executable, and the frame_thread lines the reference's own functions give when driven in
-    sequence -- the executable's stderr is a race on such input (four runs, four texts), its audio is not.  Default
+    sequence -- the executable's stderr is not deterministic on such input (four runs, four texts), its audio is.  Default
     settings of this executable (STRICT numerics, stage-by-stage RDS back end: every rounding is the reference's): both streams byte
     for byte.  With `--numerics reference` (the batch library's default: FFMA in pllCombine's filter, symbol-rate back end) the audio
     is still byte-identical and the RDS lines are compared too -- on this input they are equal; in general a near-tie may flip (2 of

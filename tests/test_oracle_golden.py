@@ -130,7 +130,7 @@ def test_binary_profile_stereo_dead_after_block0(golden):
 
 def test_oracle_chain_on_noisy_input_equals_the_reference():
     """tests/golden/chain_mode0_noisy.npz (AWGN at 4 dB CNR: decisions without wide margins): audio = stdout of the unmodified
-    reference executable, frame_thread text = the reference's own functions in sequence (the executable's stderr is a race on such
+    reference executable, frame_thread text = the reference's own functions in sequence (the executable's stderr is not deterministic on such
     input: the fixture records 4 different texts in 4 runs).  The oracle port reproduces both."""
     import os
 
