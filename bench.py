@@ -653,20 +653,15 @@ def run_fmrx_arm(args, rank, world, local_rank):
             host_bar = ShmBarrier(rank, world)
 
             def e2e_steps_arbitrated(n):
-                # a turn = the two steps a handle can hold in flight (two staging buffers, two result sets): half as many hand-overs
-                # between the halves as with one step per turn (a hand-over costs ~3 ms: a turn ends with its slowest copy)
                 tickets = []
-                k = 0
-                while k < n:
+                for k in range(n):
                     for half in (0, 1):
                         host_bar.wait()
                         if half == my_half:
-                            if tickets:
-                                rx.wait(tickets[-1])  # the previous turn's results are on the host: its result sets are free again
-                            for j in range(min(2, n - k)):
-                                tickets.append(rx.submit(h_iq[j].data_ptr(), B, hsets[j]["out"]))
+                            tickets.append(rx.submit(h_iq[k % 2].data_ptr(), B, hsets[k % 2]["out"]))
                             rx.wait_ingest(tickets[-1])
-                    k += 2
+                            if k >= 1:
+                                rx.wait(tickets[k - 1])
                 rx.wait(tickets[-1])
 
             rx.reset()
@@ -681,7 +676,7 @@ def run_fmrx_arm(args, rank, world, local_rank):
             arb_value = units / s_arb / 1e6
             ingest["arbitrated_msps"] = round(arb_value, 1)
             if arb_value > e2e_value:
-                ingest["mode"] = "arbitrated: the even and the odd ranks take turns on the host link (two steps per turn; fmrx_batch_wait_ingest + a shared-memory host barrier)"
+                ingest["mode"] = "arbitrated: the even and the odd ranks take turns on the host link (fmrx_batch_wait_ingest + a shared-memory host barrier)"
                 e2e_value, s_e2e = arb_value, s_arb
     ach_gbs = world * S * B * BLOCK_BYTES * args.steps / s_e2e / 1e9
     ceiling = max(all_gbs, ingest.get("halves_taking_turns_gbs", 0.0)) if ingest["mode"] != "free-running" else all_gbs
