@@ -565,7 +565,8 @@ def run_fmrx_arm(args, rank, world, local_rank):
     if args.device_only or args.skip_e2e:
         if rank == 0:
             print(json.dumps({"device_only": True, "value": round(value, 1), "unit": "Msps", "ms_per_step": round(ms_dev / args.steps, 4), "pll_sms": pll_sms,
-                              "filter_sms": filter_sms, "stages_ms": {k: round(v[0] / args.steps, 4) for k, v in stage.items() if v[1]}}), flush=True)
+                              "filter_sms": filter_sms, "pll_pipelined_ms": None if pll_pipelined_ms is None else round(pll_pipelined_ms, 4),
+                              "stages_ms": {k: round(v[0] / args.steps, 4) for k, v in stage.items() if v[1]}}), flush=True)
         return
 
     # ---- end to end: pinned host buffers in and out, every step's copies inside the timed region.  The caller's loop is

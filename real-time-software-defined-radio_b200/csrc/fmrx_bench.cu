@@ -9,8 +9,11 @@
 //   kind 4: DFMA            (FP64 pipe)
 //   kind 5: F2F.F64.F32 + F2F.F32.F64 pairs (the conversion pipe; 1 lane-op = one conversion)
 //   kind 6: SHF + LOP3      (integer ALU pipe)
+//   kind 7: 4 DFMA + one conversion pair, interleaved (1 lane-op = one DFMA or one conversion): do the two pipes overlap?
 // Reported as tera lane-ops per second.
 #include <cuda_runtime.h>
+
+#include <cstdlib>
 
 #include "fmrx_internal.h"
 #include "fmrx_pllmath.h"
@@ -22,24 +25,38 @@ namespace {
 // -> next sample), 8192 loops are 256 warps on 592 schedulers, and what bounds the kernel is the LATENCY of one step of
 // that chain.  This measures it in isolation: one warp, the step of csrc/fmrx_pllmath.h fed from registers (no memory
 // traffic, no other warp on the scheduler), cycles per step from clock64.
+template <int V>
 __global__ void pll_chain_kernel(float *out, long long *cycles, int steps, float freq_ratio, float scale) {
     using namespace pllmath;
+    __shared__ __align__(16) PllTheta theta[16];
+    __shared__ double kdoubles[kPllKDoubles];
+    if (threadIdx.x < 16) theta[threadIdx.x] = pll_theta_entry(threadIdx.x);
+    if (threadIdx.x < kPllKDoubles) kdoubles[threadIdx.x] = pll_k_value(threadIdx.x);
+    __syncwarp();
+    const PllK K = pll_k_from(kdoubles, 0x38000000u);
     PllCarry c{0.0f, 0.0f, 1.0f, 0.0f};
     PllFast f;
     pll_disarm(f);
     const PllCoef p{1e-6f * 3.555f, 1e-3f * 2.666f, scale, 0.1f, (2 * 3.14159265358979323846) * (double)freq_ratio};
     float acc = 0.0f, x = 0.05f + 1e-4f * threadIdx.x;
-    { const PllLibmOut o = pll_step_libm(c, p, x, 1.0f); c = o.c; pll_rearm(f, o.trig); }
+    { const PllLibmOut o = pll_step_libm(c, p, x, 1.0f); c = o.c; if (V >= 1) pll_rearm1(f, o.trig, true, theta, K); else pll_rearm(f, o.trig); }
     int bad = 0;
     const long long t0 = clock64();
     for (int k = 1; k < steps; k += 4) {
         bool ok0, ok1, ok2, ok3;
         const float x0 = -x * 0.999f + 1e-5f, x1 = -x0 * 0.999f + 1e-5f, x2 = -x1 * 0.999f + 1e-5f, x3 = -x2 * 0.999f + 1e-5f;
         x = x3;
-        acc += pll_step_fast(c, f, p, x0, __fadd_rn((float)k, 1.0f), ok0);
-        acc += pll_step_fast(c, f, p, x1, __fadd_rn((float)k, 2.0f), ok1);
-        acc += pll_step_fast(c, f, p, x2, __fadd_rn((float)k, 3.0f), ok2);
-        acc += pll_step_fast(c, f, p, x3, __fadd_rn((float)k, 4.0f), ok3);
+        if (V >= 1) {  // the input alternates in sign: x0 < 0 < x1 ...
+            acc += pll_step_fast1<V == 2>(c, f, p, K, x0, __fadd_rn((float)k, 1.0f), x1 < 0.0f, theta, ok0);
+            acc += pll_step_fast1<V == 2>(c, f, p, K, x1, __fadd_rn((float)k, 2.0f), x2 < 0.0f, theta, ok1);
+            acc += pll_step_fast1<V == 2>(c, f, p, K, x2, __fadd_rn((float)k, 3.0f), x3 < 0.0f, theta, ok2);
+            acc += pll_step_fast1<V == 2>(c, f, p, K, x3, __fadd_rn((float)k, 4.0f), x3 > 0.0f, theta, ok3);
+        } else {
+            acc += pll_step_fast(c, f, p, x0, __fadd_rn((float)k, 1.0f), ok0);
+            acc += pll_step_fast(c, f, p, x1, __fadd_rn((float)k, 2.0f), ok1);
+            acc += pll_step_fast(c, f, p, x2, __fadd_rn((float)k, 3.0f), ok2);
+            acc += pll_step_fast(c, f, p, x3, __fadd_rn((float)k, 4.0f), ok3);
+        }
         bad += !(ok0 && ok1 && ok2 && ok3);
     }
     const long long t1 = clock64();
@@ -89,6 +106,15 @@ __global__ void __launch_bounds__(256) pipe_rate_kernel(float *sink, double a, d
                 asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(f[i]) : "d"(t));
             }
             if (KIND == 6) u[i] = __funnelshift_l(u[i], u[i], 7) ^ (k1 + k2);  // SHF + LOP3
+            if (KIND == 7) {
+                double t;
+                d[i] = __fma_rn(d[i], a, b);
+                asm volatile("cvt.f64.f32 %0, %1;" : "=d"(t) : "f"(f[i]));
+                d[i] = __fma_rn(d[i], a, b);
+                d[i] = __fma_rn(d[i], a, b);
+                asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(f[i]) : "d"(t));
+                d[i] = __fma_rn(d[i], a, b);
+            }
         }
     }
     double s = 0.0;
@@ -120,7 +146,7 @@ int run_pipe(int reps, double *tera) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, t0, t1);
         // lane-ops per (i, it) per thread: one DFMA; two conversions; two integer instructions
-        const double ops = (double)grid * 256 * iters * ILP * (KIND == 4 ? 1.0 : 2.0);
+        const double ops = (double)grid * 256 * iters * ILP * (KIND == 4 ? 1.0 : KIND == 7 ? 6.0 : 2.0);
         const double rate = ops / (ms * 1e-3) / 1e12;
         if (r >= 2 && rate > best) best = rate;
     }
@@ -177,7 +203,12 @@ int measure_pll_chain(double *cycles_per_step) {
     if (e) return (int)e;
     e = cudaMalloc(&cyc, sizeof(long long));
     if (e) { cudaFree(out); return (int)e; }
-    for (int r = 0; r < 2; ++r) pll_chain_kernel<<<1, 32>>>(out, cyc, steps, 19e3f / 240e3f, 2.0f);  // second run: instruction cache warm
+    static const int variant = [] { const char *e = getenv("FMRX_PLL_STEP"); return e ? atoi(e) : 0; }();  // the kernel's variant (csrc/fmrx_pll.cu)
+    for (int r = 0; r < 2; ++r) {  // second run: instruction cache warm
+        if (variant == 0) pll_chain_kernel<0><<<1, 32>>>(out, cyc, steps, 19e3f / 240e3f, 2.0f);
+        else if (variant == 2) pll_chain_kernel<2><<<1, 32>>>(out, cyc, steps, 19e3f / 240e3f, 2.0f);
+        else pll_chain_kernel<1><<<1, 32>>>(out, cyc, steps, 19e3f / 240e3f, 2.0f);
+    }
     launch_counter() += 2;
     e = cudaMemcpy(&h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
     cudaFree(out); cudaFree(cyc);
@@ -196,6 +227,7 @@ int measure_fp32_peak(int, int kind, int reps, double *tera) {
         case 4: return run_pipe<4>(reps, tera);
         case 5: return run_pipe<5>(reps, tera);
         case 6: return run_pipe<6>(reps, tera);
+        case 7: return run_pipe<7>(reps, tera);
         default: return (int)cudaErrorInvalidValue;
     }
 }

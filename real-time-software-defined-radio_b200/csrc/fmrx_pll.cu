@@ -16,6 +16,8 @@
 // (the 114 kHz loop's argument passes 1e5 rad within three blocks).
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "fmrx_internal.h"
 #include "fmrx_pllmath.h"
 
@@ -43,7 +45,19 @@ struct PllSide {
     float Ki, Kp, fratio, scale, adj;
 };
 
-__global__ void __launch_bounds__(32) pll_kernel(PllSide A, PllSide B, long long ld, int n_streams, int n, int n_blocks) {
+// V selects the step of fmrx_pllmath.h: 0 = conversions as instructions, both signs' theta0 prepared; 1 = integer-built
+// conversions and theta0 for the next sample's sign only (fewer instructions on the FP64 and conversion pipes); 2 = as 1 with
+// the two widenings that are off the dependency chain left as conversion instructions.
+template <int V>
+__global__ void __launch_bounds__(32, 8) pll_kernel(PllSide A, PllSide B, long long ld, int n_streams, int n, int n_blocks) {
+    __shared__ __align__(16) pllmath::PllTheta theta[16];  // V = 1: (k*H1, k*L1) by (quadrant, sign of r, sign of the next sample)
+    __shared__ double kdoubles[pllmath::kPllKDoubles];      // V = 1: the step's double constants, loaded so that they stay in registers
+    if (V >= 1) {
+        if (threadIdx.x < 16) theta[threadIdx.x] = pllmath::pll_theta_entry(threadIdx.x);
+        if (threadIdx.x < pllmath::kPllKDoubles) kdoubles[threadIdx.x] = pllmath::pll_k_value(threadIdx.x);
+        __syncwarp();
+    }
+    const pllmath::PllK K = V >= 1 ? pllmath::pll_k_from(kdoubles, 0x38000000u) : pllmath::PllK{};
     int lane = blockIdx.x * 32 + threadIdx.x;
     const PllSide &P = lane < n_streams ? A : B;
     if (lane >= n_streams) lane -= n_streams;
@@ -60,10 +74,11 @@ __global__ void __launch_bounds__(32) pll_kernel(PllSide A, PllSide B, long long
     float last = st[5];
     const PllCoef p{P.Ki, P.Kp, P.scale, P.adj, __dmul_rn(kTwoPi, (double)P.fratio)};
     // the libm path, out of line: one step, everything by value
-    auto slow = [&](float xin, float cnt) {
+    auto slow = [&](float xin, float cnt, float xnext) {
         const PllLibmOut o = pll_step_libm(c, p, xin, cnt);
         c = o.c;
-        pllmath::pll_rearm(f, o.trig);
+        if (V >= 1) pllmath::pll_rearm1(f, o.trig, xnext < 0.0f, theta, K);
+        else pllmath::pll_rearm(f, o.trig);
         return o.nco;
     };
     for (int b = 0; b < n_blocks; ++b) {
@@ -72,6 +87,7 @@ __global__ void __launch_bounds__(32) pll_kernel(PllSide A, PllSide B, long long
         const float *mb = mul ? mul + (long long)b * n : nullptr;
         float *pb = prod ? prod + (long long)b * n : nullptr;
         int k = 0;
+        const bool off_ok = V == 0 || (off >= 0.0f && off < 1.0e30f);  // V = 1 rebuilds (double)cnt from the bits of a normal float >= 1
         if ((((uintptr_t)xb | (uintptr_t)ob | (uintptr_t)mb | (uintptr_t)pb) & 15) == 0 && n >= 8) {
             // the input is read two groups (8 samples, ~2.5k cycles of loop time) ahead of its use: a lane streams its
             // own row, so every load is a cache line of its own and would otherwise sit on the dependency chain
@@ -79,51 +95,77 @@ __global__ void __launch_bounds__(32) pll_kernel(PllSide A, PllSide B, long long
             const int groups = n / 4;
             const float4 *m4 = reinterpret_cast<const float4 *>(mb);
             float4 v0 = __ldg(x4), v1 = __ldg(x4 + 1);
+            const float x_after = (V >= 1 && b + 1 < n_blocks) ? __ldg(xb + n) : 1.0f;  // what follows this block's last sample
             float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
             if (pb) { w0 = __ldg(m4); w1 = __ldg(m4 + 1); }
-            for (int g = 0; g < groups; ++g, k += 4) {
-                const float4 v = v0, w = w0;
-                v0 = v1;
-                w0 = w1;
-                if (g + 2 < groups) {
-                    v1 = __ldg(x4 + g + 2);
-                    if (pb) w1 = __ldg(m4 + g + 2);
+            int g = 0;
+            while (g < groups) {
+                float4 v, w, o;
+                float xn;
+                bool redo = false;
+                // The fast run.  No call inside this loop, so the double constants of the step stay in registers from one
+                // iteration to the next (with the libm redo inside the loop ptxas rebuilt 35 of them at the top of every
+                // iteration: 9 of 176 instructions per step).
+                for (; g < groups; ++g, k += 4) {
+                    v = v0;
+                    w = w0;
+                    v0 = v1;
+                    w0 = w1;
+                    if (g + 2 < groups) {
+                        v1 = __ldg(x4 + g + 2);
+                        if (pb) w1 = __ldg(m4 + g + 2);
+                    }
+                    // ... and its 128-byte line is pulled into L2 sixteen groups before that: with 8192 lanes each on a row of
+                    // its own, every line is a DRAM page (and mostly a TLB) miss, and the register prefetch alone left 15% of
+                    // the kernel's samples waiting on it (ncu source page, profiles/r1w)
+                    if ((g & 7) == 0 && g + 16 < groups) {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(x4 + g + 16));
+                        if (pb) asm volatile("prefetch.global.L2 [%0];" ::"l"(m4 + g + 16));
+                    }
+                    // four branch-free steps = one basic block; if any of them left the fast path's domain (first group
+                    // after loading the state, zero / non-finite input, the +-pi seam: ~1e-5 of the groups) the four
+                    // carried floats are restored and the group is redone with libm
+                    const PllCarry saved = c;
+                    const float s_last = last;
+                    bool ok0, ok1, ok2, ok3;
+                    o.x = last;
+                    xn = g + 1 < groups ? v0.x : x_after;  // the sample after this group (V = 1 prepares for its sign)
+                    if (V >= 1) {
+                        o.y = pllmath::pll_step_fast1<V == 2>(c, f, p, K, v.x, count(off, k), v.y < 0.0f, theta, ok0);
+                        o.z = pllmath::pll_step_fast1<V == 2>(c, f, p, K, v.y, count(off, k + 1), v.z < 0.0f, theta, ok1);
+                        o.w = pllmath::pll_step_fast1<V == 2>(c, f, p, K, v.z, count(off, k + 2), v.w < 0.0f, theta, ok2);
+                        last = pllmath::pll_step_fast1<V == 2>(c, f, p, K, v.w, count(off, k + 3), xn < 0.0f, theta, ok3);
+                    } else {
+                        o.y = pll_step_fast(c, f, p, v.x, count(off, k), ok0);
+                        o.z = pll_step_fast(c, f, p, v.y, count(off, k + 1), ok1);
+                        o.w = pll_step_fast(c, f, p, v.z, count(off, k + 2), ok2);
+                        last = pll_step_fast(c, f, p, v.w, count(off, k + 3), ok3);
+                    }
+                    if (!(ok0 && ok1 && ok2 && ok3 && off_ok)) {
+                        c = saved;
+                        last = s_last;
+                        redo = true;
+                        break;
+                    }
+                    *reinterpret_cast<float4 *>(ob + k) = o;
+                    if (pb) *reinterpret_cast<float4 *>(pb + k) = make_float4(__fmul_rn(w.x, o.x), __fmul_rn(w.y, o.y), __fmul_rn(w.z, o.z), __fmul_rn(w.w, o.w));
                 }
-                // ... and its 128-byte line is pulled into L2 sixteen groups before that: with 8192 lanes each on a row of
-                // its own, every line is a DRAM page (and mostly a TLB) miss, and the register prefetch alone left 15% of
-                // the kernel's samples waiting on it (ncu source page, profiles/r1w)
-                if ((g & 7) == 0 && g + 16 < groups) {
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(x4 + g + 16));
-                    if (pb) asm volatile("prefetch.global.L2 [%0];" ::"l"(m4 + g + 16));
-                }
-                // four branch-free steps = one basic block; if any of them left the fast path's domain (first group
-                // after loading the state, zero / non-finite input, the +-pi seam: ~1e-5 of the groups) the four
-                // carried floats are restored and the group is redone with libm
-                const PllCarry saved = c;
-                const float s_last = last;
-                bool ok0, ok1, ok2, ok3;
-                float4 o;
+                if (!redo) break;
                 o.x = last;
-                o.y = pll_step_fast(c, f, p, v.x, count(off, k), ok0);
-                o.z = pll_step_fast(c, f, p, v.y, count(off, k + 1), ok1);
-                o.w = pll_step_fast(c, f, p, v.z, count(off, k + 2), ok2);
-                last = pll_step_fast(c, f, p, v.w, count(off, k + 3), ok3);
-                if (!(ok0 && ok1 && ok2 && ok3)) {
-                    c = saved;
-                    o.x = s_last;
-                    o.y = slow(v.x, count(off, k));
-                    o.z = slow(v.y, count(off, k + 1));
-                    o.w = slow(v.z, count(off, k + 2));
-                    last = slow(v.w, count(off, k + 3));
-                }
+                o.y = slow(v.x, count(off, k), v.y);
+                o.z = slow(v.y, count(off, k + 1), v.z);
+                o.w = slow(v.z, count(off, k + 2), v.w);
+                last = slow(v.w, count(off, k + 3), xn);
                 *reinterpret_cast<float4 *>(ob + k) = o;
                 if (pb) *reinterpret_cast<float4 *>(pb + k) = make_float4(__fmul_rn(w.x, o.x), __fmul_rn(w.y, o.y), __fmul_rn(w.z, o.z), __fmul_rn(w.w, o.w));
+                ++g;
+                k += 4;
             }
         }
         for (; k < n; ++k) {
             ob[k] = last;  // output sample k is the NCO value of step k-1 (src/helper.cpp:29,44,56)
             if (pb) pb[k] = __fmul_rn(mb[k], last);
-            last = slow(xb[k], count(off, k));
+            last = slow(xb[k], count(off, k), (k + 1 < n || b + 1 < n_blocks) ? xb[k + 1] : 1.0f);
         }
         off = __fadd_rn(off, (float)n);  // src/helper.cpp:53
     }
@@ -249,7 +291,10 @@ int launch_pll_blocks(const float *xa, float *ncoa, PllParams pa, float *sta, co
     PllSide A = make_side(xa, ncoa, sta, pa, mula, proda);
     PllSide B = xb ? make_side(xb, ncob, stb, pb, mulb, prodb) : PllSide{};
     const int lanes = xb ? 2 * n_streams : n_streams;
-    pll_kernel<<<(lanes + 31) / 32, 32, 0, st>>>(A, B, ld, n_streams, n, n_blocks);
+    static const int variant = [] { const char *e = getenv("FMRX_PLL_STEP"); return e ? atoi(e) : 0; }();
+    if (variant == 0) pll_kernel<0><<<(lanes + 31) / 32, 32, 0, st>>>(A, B, ld, n_streams, n, n_blocks);
+    else if (variant == 2) pll_kernel<2><<<(lanes + 31) / 32, 32, 0, st>>>(A, B, ld, n_streams, n, n_blocks);
+    else pll_kernel<1><<<(lanes + 31) / 32, 32, 0, st>>>(A, B, ld, n_streams, n, n_blocks);
     launch_counter() += 1;
     return (int)cudaGetLastError();
 }

@@ -145,6 +145,74 @@ FMRX_HD double cos_cw(double T) {
     return v.cs;
 }
 
+// The same routine with its fifteen non-trivial double constants taken from a struct: ptxas treats a 64-bit immediate as free to
+// rebuild and re-materialises all of them (two moves each) at the top of every loop iteration, 14 of 176 instructions per
+// step; values the kernel has LOADED (from shared memory, once per launch) stay in registers instead.  Same operations in the
+// same order as sincos_cw.
+struct PllK {
+    double two_over_pi, p1, p2, s1, s2, s3, s4, s5, s6, c1, c2, c3, c4, c5, c6;
+    unsigned bias_hi;          // 896 << 20, the exponent re-bias of the float -> double re-packing
+};
+constexpr int kPllKDoubles = 15;
+FMRX_HD double pll_k_value(int i) {
+    switch (i) {
+        case 0: return 6.36619772367581382433e-01;
+        case 1: return 1.5707963267948966;
+        case 2: return 6.123233995736766e-17;
+        case 3: return -1.66666666666666324348e-01;
+        case 4: return 8.33333333332248946124e-03;
+        case 5: return -1.98412698298579493134e-04;
+        case 6: return 2.75573137070700676789e-06;
+        case 7: return -2.50507602534068634195e-08;
+        case 8: return 1.58969099521155010221e-10;
+        case 9: return 4.16666666666666019037e-02;
+        case 10: return -1.38888888888741095749e-03;
+        case 11: return 2.48015872894767294178e-05;
+        case 12: return -2.75573143513906633035e-07;
+        case 13: return 2.08757232129817482790e-09;
+        default: return -1.13596475577881948265e-11;
+    }
+}
+FMRX_HD PllK pll_k_from(const double *v, unsigned bias_hi) {
+    PllK k;
+    k.two_over_pi = v[0]; k.p1 = v[1]; k.p2 = v[2];
+    k.s1 = v[3]; k.s2 = v[4]; k.s3 = v[5]; k.s4 = v[6]; k.s5 = v[7]; k.s6 = v[8];
+    k.c1 = v[9]; k.c2 = v[10]; k.c3 = v[11]; k.c4 = v[12]; k.c5 = v[13]; k.c6 = v[14];
+    k.bias_hi = bias_hi;
+    return k;
+}
+FMRX_HD PllK pll_k_literal() {
+    double v[kPllKDoubles];
+    for (int i = 0; i < kPllKDoubles; ++i) v[i] = pll_k_value(i);
+    return pll_k_from(v, 0x38000000u);
+}
+
+FMRX_HD SinCos sincos_k(double T, const PllK &K) {
+    const double MAGIC = 6755399441055744.0;
+    const double t = fma_(T, K.two_over_pi, MAGIC);
+    const double fn = t - MAGIC;
+    SinCos o;
+    o.q = lo_word(t) & 3;
+    double r = fma_(-fn, K.p1, T);
+    r = fma_(-fn, K.p2, r);
+    o.r = r;
+    const double z = r * r;
+    const double z2 = z * z;
+    const double sa = fma_(z, K.s2, K.s1), sb = fma_(z, K.s4, K.s3), sc = fma_(z, K.s6, K.s5);
+    const double ca = fma_(z, K.c2, K.c1), cb = fma_(z, K.c4, K.c3), cc = fma_(z, K.c6, K.c5);
+    const double z4 = z2 * z2;
+    const double rz = r * z;
+    const double hz = fma_(z, -0.5, 1.0);
+    const double sp = fma_(z4, sc, fma_(z2, sb, sa));
+    const double cp = fma_(z4, cc, fma_(z2, cb, ca));
+    const double s = fma_(rz, sp, r);
+    const double c = fma_(z2, cp, hz);
+    const double sn0 = (o.q & 1) ? c : s, cs0 = (o.q & 1) ? s : c;
+    o.sn = make_double_(hi_word_(sn0) ^ (int)(((unsigned)o.q & 2u) << 30), lo_word(sn0));
+    o.cs = make_double_(hi_word_(cs0) ^ (int)((((unsigned)o.q + 1u) & 2u) << 30), lo_word(cs0));
+    return o;
+}
+
 FMRX_HD float mul_rn(float a, float b) {
 #ifdef __CUDA_ARCH__
     return __fmul_rn(a, b);
@@ -202,6 +270,7 @@ struct PllFast {
     double cs, sn;
     double th_hi_p, th_s1_p, th_hi_n, th_s1_n;
     bool usable_p, usable_n;  // armed and not within 1e-5 of the seam, for x > 0 / x < 0
+    bool neg;                 // V = 1: the sign of x the (single) theta0 in th_hi_p / th_s1_p / usable_p was prepared for
 };
 
 constexpr float kTrigLimitF = 1.0e12f;  // < 2^40
@@ -227,9 +296,87 @@ FMRX_HD void pll_prepare(PllFast &f, const SinCos &v) {
     f.usable_n = !(q == 0 && near0);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Variant 1 of the step (round 2): the same arithmetic with fewer instructions on the two half-rate pipes.  On its
+// partition the kernel is bound by instruction issue, and ncu shows the FP64 pipe and the conversion (XU) pipe taking
+// turns: 57.5 FP64 instructions at 2 scheduler-cycles and 16.75 conversions at 8 per step.  A float -> double
+// conversion of a NORMAL finite float is a re-packing of its bits (sign, exponent + 896, mantissa << 29) -- exact, and
+// three integer instructions on pipes the step leaves idle; `ok` already sends zero / non-finite values to the libm
+// path and now also anything outside [FLT_MIN, 1e30).  theta0 is prepared for the sign of the NEXT sample only (the
+// caller knows it: the input is in registers two groups ahead), with k * (pi/2) and k * (pi/2's tail) picked as bit
+// patterns (k is -2..2: the same mantissas, exponent + 1 for |k| = 2) instead of two int -> double conversions, two
+// multiplies and one of the two FMAs; a wrong prediction is caught in `ok` (f.neg) and costs one libm group.
+// ---------------------------------------------------------------------------------------------------------------
+FMRX_HD unsigned float_bits(float v) {
+#ifdef __CUDA_ARCH__
+    return __float_as_uint(v);
+#else
+    unsigned u;
+    memcpy(&u, &v, 4);
+    return u;
+#endif
+}
+// |v| in [FLT_MIN, 1e30): false for zero, subnormal, huge, infinite and NaN
+FMRX_HD bool is_plain(float v) { return fabsf(v) >= 1.17549435e-38f && fabsf(v) < 1.0e30f; }
+// (double)v for a normal finite float, exact
+FMRX_HD double widen(float v, const PllK &K) {
+    // arithmetic shift: ssss eeeeeeee mmm...; drop the three sign copies below the top one, re-bias the exponent
+    const unsigned b = float_bits(v);
+    const unsigned h = (unsigned)((int)b >> 3);
+    return make_double((int)((h & 0x8FFFFFFFu) + K.bias_hi), (int)(b << 29));
+}
+// the same for a value known to be positive
+FMRX_HD double widen_pos(float v, const PllK &K) {
+    const unsigned t = float_bits(v);
+    return make_double((int)((t >> 3) + K.bias_hi), (int)(t << 29));
+}
+
+// theta0 = k*(pi/2) - r in (-pi, pi] as (k*H1, k*L1), H1 + L1 = pi/2: looked up by (quadrant of T, sign of r, sign of the
+// next sample) -- sixteen pairs of doubles; the kernel keeps the table in shared memory (one LDS.128 per step on a pipe the
+// step does not otherwise use), the host builds the entry on the fly.
+//   qq = (q + 2*[x < 0]) & 3:  0 -> k = 0, 1 -> -1, 2 -> +2 (r >= 0) or -2 (r < 0), 3 -> +1
+struct PllTheta {
+    double kh, kl;
+};
+FMRX_HD int pll_theta_index(int q, bool rneg, bool neg_next) { return q | (rneg ? 4 : 0) | (neg_next ? 8 : 0); }
+FMRX_HD PllTheta pll_theta_entry(int idx) {
+    const double H1 = 1.5707963267948966, L1 = 6.123233995736766e-17;
+    const int qq = ((idx & 3) + ((idx & 8) ? 2 : 0)) & 3;
+    const bool rneg = (idx & 4) != 0;
+    const double k = qq == 0 ? 0.0 : qq == 1 ? -1.0 : qq == 3 ? 1.0 : (rneg ? -2.0 : 2.0);
+    PllTheta t;
+    t.kh = k * H1;  // exact: k is 0, +-1, +-2
+    t.kl = k * L1;
+    return t;
+}
+
+FMRX_HD void pll_prepare1(PllFast &f, const SinCos &v, bool neg_next, const PllTheta *table) {
+    f.cs = v.cs;
+    f.sn = v.sn;
+    const int rh = hi_word(v.r);
+    const bool rneg = rh < 0;                                      // sign bit (a -0 is inside the seam band anyway)
+    const bool near0 = (unsigned)(rh & 0x7fffffff) < 0x3EE4F8B5u;  // |r| < ~1e-5
+    const int idx = pll_theta_index(v.q, rneg, neg_next);
+#ifdef __CUDA_ARCH__
+    const PllTheta t = table[idx];
+#else
+    const PllTheta t = table ? table[idx] : pll_theta_entry(idx);
+#endif
+    f.th_hi_p = t.kh;
+    f.th_s1_p = t.kl - v.r;  // = fma(k, L1, -r): k * L1 is exact
+    const int q2 = neg_next ? 0 : 2;  // the quadrant whose theta0 sits on the +-pi seam
+    f.usable_p = !((v.q == q2) & near0);
+    f.neg = neg_next;
+}
+
 // re-arm the fast detector from the float trigArg of the step just taken
 FMRX_HD void pll_rearm(PllFast &f, float trig) {
     if (fabsf(trig) < kTrigLimitF) pll_prepare(f, sincos_cw((double)trig));
+    else pll_disarm(f);
+}
+
+FMRX_HD void pll_rearm1(PllFast &f, float trig, bool neg_next, const PllTheta *table, const PllK &K) {
+    if (is_plain(trig) && fabsf(trig) < kTrigLimitF) pll_prepare1(f, sincos_k((double)trig, K), neg_next, table);
     else pll_disarm(f);
 }
 
@@ -258,6 +405,39 @@ FMRX_HD float pll_step_fast(PllCarry &c, PllFast &f, const PllCoef &p, float x, 
     c.fbi = (float)v.cs;
     c.fbq = (float)v.sn;
     return (float)cos_cw((double)targ);
+}
+
+// variant 1 (see above): neg_next = sign of the sample the NEXT step will see
+// F2F_SIDE: the two widenings off the detector -> loop filter -> oscillator chain (1/x and the NCO argument) as conversion
+// instructions again: 6 instructions fewer per step for 16 more cycles of the conversion pipe (kernel variant 2)
+template <bool F2F_SIDE = false>
+FMRX_HD float pll_step_fast1(PllCarry &c, PllFast &f, const PllCoef &p, const PllK &K, float x, float cnt, bool neg_next, const PllTheta *table, bool &ok) {
+    const bool neg = x < 0.0f;
+    const float ax = fabsf(x);
+    const float eI = mul_rn(x, c.fbi);
+    const float eQ = mul_rn(x, -c.fbq);
+    // `&`, not `&&`: one basic block.  x in (1e-18, 1e18) and |fbi|, |fbq| <= 1 bound eI, eQ from above; cnt = (offset + k) + 1
+    // with an offset the caller has checked is plain once per block
+    bool good = f.usable_p & (neg == f.neg) & (ax > 1e-18f) & (ax < 1e18f) & (fabsf(eI) >= 1.17549435e-38f) & (fabsf(eQ) >= 1.17549435e-38f);
+    const double rx = F2F_SIDE ? (double)rcp_approx(x) : widen(rcp_approx(x), K);
+    const double dI = widen(eI, K), dQ = widen(eQ, K);
+    const double dot = fma_(dQ, -f.sn, dI * f.cs);
+    const double cross = fma_(dQ, f.cs, dI * f.sn);
+    const double e = fma_(-dot, rx, 2.0);
+    const double raw = f.th_hi_p + fma_(cross * rx, e, f.th_s1_p);
+    const double ang = make_double((hi_word(raw) & 0x7fffffff) | (int)(float_bits(eQ) & 0x80000000u), lo_word(raw));  // copysign(|raw|, eQ)
+    const float eD = (float)ang;
+    c.integ = add_rn(c.integ, mul_rn(p.Ki, eD));
+    c.phase = add_rn(c.phase, add_rn(mul_rn(p.Kp, eD), c.integ));
+    const float trig = (float)dadd_rn(dmul_rn(p.w, widen_pos(cnt, K)), widen(c.phase, K));  // src/helper.cpp:41: double expression, no FMA
+    const float targ = add_rn(mul_rn(trig, p.scale), p.adj);
+    good = good & is_plain(c.phase) & (fabsf(trig) >= 1.17549435e-38f) & (fabsf(trig) < kTrigLimitF) & (fabsf(targ) >= 1.17549435e-38f) & (fabsf(targ) < kTrigLimitF);
+    ok = good;
+    const SinCos v = sincos_k(widen(trig, K), K);
+    pll_prepare1(f, v, neg_next, table);
+    c.fbi = (float)v.cs;
+    c.fbq = (float)v.sn;
+    return (float)sincos_k(F2F_SIDE ? (double)targ : widen(targ, K), K).cs;
 }
 
 // the same step through libm, everything by value (a cold, out-of-line call on the device must not pin the caller's
@@ -292,6 +472,20 @@ FMRX_HD float pll_step(PllCarry &c, PllFast &f, const PllCoef &p, float x, float
         c = o.c;
         out = o.nco;
         pll_rearm(f, o.trig);
+    }
+    return out;
+}
+
+FMRX_HD float pll_step1(PllCarry &c, PllFast &f, const PllCoef &p, float x, float cnt, bool neg_next, const PllTheta *table) {
+    const PllK K = pll_k_literal();
+    const PllCarry saved = c;
+    bool ok;
+    float out = pll_step_fast1(c, f, p, K, x, cnt, neg_next, table, ok);
+    if (!ok || !is_plain(cnt)) {
+        const PllLibmOut o = pll_step_libm(saved, p, x, cnt);
+        c = o.c;
+        out = o.nco;
+        pll_rearm1(f, o.trig, neg_next, table, K);
     }
     return out;
 }

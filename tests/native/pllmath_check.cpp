@@ -1,7 +1,9 @@
 // CPU check of the PLL's double-precision kernels (the product header fmrx_pllmath.h compiled for the host) against
 // glibc, which is what the reference links (fmPLL, /root/reference/src/helper.cpp:13-57 calls atan2/cos/sin on doubles).
 //   pllmath_check sincos <n>        max error of sincos_cw vs glibc sin/cos in double ulps over float-valued arguments
-//   pllmath_check loop <blocks>     runs the fast loop and a libm-only loop side by side and counts float mismatches
+//   pllmath_check loop <blocks> [variant]   runs the fast loop (variant 0: conversion instructions; 1: integer-built
+//                                   conversions, theta0 for the next sample's sign) and a libm-only loop side by side and counts float mismatches
+//   pllmath_check widen <n>         the integer-built float -> double conversion against the cast
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -53,8 +55,28 @@ int main(int argc, char **argv) {
         printf("{\"n\": %ld, \"max_ulp_sin\": %.3f, \"max_ulp_cos\": %.3f, \"max_abs\": %.3e, \"float_flips\": %ld}\n", n, worst_s, worst_c, worst_abs, flips);
         return 0;
     }
+    if (!strcmp(argv[1], "widen")) {
+        const long n = atol(argv[2]);
+        long bad = 0;
+        for (long i = 0; i < n; ++i) {
+            unsigned u = (unsigned)rng();
+            float v;
+            memcpy(&v, &u, 4);
+            if (!is_plain(v)) continue;
+            const PllK K = pll_k_literal();
+            const double w = widen(v, K), wp = widen_pos(fabsf(v), K);
+            bad += (w != (double)v) || (wp != (double)fabsf(v)) || (std::signbit(w) != std::signbit(v));
+        }
+        const float edge[] = {1.17549435e-38f, -1.17549435e-38f, 9.99999e29f, 1.0f, -1.0f, 16777216.0f, 3.0e-20f};
+        for (float v : edge) bad += widen(v, pll_k_literal()) != (double)v;
+        printf("{\"n\": %ld, \"bad\": %ld}\n", n, bad);
+        return 0;
+    }
     if (!strcmp(argv[1], "loop")) {
-        const int blocks = atoi(argv[2]), N = 15360;
+        const int blocks = atoi(argv[2]), N = 15360, variant = argc > 3 ? atoi(argv[3]) : 0;
+        std::vector<float> xs(N + 1);
+        PllTheta table[16];  // variant 2: the lookup table as the kernel stages it
+        for (int i = 0; i < 16; ++i) table[i] = pll_theta_entry(i);
         long total = 0, mism = 0, fast_steps = 0;
         double max_nco_diff = 0;
         for (int cfg = 0; cfg < 2; ++cfg) {
@@ -75,9 +97,19 @@ int main(int argc, char **argv) {
                         const double t = ((double)b * N + k) / Fs;
                         float x = (float)(amp * cos(2 * 3.14159265358979323846 * (freq + df) * t + ph0) + amp * noise(rng));
                         if (trial == 3 && (k % 977) == 0) x = 0.0f;  // exact zeros exercise the libm path
+                        xs[k] = x;
+                    }
+                    xs[N] = 1.0f;  // the kernel does not look across a block boundary either: it predicts "positive"
+                    for (int k = 0; k < N; ++k) {
+                        const float x = xs[k];
+                        const bool neg_next = xs[k + 1] < 0.0f;
                         const float cnt = add_rn(add_rn(off, (float)k), 1.0f);
-                        { bool ok; PllCarry pc = c; PllFast pf = f; pll_step_fast(pc, pf, p, x, cnt, ok); fast_steps += ok; }
-                        const float a = pll_step(c, f, p, x, cnt), g = ref_step(r, x, cnt);
+                        {
+                            bool ok; PllCarry pc = c; PllFast pf = f;
+                            if (variant) pll_step_fast1(pc, pf, p, pll_k_literal(), x, cnt, neg_next, variant == 2 ? table : nullptr, ok); else pll_step_fast(pc, pf, p, x, cnt, ok);
+                            fast_steps += ok;
+                        }
+                        const float a = variant ? pll_step1(c, f, p, x, cnt, neg_next, variant == 2 ? table : nullptr) : pll_step(c, f, p, x, cnt), g = ref_step(r, x, cnt);
                         ++total;
                         const bool same = a == g && c.integ == r.integ && c.phase == r.phase && c.fbi == r.fbi && c.fbq == r.fbq;
                         if (!same) {
