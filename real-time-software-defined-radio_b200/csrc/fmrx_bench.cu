@@ -10,6 +10,7 @@
 //   kind 5: F2F.F64.F32 + F2F.F32.F64 pairs (the conversion pipe; 1 lane-op = one conversion)
 //   kind 6: SHF + LOP3      (integer ALU pipe)
 //   kind 7: 4 DFMA + one conversion pair, interleaved (1 lane-op = one DFMA or one conversion): do the two pipes overlap?
+//   kind 8: DFMA with three distinct vector-register operands (kind 4's multiplier and addend are kernel parameters, i.e. uniform)
 // Reported as tera lane-ops per second.
 #include <cuda_runtime.h>
 
@@ -96,6 +97,9 @@ __global__ void __launch_bounds__(256) pipe_rate_kernel(float *sink, double a, d
 #pragma unroll
     for (int i = 0; i < ILP; ++i) { d[i] = threadIdx.x * 1e-3 + i; f[i] = threadIdx.x * 1e-3f + i; u[i] = threadIdx.x * 2654435761u + i; }
     const unsigned k1 = (unsigned)__double2loint(a) | 1u, k2 = (unsigned)__double2hiint(b);
+    double e[ILP], g[ILP];  // kind 8: per-thread values, so they live in vector registers
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) { e[i] = a + 1e-9 * (threadIdx.x + i); g[i] = b + 1e-12 * (threadIdx.x * 3 + i); }
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int i = 0; i < ILP; ++i) {
@@ -106,6 +110,7 @@ __global__ void __launch_bounds__(256) pipe_rate_kernel(float *sink, double a, d
                 asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(f[i]) : "d"(t));
             }
             if (KIND == 6) u[i] = __funnelshift_l(u[i], u[i], 7) ^ (k1 + k2);  // SHF + LOP3
+            if (KIND == 8) d[i] = __fma_rn(d[i], e[i], g[i]);
             if (KIND == 7) {
                 double t;
                 d[i] = __fma_rn(d[i], a, b);
@@ -146,7 +151,7 @@ int run_pipe(int reps, double *tera) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, t0, t1);
         // lane-ops per (i, it) per thread: one DFMA; two conversions; two integer instructions
-        const double ops = (double)grid * 256 * iters * ILP * (KIND == 4 ? 1.0 : KIND == 7 ? 6.0 : 2.0);
+        const double ops = (double)grid * 256 * iters * ILP * ((KIND == 4 || KIND == 8) ? 1.0 : KIND == 7 ? 6.0 : 2.0);
         const double rate = ops / (ms * 1e-3) / 1e12;
         if (r >= 2 && rate > best) best = rate;
     }
@@ -203,7 +208,7 @@ int measure_pll_chain(double *cycles_per_step) {
     if (e) return (int)e;
     e = cudaMalloc(&cyc, sizeof(long long));
     if (e) { cudaFree(out); return (int)e; }
-    static const int variant = [] { const char *e = getenv("FMRX_PLL_STEP"); return e ? atoi(e) : 0; }();  // the kernel's variant (csrc/fmrx_pll.cu)
+    static const int variant = [] { const char *e = getenv("FMRX_PLL_STEP"); return e ? atoi(e) : 2; }();  // the kernel's variant (csrc/fmrx_pll.cu)
     for (int r = 0; r < 2; ++r) {  // second run: instruction cache warm
         if (variant == 0) pll_chain_kernel<0><<<1, 32>>>(out, cyc, steps, 19e3f / 240e3f, 2.0f);
         else if (variant == 2) pll_chain_kernel<2><<<1, 32>>>(out, cyc, steps, 19e3f / 240e3f, 2.0f);
@@ -228,6 +233,7 @@ int measure_fp32_peak(int, int kind, int reps, double *tera) {
         case 5: return run_pipe<5>(reps, tera);
         case 6: return run_pipe<6>(reps, tera);
         case 7: return run_pipe<7>(reps, tera);
+        case 8: return run_pipe<8>(reps, tera);
         default: return (int)cudaErrorInvalidValue;
     }
 }

@@ -733,7 +733,7 @@ int fmrx_batch_create(const fmrx_config *cfg, fmrx_batch **out) {
         if (const char *e = getenv("FMRX_PIPE_PRIO")) { if (e[0] == '0') greatest = least; }  // experiment switch: equal priorities
         const int mid = greatest < least ? greatest + 1 : least;
         // FMRX_PLL_SMS: SMs set aside for the PLL stream (0 = no partition).  Default: the split that minimises
-        // max(PLL phase, filter phases) under the measured cost model: the PLL kernel takes 3.65 / 4.6 / 6.5 / 8.7 ms
+        // max(PLL phase, filter phases) under the measured cost model: the PLL kernel takes 3.2 / 4.4 / 6.1 / 8.8 ms
         // per 64 ms block at 1 / 2 / 3 / 4 warps per scheduler (one warp = 32 loops), the filters of 4096 stations take
         // f ms on the whole device and scale with the SMs they are left with.  4096 stations, stereo + RDS: 32 / 116.
         int pll_sms = 0;
@@ -748,7 +748,7 @@ int fmrx_batch_create(const fmrx_config *cfg, fmrx_batch **out) {
             double best = 1e30;
             for (int p = 8; p <= 64 && p < sms; p += 8) {
                 const int w = (warps + 4 * p - 1) / (4 * p);
-                const double t_pll = w <= 1 ? 3.65 : w == 2 ? 4.6 : w == 3 ? 6.5 : w == 4 ? 8.7 : 2.2 * w;
+                const double t_pll = w <= 1 ? 3.2 : w == 2 ? 4.4 : w == 3 ? 6.1 : w == 4 ? 8.8 : 2.2 * w;
                 const double t = std::max(t_pll, f_ms * sms / (sms - p));
                 if (t < best * 0.98) { best = t; pll_sms = p; }   // ties go to the smaller partition
             }

@@ -55,10 +55,10 @@ __global__ void __launch_bounds__(32, 8) pll_kernel(PllSide A, PllSide B, long l
     if (V >= 1) {
         if (threadIdx.x < 16) theta[threadIdx.x] = pllmath::pll_theta_entry(threadIdx.x);
         if (threadIdx.x < pllmath::kPllKDoubles) kdoubles[threadIdx.x] = pllmath::pll_k_value(threadIdx.x);
-        __syncwarp();
+        __syncthreads();
     }
     const pllmath::PllK K = V >= 1 ? pllmath::pll_k_from(kdoubles, 0x38000000u) : pllmath::PllK{};
-    int lane = blockIdx.x * 32 + threadIdx.x;
+    int lane = blockIdx.x * blockDim.x + threadIdx.x;
     const PllSide &P = lane < n_streams ? A : B;
     if (lane >= n_streams) lane -= n_streams;
     if (lane >= n_streams || P.x == nullptr) return;
@@ -291,10 +291,11 @@ int launch_pll_blocks(const float *xa, float *ncoa, PllParams pa, float *sta, co
     PllSide A = make_side(xa, ncoa, sta, pa, mula, proda);
     PllSide B = xb ? make_side(xb, ncob, stb, pb, mulb, prodb) : PllSide{};
     const int lanes = xb ? 2 * n_streams : n_streams;
-    static const int variant = [] { const char *e = getenv("FMRX_PLL_STEP"); return e ? atoi(e) : 0; }();
-    if (variant == 0) pll_kernel<0><<<(lanes + 31) / 32, 32, 0, st>>>(A, B, ld, n_streams, n, n_blocks);
-    else if (variant == 2) pll_kernel<2><<<(lanes + 31) / 32, 32, 0, st>>>(A, B, ld, n_streams, n, n_blocks);
-    else pll_kernel<1><<<(lanes + 31) / 32, 32, 0, st>>>(A, B, ld, n_streams, n, n_blocks);
+    static const int variant = [] { const char *e = getenv("FMRX_PLL_STEP"); return e ? atoi(e) : 2; }();
+    const int cta = 32, grid = (lanes + cta - 1) / cta;  // one warp per CTA (64- and 128-thread CTAs measure the same: the block scheduler already spreads the warps over the schedulers)
+    if (variant == 0) pll_kernel<0><<<grid, cta, 0, st>>>(A, B, ld, n_streams, n, n_blocks);
+    else if (variant == 2) pll_kernel<2><<<grid, cta, 0, st>>>(A, B, ld, n_streams, n, n_blocks);
+    else pll_kernel<1><<<grid, cta, 0, st>>>(A, B, ld, n_streams, n, n_blocks);
     launch_counter() += 1;
     return (int)cudaGetLastError();
 }

@@ -213,6 +213,18 @@ FMRX_HD SinCos sincos_k(double T, const PllK &K) {
     return o;
 }
 
+// the bare MUFU.RCP (flush-to-zero form): __fdividef wraps it in a range check and two scalings that `ok` makes redundant -- a step
+// whose |x| is outside (1e-18, 1e18) is redone by libm whatever this returns
+FMRX_HD float rcp_bare(float x) {
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
+
 FMRX_HD float mul_rn(float a, float b) {
 #ifdef __CUDA_ARCH__
     return __fmul_rn(a, b);
@@ -419,7 +431,7 @@ FMRX_HD float pll_step_fast1(PllCarry &c, PllFast &f, const PllCoef &p, const Pl
     // `&`, not `&&`: one basic block.  x in (1e-18, 1e18) and |fbi|, |fbq| <= 1 bound eI, eQ from above; cnt = (offset + k) + 1
     // with an offset the caller has checked is plain once per block
     bool good = f.usable_p & (neg == f.neg) & (ax > 1e-18f) & (ax < 1e18f) & (fabsf(eI) >= 1.17549435e-38f) & (fabsf(eQ) >= 1.17549435e-38f);
-    const double rx = F2F_SIDE ? (double)rcp_approx(x) : widen(rcp_approx(x), K);
+    const double rx = F2F_SIDE ? (double)rcp_bare(x) : widen(rcp_bare(x), K);
     const double dI = widen(eI, K), dQ = widen(eQ, K);
     const double dot = fma_(dQ, -f.sn, dI * f.cs);
     const double cross = fma_(dQ, f.cs, dI * f.sn);
