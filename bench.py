@@ -53,7 +53,7 @@ STAGE_BYTES = {
 }
 
 
-PROFILE_TAG = "r4"  # profiles/<tag>_ncu_kernels.csv (tools/ncu_trim.py) and profiles/<tag>_sass_mix.json (tools/sass_mix.py)
+PROFILE_TAG = "r5"  # profiles/<tag>_ncu_kernels.csv (tools/ncu_trim.py) and profiles/<tag>_sass_mix.json (tools/sass_mix.py)
 # which kernel launches of one chain step make up a bench stage (names as tools/ncu_trim.py shortens them; in launch order)
 STAGE_KERNELS = {
     "frontend": ("frontend_stream4_kernel<1>", "frontend_edge_kernel<1>", "iq_state_kernel<1>"),
@@ -67,6 +67,8 @@ def ncu_profile():
     import csv
 
     path = os.path.join(ROOT, "profiles", f"{PROFILE_TAG}_ncu_kernels.csv")
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "profiles", "r4_ncu_kernels.csv")  # the previous capture (same kernels except the PLL step variant)
     out = {}
     if os.path.exists(path):
         for r in csv.DictReader(open(path)):
@@ -183,13 +185,22 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------------
 # the reference's CPU implementation, timed on the host cores (cpu_baseline leg and --impl reference)
 # ---------------------------------------------------------------------------------------------------------------------
+_CPU_SAMPLES = {}
+
+
+def _cpu_sample(n_blocks, mode):
+    if (n_blocks, mode) not in _CPU_SAMPLES:
+        from fmrx import synth
+
+        _CPU_SAMPLES[(n_blocks, mode)] = synth.synth_iq(n_blocks, mode, seed=1)
+    return _CPU_SAMPLES[(n_blocks, mode)]
+
+
 def cpu_reference_run(n_blocks, procs, mode=0):
     """P independent processes of the reference path over `n_blocks` blocks each.  Uses the unmodified reference
     executable (oracle/_ref/fm_radio, kind "reference") when it was built, else the oracle port's chain (kind "port").
     Returns (Msps aggregate, kind, seconds)."""
-    from fmrx import synth
-
-    raw = synth.synth_iq(n_blocks, mode, seed=1)
+    raw = _cpu_sample(n_blocks, mode)  # synthesised once per (length, mode): the reference arm calls this once per step
     ref_bin = os.path.join(ROOT, "oracle", "_ref", "fm_radio")
     tmpdir = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
     path = os.path.join(tmpdir, f"fmrx_bench_{os.getpid()}.raw")
@@ -818,7 +829,9 @@ def run_fmrx_arm(args, rank, world, local_rank):
     # ---- rooflines, every denominator measured in this run (MEASURED_PEAKS.json carries HBM and bf16-tensor peaks only)
     peak_ffma = fmrx.measure_fp32_peak(0, local_rank)      # T FMA/s  -> 2 flop each
     peak_muladd = fmrx.measure_fp32_peak(1, local_rank)    # T lane-ops/s, 1 flop each (the reference-exact tap)
-    rate_dfma = fmrx.measure_fp32_peak(4, local_rank)      # T DFMA/s
+    rate_dfma = fmrx.measure_fp32_peak(4, local_rank)      # T DFMA/s, multiplier and addend uniform (the form the microbenchmark of round 1 measured)
+    rate_dfma3 = fmrx.measure_fp32_peak(8, local_rank)     # T DFMA/s with three vector-register operands: what the PLL step's polynomials issue
+    rate_mixed = fmrx.measure_fp32_peak(7, local_rank)     # 4 DFMA + 2 conversions interleaved: the two pipes overlap (rate ~ the slower of the two alone)
     rate_cvt = fmrx.measure_fp32_peak(5, local_rank)       # T float<->double conversions/s
     rate_alu = fmrx.measure_fp32_peak(6, local_rank)       # T integer ALU lane-ops/s
     hbm_peak, hbm_src = measured_peaks()
@@ -872,7 +885,7 @@ def run_fmrx_arm(args, rank, world, local_rank):
         clk = peak_ffma * 1e12 / (sms_total * 128.0)                           # effective SM clock during the microbenchmarks, Hz (FFMA: 128 lanes per clock per SM)
         per_sched = lambda rate: rate * 1e12 / (sms_total * 4.0) / clk / 32.0  # noqa: E731  warp-instructions per cycle per scheduler on that pipe
         cyc = {"issue": mx["total"] / spi,
-               "fp64": mx.get("fp64", 0) / spi / per_sched(rate_dfma),
+               "fp64": mx.get("fp64", 0) / spi / per_sched(rate_dfma3),
                "xu": (mx.get("cvt", 0) + mx.get("mufu", 0)) / spi / per_sched(rate_cvt),
                "alu": mx.get("alu", 0) / spi / per_sched(rate_alu),
                "fma": (mx.get("fp32", 0) + mx.get("fp32_packed", 0)) / spi / per_sched(peak_ffma)}
@@ -895,7 +908,8 @@ def run_fmrx_arm(args, rank, world, local_rank):
                "scheduler_cycles_per_warp_step": round(t_used * 1e-3 * clk / steps_total / max(1, -(-warps // scheds)), 1),
                "bound_cycles_per_warp_step": round(bound_cyc, 1), "bound_by_pipe": {k: round(v, 1) for k, v in cyc.items()},
                "instructions_per_step": {k: round(v / spi, 2) for k, v in mx.items()}, "instruction_mix_source": mix_path,
-               "pipe_rates_tera_lane_ops": {"ffma": round(peak_ffma, 2), "dfma": round(rate_dfma, 2), "f2f": round(rate_cvt, 2), "alu": round(rate_alu, 2)},
+               "pipe_rates_tera_lane_ops": {"ffma": round(peak_ffma, 2), "dfma_uniform_operands": round(rate_dfma, 2), "dfma_three_registers": round(rate_dfma3, 2), "f2f": round(rate_cvt, 2),
+                                            "alu": round(rate_alu, 2), "dfma_and_f2f_interleaved_4_to_2": round(rate_mixed, 2)},
                "clock_hz_effective": round(clk), "alone_on_whole_device_ms": per["pll"]["ms_per_step"],
                "chain_latency_cycles": round(chain, 1), "latency_floor_ms": round(steps_total * chain / clk * 1e3, 3),
                "note": "alone on the whole device the kernel sits on its latency floor (one warp per scheduler at most: alone_on_whole_device_ms vs latency_floor_ms); "

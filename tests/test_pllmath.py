@@ -26,9 +26,19 @@ def test_sincos_within_two_ulp_and_float_identical(checker):
     assert r["float_flips"] == 0, r
 
 
-def test_loop_bit_identical_to_libm_loop(checker):
+@pytest.mark.parametrize("variant", [0, 1, 2], ids=["conversion instructions", "integer-built conversions", "same, theta0 from the staged table"])
+def test_loop_bit_identical_to_libm_loop(checker, variant):
     """8 loops (19 kHz x2 and 114 kHz x0.5; clean, weak, detuned+strong, noisy with exact zeros) x 12 blocks: every
-    carried float (integrator, phase estimate, feedback I/Q) and every NCO sample equal to the libm-only recurrence."""
-    r = json.loads(subprocess.check_output([checker, "loop", "12"]))
+    carried float (integrator, phase estimate, feedback I/Q) and every NCO sample equal to the libm-only recurrence.
+    Variant 0 is pll_step_fast, variants 1 / 2 pll_step_fast1 (what the kernel runs by default), the latter with the theta0
+    table staged as the kernel stages it in shared memory."""
+    r = json.loads(subprocess.check_output([checker, "loop", "12", str(variant)]))
     assert r["fast_steps"] > 0.99 * r["steps"], r   # the short-chain path is the one being exercised
     assert r["mismatches"] == 0, r
+
+
+def test_integer_built_widening_is_the_cast(checker):
+    """float -> double by re-packing the bits (pllmath::widen / widen_pos) equals the conversion for every normal finite float tried
+    (4 M random bit patterns inside the range `ok` admits, plus the edges of that range)."""
+    r = json.loads(subprocess.check_output([checker, "widen", "4000000"]))
+    assert r["bad"] == 0, r
