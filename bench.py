@@ -57,7 +57,7 @@ PROFILE_TAG = "r5"  # profiles/<tag>_ncu_kernels.csv (tools/ncu_trim.py) and pro
 # which kernel launches of one chain step make up a bench stage (names as tools/ncu_trim.py shortens them; in launch order)
 STAGE_KERNELS = {
     "frontend": ("frontend_stream4_kernel<1>", "frontend_edge_kernel<1>", "iq_state_kernel<1>"),
-    "pll": ("pll_kernel",), "combine": ("combine_kernel",), "rds_decode": ("rds_decode_kernel",),
+    "pll": ("pll_kernel",), "combine": ("combine4_kernel", "combine_kernel"), "rds_decode": ("rds_decode_kernel",),
     "rds_symbols": ("rds_symbol_kernel",), "bpf_fused": ("fir151_multi_kernel",),
 }
 

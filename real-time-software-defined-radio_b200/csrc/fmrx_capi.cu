@@ -748,7 +748,7 @@ int fmrx_batch_create(const fmrx_config *cfg, fmrx_batch **out) {
             double best = 1e30;
             for (int p = 8; p <= 64 && p < sms; p += 8) {
                 const int w = (warps + 4 * p - 1) / (4 * p);
-                const double t_pll = w <= 1 ? 3.2 : w == 2 ? 4.4 : w == 3 ? 6.1 : w == 4 ? 8.8 : 2.2 * w;
+                const double t_pll = w <= 1 ? 3.2 : w == 2 ? (p >= 32 ? 4.4 : 5.0) : w == 3 ? 6.1 : w == 4 ? 8.8 : 2.2 * w;  // two warps per scheduler on a 16-SM partition (mode 1's single loop): 4.9-5.0 measured
                 const double t = std::max(t_pll, f_ms * sms / (sms - p));
                 if (t < best * 0.98) { best = t; pll_sms = p; }   // ties go to the smaller partition
             }

@@ -43,7 +43,7 @@ def kernels(tag, note):
     rows = list(csv.reader(open(src)))
     h, units = rows[0], rows[1]
     idx = [(h.index(c), lab) for c, lab in COLS if c in h]
-    out = [f"# ncu `--set full --clock-control none` capture `{tag}` — one chain step, 4096 stations x 1 block (tools/prof_chain.py 4096 1)", ""]
+    out = [f"# ncu `--set full --clock-control none` capture `{tag}` — one steady-state chain step, 4096 stations x 1 block of the synthetic multiplex (tools/gpu_final.sh: third step of tools/prof_chain.py 4096 3)", ""]
     if note:
         out += [note, ""]
     out += ["Times are ncu's serialised, cold-cache per-launch durations (compare shares, not absolutes); DRAM bytes are per launch.", ""]
