@@ -76,19 +76,33 @@ def ncu_profile():
     return out, os.path.relpath(path, ROOT)
 
 
-def stage_traffic(prof, stage, fir_order):
-    """dram read + write bytes of the launches that make up `stage` in the committed capture (4096 stations x 1 block), or None"""
-    def tot(rows):
-        return sum(float(r["dram_read_bytes"]) + float(r["dram_write_bytes"]) for r in rows)
-
+def stage_rows(prof, stage, fir_order):
+    """the launches that make up `stage` in the committed capture (4096 stations x 1 block)"""
     if stage in STAGE_KERNELS:
-        rows = [r for k, v in prof.items() if any(k.startswith(p) for p in STAGE_KERNELS[stage]) for r in v]
-        return tot(rows) if rows else None
+        return [r for k, v in prof.items() if any(k.startswith(p) for p in STAGE_KERNELS[stage]) for r in v]
     if stage in fir_order:  # the FIR stages share one kernel template: identify the launch by its position among the fir151_kernel launches
         firs = sorted((r for k, v in prof.items() if k.startswith("fir151_kernel") for r in v), key=lambda r: int(r["launch"]))
         i = fir_order.index(stage)
-        return tot([firs[i]]) if i < len(firs) else None
-    return None
+        return [firs[i]] if i < len(firs) else []
+    return []
+
+
+def stage_traffic(prof, stage, fir_order):
+    """dram read + write bytes of those launches, or None"""
+    rows = stage_rows(prof, stage, fir_order)
+    return sum(float(r["dram_read_bytes"]) + float(r["dram_write_bytes"]) for r in rows) if rows else None
+
+
+def stage_pipes(prof, stage, fir_order):
+    """pipe utilisation of the stage's longest launch in the committed capture (ncu, % of peak while the SM is active): what the kernel is bound by"""
+    rows = stage_rows(prof, stage, fir_order)
+    if not rows:
+        return None
+    r = max(rows, key=lambda x: float(x["duration_ms"]))
+    keys = (("issue_active_pct", "issue"), ("pipe_fma_pct", "fma"), ("pipe_alu_pct", "alu"), ("pipe_fp64_pct", "fp64"), ("pipe_xu_pct", "xu"), ("pipe_lsu_pct", "lsu"))
+    out = {lab: round(float(r[k]), 1) for k, lab in keys if r.get(k) not in (None, "")}
+    out["busiest"] = max((k for k in out if k != "issue"), key=lambda k: out[k]) if len(out) > 1 else None
+    return out
 
 
 def sass_mix():
@@ -870,6 +884,7 @@ def run_fmrx_arm(args, rank, world, local_rank):
                                 "the *_survey_algorithmic pair counts the MACs of the three full-rate stages it replaces"})
         gbs = STAGE_BYTES[name] * S * B * args.steps / (ms * 1e-3) / 1e9
         tr = stage_traffic(prof, name, fir_order) if args.numerics == "reference" else None  # the committed capture is of the default numerics
+        ent["ncu_pipes_pct"] = stage_pipes(prof, name, fir_order) if args.numerics == "reference" else None
         ent.update({"hbm_gbs": round(gbs, 1), "frac_hbm": round(gbs / hbm_peak, 4), "algorithmic_bytes": STAGE_BYTES[name] * S * B,
                     "traffic": None if tr is None else round(tr * S * B / 4096.0), "traffic_over_algorithmic": None if tr is None else round(tr / (STAGE_BYTES[name] * 4096.0), 3)})
         per[name] = ent

@@ -191,7 +191,7 @@ __global__ void combine_kernel(const float *mono, const float *stereo, int16_t *
     if (i >= n_total) return;
     const float m = mono_delay == 0 ? mono[(long long)s * ld + i] : (i >= mono_delay ? mono[(long long)s * ld + i - mono_delay] : mono_tail[s * 16 + i]);
     const float t = stereo ? stereo[(long long)s * ld + i] : 0.0f;
-    const float l = __fdiv_rn(__fadd_rn(m, t), 2.0f), r = __fdiv_rn(__fsub_rn(m, t), 2.0f);
+    const float l = __fmul_rn(__fadd_rn(m, t), 0.5f), r = __fmul_rn(__fsub_rn(m, t), 0.5f);  // the `/2` of src/fm_radio.cpp:250-251: the same correctly rounded value, without the division sequence
     const long long o = ((long long)s * ld + i) * 2;
     if (audio_f) *reinterpret_cast<float2 *>(audio_f + o) = make_float2(l, r);
     if (audio) *reinterpret_cast<short2 *>(audio + o) = make_short2(quantise(l, mult), quantise(r, mult));
@@ -209,7 +209,7 @@ __global__ void combine4_kernel(const float *mono, const float *stereo, int16_t 
     const float mv[4] = {m.x, m.y, m.z, m.w}, tv[4] = {t.x, t.y, t.z, t.w};
     float l[4], r[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { l[i] = __fdiv_rn(__fadd_rn(mv[i], tv[i]), 2.0f); r[i] = __fdiv_rn(__fsub_rn(mv[i], tv[i]), 2.0f); }
+    for (int i = 0; i < 4; ++i) { l[i] = __fmul_rn(__fadd_rn(mv[i], tv[i]), 0.5f); r[i] = __fmul_rn(__fsub_rn(mv[i], tv[i]), 0.5f); }
     if (audio_f) {
         float4 *f = reinterpret_cast<float4 *>(audio_f + 2 * at);
         f[0] = make_float4(l[0], r[0], l[1], r[1]);
