@@ -309,14 +309,13 @@ FMRX_HD void pll_prepare(PllFast &f, const SinCos &v) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Variant 1 of the step (round 2): the same arithmetic with fewer instructions on the two half-rate pipes.  On its
-// partition the kernel is bound by instruction issue, and ncu shows the FP64 pipe and the conversion (XU) pipe taking
-// turns: 57.5 FP64 instructions at 2 scheduler-cycles and 16.75 conversions at 8 per step.  A float -> double
-// conversion of a NORMAL finite float is a re-packing of its bits (sign, exponent + 896, mantissa << 29) -- exact, and
-// three integer instructions on pipes the step leaves idle; `ok` already sends zero / non-finite values to the libm
-// path and now also anything outside [FLT_MIN, 1e30).  theta0 is prepared for the sign of the NEXT sample only (the
-// caller knows it: the input is in registers two groups ahead), with k * (pi/2) and k * (pi/2's tail) picked as bit
-// patterns (k is -2..2: the same mantissas, exponent + 1 for |k| = 2) instead of two int -> double conversions, two
+// Variants 1 and 2 of the step (round 2, second session): the same arithmetic with fewer conversion and FP64 instructions and
+// a shorter dependency chain (488 -> 412 cycles per step for one warp alone; DESIGN 3.4 for what it does and does not buy on
+// the partition).  A float -> double conversion of a NORMAL finite float is a re-packing of its bits (sign, exponent + 896,
+// mantissa << 29) -- exact, three integer instructions and a shift instead of an F2F.F64.F32 on the 16-lane conversion pipe;
+// `ok` already sends zero / non-finite values to the libm path and now also anything outside [FLT_MIN, 1e30).  theta0 is
+// prepared for the sign of the NEXT sample only (the caller knows it: the input is in registers two groups ahead), with
+// k * (pi/2) and k * (pi/2's tail) read from a 16-entry table (k is -2..2) instead of two int -> double conversions, two
 // multiplies and one of the two FMAs; a wrong prediction is caught in `ok` (f.neg) and costs one libm group.
 // ---------------------------------------------------------------------------------------------------------------
 FMRX_HD unsigned float_bits(float v) {
