@@ -92,7 +92,10 @@ __global__ void __launch_bounds__(256) rds_phase_kernel(const FastDev a) {
     }
 }
 
-__global__ void __launch_bounds__(256) rds_symbol_kernel(const FastDev a) {
+// Ten warps per CTA: the 19 filter phases are dealt out two to a warp (one warp takes one).  With eight warps three of them took three
+// phases and the CTA waited for those: 0.199 ms per 4096-station step.
+constexpr int SYM_NT = 320;
+__global__ void __launch_bounds__(SYM_NT) rds_symbol_kernel(const FastDev a) {
     extern __shared__ __align__(16) float ps[];  // ZPAD zeros | NIF products of this block | ELEN edge products of the previous one
     float *pz = ps + ZPAD, *pw = ps + ZPAD + NIF;
     const int b = blockIdx.x, s = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -103,13 +106,13 @@ __global__ void __launch_bounds__(256) rds_symbol_kernel(const FastDev a) {
     const bool aligned = ((uintptr_t)pb & 15) == 0;
     if (aligned) {
         const unsigned sbase = (unsigned)__cvta_generic_to_shared(pz);
-        for (int i = threadIdx.x; i < NIF / 4; i += 256) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + 16u * i), "l"(pb + 4 * i) : "memory");
+        for (int i = threadIdx.x; i < NIF / 4; i += SYM_NT) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + 16u * i), "l"(pb + 4 * i) : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
     } else {
-        for (int i = threadIdx.x; i < NIF; i += 256) pz[i] = pb[i];
+        for (int i = threadIdx.x; i < NIF; i += SYM_NT) pz[i] = pb[i];
     }
-    for (int i = threadIdx.x; i < ZPAD; i += 256) ps[i] = 0.0f;
-    for (int m = threadIdx.x; m < ELEN; m += 256) {
+    for (int i = threadIdx.x; i < ZPAD; i += SYM_NT) ps[i] = 0.0f;
+    for (int m = threadIdx.x; m < ELEN; m += SYM_NT) {
         float v = 0.0f;
         if (m < EN) {
             const int src = m < AN ? A0 + m : B0 + (m - AN);
@@ -120,7 +123,7 @@ __global__ void __launch_bounds__(256) rds_symbol_kernel(const FastDev a) {
     if (aligned) asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     const bool dense = a.first_block_is_zero && b == 0;  // the decoder re-derives the sampling phase from rrc[0..23] of block 0
-    for (int phi = warp; phi < U; phi += 8) {
+    for (int phi = warp; phi < U; phi += SYM_NT / 32) {
         float w[WLEN / 32];
 #pragma unroll
         for (int i = 0; i < WLEN / 32; ++i) w[i] = __ldg(a.W + phi * WLEN + 32 * i + lane);
@@ -148,7 +151,7 @@ __global__ void __launch_bounds__(256) rds_symbol_kernel(const FastDev a) {
     // the carried state for the next call: the edge products of the LAST block of this one.  Written by the CTA that read the old
     // state (block 0's, after the barrier above), so no other CTA of this launch races with it.
     const float *pl = a.p + (long long)s * a.ld + (long long)(a.n_blocks - 1) * NIF;
-    for (int m = threadIdx.x; m < EN; m += 256) ed[m] = pl[m < AN ? A0 + m : B0 + (m - AN)];
+    for (int m = threadIdx.x; m < EN; m += SYM_NT) ed[m] = pl[m < AN ? A0 + m : B0 + (m - AN)];
 }
 
 struct Tables {
@@ -237,7 +240,7 @@ int launch_rds_fast(const RdsFastJob &j, fmrx_stream_t st) {
     const int smem = (ZPAD + NIF + ELEN) * (int)sizeof(float);
     // per device (per context), so set on every launch: a process may hold handles on several GPUs (fmrx_config.device)
     if (cudaError_t e0 = cudaFuncSetAttribute(rds_symbol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) return (int)e0;
-    rds_symbol_kernel<<<dim3(j.n_blocks, j.n_streams), 256, smem, st>>>(d);
+    rds_symbol_kernel<<<dim3(j.n_blocks, j.n_streams), SYM_NT, smem, st>>>(d);
     launch_counter() += 1;
     return (int)cudaGetLastError();
 }
