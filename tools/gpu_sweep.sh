@@ -1,6 +1,6 @@
 #!/bin/bash
 # device-resident bench under a list of environment settings, one line each:
-#   bash tools/gpu_sweep.sh <tag> "FMRX_PLL_STEP=2 FMRX_PLL_CTA=128" "FMRX_PLL_SMS=22 ..." ...
+#   bash tools/gpu_sweep.sh <tag> "FMRX_PLL_STEP=0" "FMRX_PLL_STEP=2 FMRX_PLL_SMS=24" ...
 TAG=$1; shift
 OUT=gpurun_out; mkdir -p $OUT
 for envs in "$@"; do
